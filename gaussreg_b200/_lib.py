@@ -1,0 +1,67 @@
+"""ctypes loader for the in-tree sm_100a library (include/gaussreg_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or the call fails, the
+caller gets a RuntimeError.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgaussreg_b200.so")
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+_f32 = ctypes.c_float
+_sz = ctypes.c_size_t
+
+_SIGNATURES = {
+    "gr_version": (ctypes.c_char_p, []),
+    "gr_last_error": (ctypes.c_char_p, []),
+    "gr_launch_count": (_i64, []),
+    "gr_grid_subsample_workspace_size": (_sz, [_i64, _i32]),
+    "gr_grid_subsample": (_i32, [_vp, _vp, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_radius_neighbors_workspace_size": (_sz, [_i64, _i64, _i32]),
+    "gr_radius_neighbors": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+}
+
+_STATUS = {-1: "bad argument", -2: "workspace too small", -3: "capacity overflow", -4: "CUDA error"}
+
+
+def exported_symbols():
+    """Every symbol include/gaussreg_b200.h declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def register(name, restype, argtypes):
+    _SIGNATURES[name] = (restype, argtypes)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m gaussreg_b200.build` "
+                "(gaussreg_b200 has no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = _STATUS.get(status, f"status {status}")
+        detail = lib().gr_last_error().decode() if status == -4 else ""
+        raise RuntimeError(f"gaussreg_b200.{what} failed: {msg} {detail}".strip())
+
+
+def launch_count():
+    return int(lib().gr_launch_count())

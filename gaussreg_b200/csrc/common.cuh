@@ -1,0 +1,99 @@
+// Shared helpers for the gaussreg_b200 sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gaussreg_b200.h"
+
+#define GR_STR_(x) #x
+#define GR_STR(x) GR_STR_(x)
+
+namespace gr {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_last_error(const char* what, cudaError_t e);
+void count_launch(int n = 1);
+
+#define GR_CHECK_LAUNCH(name)                                 \
+  do {                                                        \
+    ::gr::count_launch();                                     \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) {                                 \
+      ::gr::set_last_error(name, e__);                        \
+      return GR_ERR_CUDA;                                     \
+    }                                                         \
+  } while (0)
+
+#define GR_CHECK_CUDA(expr)                                   \
+  do {                                                        \
+    cudaError_t e__ = (expr);                                 \
+    if (e__ != cudaSuccess) {                                 \
+      ::gr::set_last_error(#expr, e__);                       \
+      return GR_ERR_CUDA;                                     \
+    }                                                         \
+  } while (0)
+
+// ---- workspace carving ----------------------------------------------------------------------
+struct Carver {
+  char* base;
+  size_t off;
+  size_t cap;
+  bool ok;
+  __host__ Carver(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes), ok(true) {}
+  template <typename T>
+  __host__ T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    if (base != nullptr && off > cap) ok = false;
+    return r;
+  }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// order-preserving float <-> uint mapping (for atomicMin/Max on floats)
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int o) {
+  unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// largest b with off[b] <= i, off has nb+1 ascending entries (off[0] = 0)
+__device__ __forceinline__ int find_segment(const int* __restrict__ off, int nb, int i) {
+  int lo = 0, hi = nb;  // invariant: off[lo] <= i < off[hi] (caller guarantees i < off[nb])
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace gr

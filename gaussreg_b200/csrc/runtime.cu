@@ -1,0 +1,19 @@
+// Library-level bookkeeping: version string, last-error text, launch counter.
+#include <atomic>
+#include <string>
+
+#include "common.cuh"
+
+namespace gr {
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_last_error(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace gr
+
+extern "C" const char* gr_version(void) { return "gaussreg_b200 0.1 (sm_100a, CUDA " GR_STR(__CUDACC_VER_MAJOR__) "." GR_STR(__CUDACC_VER_MINOR__) ")"; }
+extern "C" const char* gr_last_error(void) { return gr::g_last_error.c_str(); }
+extern "C" int64_t gr_launch_count(void) { return gr::g_launches.load(std::memory_order_relaxed); }

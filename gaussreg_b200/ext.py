@@ -1,0 +1,137 @@
+"""Drop-in for the reference's native module ``geotransformer.ext`` (geotransformer/extensions/pybind.cpp:6-18).
+
+Same two functions, same argument meaning, same dtype/contiguity checks and RuntimeError behaviour
+(geotransformer/extensions/common/torch_helper.h:6-35) -- but the work runs on the current CUDA
+device through the C ABI in include/gaussreg_b200.h.  Tensors may live on the CPU (the reference's
+convention: they are moved to the current CUDA device and the results are returned on the CPU) or
+already on the GPU (results stay there).  There is no CPU implementation behind this module.
+
+`install_as_geotransformer_ext()` registers this module under the name the reference's
+`geotransformer/modules/ops/{grid_subsample,radius_search}.py` import.
+"""
+import sys
+
+import torch
+
+from . import _lib
+
+
+def _check(t, name, dtype, what):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {what} tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("gaussreg_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, dev):
+    """Grow-only scratch buffer per device (stream-ordered reuse on the current stream)."""
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+def grid_subsample_device(points, lengths, voxel_size, n_points=None):
+    """Sync-free core: returns (out_points[capacity n], out_lengths, out_total) all on the device.
+
+    ``points`` may hold more rows than sum(lengths); only the first sum(lengths) are used.
+    """
+    L = _lib.lib()
+    dev = points.device
+    n = points.shape[0] if n_points is None else int(n_points)
+    batch = lengths.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_len = torch.empty((batch,), dtype=torch.int64, device=dev)
+    out_total = torch.empty((1,), dtype=torch.int64, device=dev)
+    nbytes = L.gr_grid_subsample_workspace_size(n, batch)
+    ws = _workspace(nbytes, dev)
+    st = L.gr_grid_subsample(points.data_ptr(), lengths.data_ptr(), batch, n, float(voxel_size), out.data_ptr(),
+                             out_len.data_ptr(), out_total.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "grid_subsample")
+    return out, out_len, out_total
+
+
+def grid_subsampling(points, lengths, voxel_size):
+    """ext.grid_subsampling(points (N,3) f32, lengths (B,) i64, voxel_size) -> [s_points (M,3), s_lengths (B,)]"""
+    _check(points, "points", torch.float32, "a float")
+    _check(lengths, "lengths", torch.int64, "an long")
+    src_dev = points.device
+    dev = src_dev if src_dev.type == "cuda" else _device()
+    p = points.to(dev, non_blocking=True)
+    l = lengths.to(dev, non_blocking=True)
+    if p.shape[0] == 0:
+        return [points.new_zeros((0, 3)), torch.zeros_like(lengths)]
+    with torch.cuda.device(dev):
+        out, out_len, out_total = grid_subsample_device(p, l, voxel_size)
+        m = int(out_total.item())  # the reference API returns a data-dependent shape
+    s_points = out[:m]
+    if src_dev.type != "cuda":
+        return [s_points.cpu(), out_len.cpu()]
+    return [s_points.contiguous() if m != out.shape[0] else s_points, out_len]
+
+
+def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None):
+    """Sync-free core: fills a (Nq, ld) int64 table (first min(count, ld) sorted neighbours per row,
+    padded with Ns) and returns (table, max_count device scalar)."""
+    L = _lib.lib()
+    dev = q_points.device
+    nq, ns, batch = q_points.shape[0], s_points.shape[0], q_lengths.shape[0]
+    max_count = torch.empty((1,), dtype=torch.int32, device=dev)
+    if out is None and ld > 0:
+        out = torch.empty((nq, ld), dtype=torch.int64, device=dev)
+    nbytes = L.gr_radius_neighbors_workspace_size(nq, ns, batch)
+    ws = _workspace(nbytes, dev)
+    st = L.gr_radius_neighbors(q_points.data_ptr(), s_points.data_ptr(), q_lengths.data_ptr(), s_lengths.data_ptr(),
+                               batch, nq, ns, float(radius), out.data_ptr() if out is not None else None,
+                               int(ld), max_count.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "radius_neighbors")
+    return out, max_count
+
+
+def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius):
+    """ext.radius_neighbors(q (N,3), s (M,3), q_lengths, s_lengths, radius) -> (N, max_count) i64, padded with M"""
+    _check(q_points, "q_points", torch.float32, "a float")
+    _check(s_points, "s_points", torch.float32, "a float")
+    _check(q_lengths, "q_lengths", torch.int64, "an long")
+    _check(s_lengths, "s_lengths", torch.int64, "an long")
+    src_dev = q_points.device
+    dev = src_dev if src_dev.type == "cuda" else _device()
+    q = q_points.to(dev, non_blocking=True)
+    s = s_points.to(dev, non_blocking=True)
+    ql = q_lengths.to(dev, non_blocking=True)
+    sl = s_lengths.to(dev, non_blocking=True)
+    with torch.cuda.device(dev):
+        _, max_count = radius_neighbors_device(q, s, ql, sl, radius, 0)  # count pass
+        w = int(max_count.item())
+        if w == 0 or q.shape[0] == 0:
+            out = torch.empty((q.shape[0], w), dtype=torch.int64, device=dev)
+        else:
+            out, _ = radius_neighbors_device(q, s, ql, sl, radius, w)
+    return out.cpu() if src_dev.type != "cuda" else out
+
+
+def install_as_geotransformer_ext():
+    """Make ``importlib.import_module('geotransformer.ext')`` resolve to this module."""
+    mod = sys.modules[__name__]
+    sys.modules["geotransformer.ext"] = mod
+    parent = sys.modules.get("geotransformer")
+    if parent is not None:
+        setattr(parent, "ext", mod)
+    return mod
