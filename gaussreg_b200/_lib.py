@@ -25,6 +25,31 @@ _SIGNATURES = {
     "gr_grid_subsample": (_i32, [_vp, _vp, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_radius_neighbors_workspace_size": (_sz, [_i64, _i64, _i32]),
     "gr_radius_neighbors": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "gr_gemm": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
+                       _vp, _i64, _i64, _i32, _vp]),
+    "gr_kpconv_aggregate_workspace_size": (_sz, [_i64]),
+    "gr_kpconv_aggregate": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "gr_group_norm_workspace_size": (_sz, [_i64, _i32]),
+    "gr_group_norm": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "gr_layer_norm_add": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "gr_maxpool": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "gr_upsample_concat": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "gr_gather_rows": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "gr_point_to_node_workspace_size": (_sz, [_i64, _i64]),
+    "gr_point_to_node_partition": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_embedding_indices": (_i32, [_vp, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "gr_sinusoid_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "gr_embedding_combine": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),
+    "gr_l2_normalize_rows": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),
+    "gr_superpoint_matching_workspace_size": (_sz, [_i32, _i32, _i32]),
+    "gr_superpoint_matching": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_sinkhorn": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "gr_lgr_workspace_size": (_sz, [_i32, _i32, _i32]),
+    "gr_local_global_registration": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _f32, _i32, _i32,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_weighted_procrustes": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
 }
 
 _STATUS = {-1: "bad argument", -2: "workspace too small", -3: "capacity overflow", -4: "CUDA error"}

@@ -1,0 +1,177 @@
+// fp32 GEMM with fused epilogue (SIMT FFMA path).
+//
+//   C[b] = act( alpha * A[b] * op(B[b]) / row_div[:,None] + bias[None,:] + residual[b] )
+//
+// A is (M,K) row-major with leading dimension lda; B is either (N,K) row-major ("NT": torch Linear
+// weights, Q K^T) or (K,N) row-major ("NN": KPConv weights, P V).  Batched through element strides, so
+// "b n (h c)" head slices are addressed without copies.  fp32 accumulate in K order: this is the
+// selection-safe path (top-k / argmin steps follow most of these products, SURVEY.md section 7 hard
+// part 2); the tcgen05 3xTF32 path for the large products lives in gemm_tc.cu.
+#include "common.cuh"
+
+namespace gr {
+
+struct GemmParams {
+  const float* A; const float* B; float* C;
+  const float* bias; const float* row_div; const float* residual;
+  long long lda, ldb, ldc, ldr;
+  long long sA, sB, sC, sR;  // batch strides (elements)
+  int M, N, K;
+  float alpha;
+  int act;  // 0 none, 1 relu, 2 leaky relu 0.1
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : 0.1f * v;
+  return v;
+}
+
+template <int BM, int BN, int BK, int TM, int TN, bool TRANSB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+  float* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
+
+  // global -> register staging, one element per (thread, step)
+  constexpr int A_ELEMS = BM * BK / NT;
+  constexpr int B_ELEMS = BN * BK / NT;
+  float ra[A_ELEMS], rb[B_ELEMS];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_ELEMS; ++i) {
+      const int e = tid + i * NT;          // consecutive threads walk K first (K-contiguous rows)
+      const int kk = e % BK, mm = e / BK;
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < p.M && gk < p.K) ? A[(long long)gm * p.lda + gk] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < B_ELEMS; ++i) {
+      const int e = tid + i * NT;
+      if (TRANSB) {
+        const int kk = e % BK, nn = e / BK;
+        const int gn = n0 + nn, gk = k0 + kk;
+        rb[i] = (gn < p.N && gk < p.K) ? B[(long long)gn * p.ldb + gk] : 0.f;
+      } else {
+        const int nn = e % BN, kk = e / BN;  // N-contiguous rows
+        const int gn = n0 + nn, gk = k0 + kk;
+        rb[i] = (gn < p.N && gk < p.K) ? B[(long long)gk * p.ldb + gn] : 0.f;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_ELEMS; ++i) {
+      const int e = tid + i * NT;
+      As[buf][e % BK][e / BK] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B_ELEMS; ++i) {
+      const int e = tid + i * NT;
+      if (TRANSB) Bs[buf][e % BK][e / BK] = rb[i];
+      else Bs[buf][e / BN][e % BN] = rb[i];
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) load_tiles((t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
+        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= p.M) continue;
+    const float rd = p.row_div ? p.row_div[gm] : 1.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= p.N) continue;
+      float v = acc[i][j] * p.alpha;
+      if (p.row_div) v = v / rd;
+      if (p.bias) v += p.bias[gn];
+      if (R) v += R[(long long)gm * p.ldr + gn];
+      C[(long long)gm * p.ldc + gn] = apply_act(v, p.act);
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+static int launch_sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
+  constexpr int NT = (BM / TM) * (BN / TN);
+  if (transb) sgemm_kernel<BM, BN, BK, TM, TN, true><<<grid, NT, 0, st>>>(p);
+  else sgemm_kernel<BM, BN, BK, TM, TN, false><<<grid, NT, 0, st>>>(p);
+  GR_CHECK_LAUNCH("sgemm_kernel");
+  return GR_OK;
+}
+
+int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || batch <= 0) return GR_OK;
+  // pick the largest tile that still yields at least ~1.5 waves of CTAs on 148 SMs
+  const long long ctas128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * batch;
+  const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
+  if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
+  if (ctas64 >= 148 || p.M > 32) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
+  return launch_sgemm<32, 32, 8, 4, 4>(p, batch, transb, st);
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
+                       int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
+                       const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
+                       int act, void* stream) {
+  if (M < 0 || N < 0 || K < 0 || batch < 0 || act < 0 || act > 2) return GR_ERR_BAD_ARG;
+  if (M == 0 || N == 0 || batch == 0) return GR_OK;
+  if (!A || !B || !C) return GR_ERR_BAD_ARG;
+  GemmParams p;
+  p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr;
+  p.sA = strideA; p.sB = strideB; p.sC = strideC; p.sR = strideR;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
+  return sgemm(p, batch, trans_b != 0, static_cast<cudaStream_t>(stream));
+}

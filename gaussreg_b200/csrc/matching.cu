@@ -1,0 +1,251 @@
+// M1: superpoint matching (geotransformer/modules/geotransformer/superpoint_matching.py:13-50) and
+// S1: log-domain Sinkhorn with learnable dustbin (modules/sinkhorn/learnable_sinkhorn.py:5-66).
+#include "common.cuh"
+
+namespace gr {
+
+// ---------------------------------------------------------------------------------------------
+// M1
+// ---------------------------------------------------------------------------------------------
+
+// S[i,j] = mask ? exp(-max(2 - 2 xy, 0)) : 0 (in place on xy); rowsum[i] in fixed order (warp per row)
+__global__ void __launch_bounds__(256) match_exp_rows_kernel(float* __restrict__ S, int Nr, int Ns,
+                                                             const unsigned char* __restrict__ rmask,
+                                                             const unsigned char* __restrict__ smask, float* __restrict__ rowsum) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= Nr) return;
+  const int lane = threadIdx.x & 31;
+  const bool rv = rmask[i] != 0;
+  float s = 0.f;
+  for (int j = lane; j < Ns; j += 32) {
+    float v = 0.f;
+    if (rv && smask[j]) v = expf(-fmaxf(2.0f - 2.0f * S[(long long)i * Ns + j], 0.0f));
+    S[(long long)i * Ns + j] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) rowsum[i] = s;
+}
+
+__global__ void __launch_bounds__(256) match_colsum_kernel(const float* __restrict__ S, int Nr, int Ns, float* __restrict__ colsum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Ns) return;
+  float s = 0.f;
+  for (int i = 0; i < Nr; ++i) s += S[(long long)i * Ns + j];
+  colsum[j] = s;
+}
+
+// key = (score bits << 32) | ~flat  -> descending key order == descending score, ascending flat index
+__global__ void __launch_bounds__(256) match_keys_kernel(const float* __restrict__ S, int Nr, int Ns,
+                                                         const float* __restrict__ rowsum, const float* __restrict__ colsum,
+                                                         const unsigned char* __restrict__ rmask, const unsigned char* __restrict__ smask,
+                                                         int dual, unsigned long long* __restrict__ keys, int* __restrict__ n_valid) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    int a = 0, b = 0;
+    for (int i = 0; i < Nr; ++i) a += rmask[i] != 0;
+    for (int j = 0; j < Ns; ++j) b += smask[j] != 0;
+    *n_valid = a * b > 0 ? (int)min((long long)a * b, (long long)0x7fffffff) : 0;
+  }
+  if (t >= (long long)Nr * Ns) return;
+  const int i = (int)(t / Ns), j = (int)(t % Ns);
+  unsigned long long key = 0ull;
+  if (rmask[i] && smask[j]) {
+    const float v = S[t];
+    const float sc = dual ? (v / rowsum[i]) * (v / colsum[j]) : v;
+    key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)t);
+    if (key == 0ull) key = 1ull;
+  }
+  keys[t] = key;
+}
+
+constexpr int kTopChunk = 2048;
+
+// each CTA sorts a chunk of 2048 keys (descending) in shared memory and keeps the first `keep`
+__global__ void __launch_bounds__(1024) topk_chunk_kernel(const unsigned long long* __restrict__ in, long long n, int keep,
+                                                          unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long sh[kTopChunk];
+  const long long base = (long long)blockIdx.x * kTopChunk;
+  for (int i = threadIdx.x; i < kTopChunk; i += blockDim.x) sh[i] = (base + i < n) ? in[base + i] : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= kTopChunk; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < kTopChunk / 2; t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = sh[lo], b = sh[hi];
+        if ((a < b) == desc) { sh[lo] = b; sh[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < keep; i += blockDim.x) out[(long long)blockIdx.x * keep + i] = sh[i];
+}
+
+__global__ void match_decode_kernel(const unsigned long long* __restrict__ keys, int k, int Ns, const int* __restrict__ n_valid,
+                                    long long* __restrict__ ref_idx, long long* __restrict__ src_idx, float* __restrict__ scores,
+                                    int* __restrict__ count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = min(k, *n_valid);
+  if (t == 0) *count = c;
+  if (t >= k) return;
+  if (t < c) {
+    const unsigned long long key = keys[t];
+    const unsigned int flat = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+    ref_idx[t] = flat / Ns;
+    src_idx[t] = flat % Ns;
+    scores[t] = __uint_as_float((unsigned int)(key >> 32));
+  } else {
+    ref_idx[t] = 0; src_idx[t] = 0; scores[t] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// S1
+// ---------------------------------------------------------------------------------------------
+
+// one CTA per patch pair; the (K+1)x(K+1) padded score matrix stays in shared memory for all iterations
+__global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+                                                       const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
+                                                       int K, int iters, float inf, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int K1 = K + 1;
+  float* ps = sm;               // K1*K1
+  float* u = ps + K1 * K1;      // K1
+  float* v = u + K1;            // K1
+  float* lmu = v + K1;          // K1
+  float* lnu = lmu + K1;        // K1
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const unsigned char* rm = row_masks + (long long)b * K;
+  const unsigned char* cm = col_masks + (long long)b * K;
+  const float alpha = *alpha_p;
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  {
+    int a = 0, c = 0;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { a += rm[i] != 0; c += cm[i] != 0; }
+    a = warp_sum(a); c = warp_sum(c);
+    if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], c); }
+  }
+  for (int t = threadIdx.x; t < K1 * K1; t += blockDim.x) {
+    const int i = t / K1, j = t % K1;
+    const bool masked = (i < K && !rm[i]) || (j < K && !cm[j]);
+    float val = (i < K && j < K) ? scores[((long long)b * K + i) * K + j] : alpha;
+    ps[t] = masked ? -inf : val;
+  }
+  __syncthreads();
+  const float nvr = (float)s_cnt[0], nvc = (float)s_cnt[1];
+  const float norm = -logf(nvr + nvc);
+  for (int i = threadIdx.x; i < K1; i += blockDim.x) {
+    float mu = i < K ? norm : logf(nvc) + norm;
+    float nu = i < K ? norm : logf(nvr) + norm;
+    if (i < K && !rm[i]) mu = -inf;
+    if (i < K && !cm[i]) nu = -inf;
+    lmu[i] = mu; lnu[i] = nu; u[i] = 0.f; v[i] = 0.f;
+  }
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+    // u_i = log_mu_i - logsumexp_j(ps_ij + v_j)
+    for (int i = warp; i < K1; i += nwarp) {
+      float mx = -INFINITY;
+      for (int j = lane; j < K1; j += 32) mx = fmaxf(mx, ps[i * K1 + j] + v[j]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int j = lane; j < K1; j += 32) s += expf(ps[i * K1 + j] + v[j] - mx);
+      s = warp_sum(s);
+      if (lane == 0) u[i] = lmu[i] - (logf(s) + mx);
+    }
+    __syncthreads();
+    // v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
+    for (int j = warp; j < K1; j += nwarp) {
+      float mx = -INFINITY;
+      for (int i = lane; i < K1; i += 32) mx = fmaxf(mx, ps[i * K1 + j] + u[i]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int i = lane; i < K1; i += 32) s += expf(ps[i * K1 + j] + u[i] - mx);
+      s = warp_sum(s);
+      if (lane == 0) v[j] = lnu[j] - (logf(s) + mx);
+    }
+    __syncthreads();
+  }
+  float* o = out + (long long)b * K1 * K1;
+  for (int t = threadIdx.x; t < K1 * K1; t += blockDim.x) {
+    const int i = t / K1, j = t % K1;
+    o[t] = (ps[t] + u[i] + v[j]) - norm;
+  }
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+extern "C" size_t gr_superpoint_matching_workspace_size(int Nr, int Ns, int k) {
+  Carver c(nullptr, 0);
+  c.take<float>(Nr);
+  c.take<float>(Ns);
+  const long long n = (long long)Nr * Ns;
+  c.take<unsigned long long>(n);
+  long long m = n;
+  while (m > kTopChunk) { m = ((m + kTopChunk - 1) / kTopChunk) * k; c.take<unsigned long long>(m); }
+  c.take<unsigned long long>(k);
+  c.take<int>(4);
+  return c.off;
+}
+
+/* M1.  xy: (Nr,Ns) f32 = ref_feats . src_feats^T, overwritten.  Outputs k entries (padded with 0 beyond *count). */
+extern "C" int gr_superpoint_matching(float* xy, int Nr, int Ns, const uint8_t* ref_masks, const uint8_t* src_masks, int k,
+                                      int dual_normalization, int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* count,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  if (Nr <= 0 || Ns <= 0 || k <= 0 || k > 1024 || (long long)Nr * Ns >= (1ll << 32)) return GR_ERR_BAD_ARG;
+  if (!xy || !ref_masks || !src_masks || !ref_idx || !src_idx || !scores || !count) return GR_ERR_BAD_ARG;
+  Carver c(ws, ws_bytes);
+  float* rowsum = c.take<float>(Nr);
+  float* colsum = c.take<float>(Ns);
+  const long long n = (long long)Nr * Ns;
+  unsigned long long* keys = c.take<unsigned long long>(n);
+  unsigned long long* level[8];
+  long long level_n[8];
+  int nl = 0;
+  long long m = n;
+  while (m > kTopChunk) { m = ((m + kTopChunk - 1) / kTopChunk) * k; level[nl] = c.take<unsigned long long>(m); level_n[nl] = m; ++nl; }
+  unsigned long long* fin = c.take<unsigned long long>(k);
+  int* n_valid = c.take<int>(4);
+  if (!ws || !c.ok) return GR_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  match_exp_rows_kernel<<<ceil_div(Nr, 8), 256, 0, st>>>(xy, Nr, Ns, ref_masks, src_masks, rowsum);
+  GR_CHECK_LAUNCH("match_exp_rows_kernel");
+  match_colsum_kernel<<<ceil_div(Ns, 256), 256, 0, st>>>(xy, Nr, Ns, colsum);
+  GR_CHECK_LAUNCH("match_colsum_kernel");
+  match_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xy, Nr, Ns, rowsum, colsum, ref_masks, src_masks, dual_normalization, keys, n_valid);
+  GR_CHECK_LAUNCH("match_keys_kernel");
+  const unsigned long long* cur = keys;
+  long long cur_n = n;
+  for (int l = 0; l < nl; ++l) {
+    topk_chunk_kernel<<<ceil_div(cur_n, kTopChunk), 1024, 0, st>>>(cur, cur_n, k, level[l]);
+    GR_CHECK_LAUNCH("topk_chunk_kernel");
+    cur = level[l]; cur_n = level_n[l];
+  }
+  topk_chunk_kernel<<<1, 1024, 0, st>>>(cur, cur_n, k, fin);
+  GR_CHECK_LAUNCH("topk_chunk_kernel");
+  match_decode_kernel<<<ceil_div(k, 256), 256, 0, st>>>(fin, k, Ns, n_valid, reinterpret_cast<long long*>(ref_idx),
+                                                        reinterpret_cast<long long*>(src_idx), scores, count);
+  GR_CHECK_LAUNCH("match_decode_kernel");
+  return GR_OK;
+}
+
+/* S1.  scores (P,K,K), masks (P,K) u8 (1 = valid), alpha device scalar -> out (P,K+1,K+1). */
+extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_t* col_masks, const float* alpha, int P,
+                           int K, int num_iterations, float inf, float* out, void* stream) {
+  if (P < 0 || K <= 0 || num_iterations < 0) return GR_ERR_BAD_ARG;
+  if (P == 0) return GR_OK;
+  if (!scores || !row_masks || !col_masks || !alpha || !out) return GR_ERR_BAD_ARG;
+  const size_t smem = ((size_t)(K + 1) * (K + 1) + 4 * (size_t)(K + 1)) * sizeof(float);
+  if (smem > 220 * 1024) return GR_ERR_CAPACITY;
+  if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sinkhorn_kernel<<<P, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K, num_iterations, inf, out);
+  GR_CHECK_LAUNCH("sinkhorn_kernel");
+  return GR_OK;
+}

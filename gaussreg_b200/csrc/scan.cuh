@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in,
+static __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in,
                                                                     uint32_t* __restrict__ tile_sums, int64_t n) {
   __shared__ uint32_t sh[8];
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_
 }
 
 // single CTA: exclusive scan of tile_sums[0..m) in place
-__global__ void __launch_bounds__(kScanThreads) scan_tilesums_kernel(uint32_t* __restrict__ tile_sums, int m) {
+static __global__ void __launch_bounds__(kScanThreads) scan_tilesums_kernel(uint32_t* __restrict__ tile_sums, int m) {
   __shared__ uint32_t sh[9];
   uint32_t carry = 0;
   for (int base = 0; base < m; base += kScanThreads) {
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tilesums_kernel(uint32_t* _
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_final_kernel(const uint32_t* in, uint32_t* out,
+static __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(const uint32_t* in, uint32_t* out,
                                                                    const uint32_t* __restrict__ tile_sums, int64_t n) {
   __shared__ uint32_t sh[9];
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanItems;

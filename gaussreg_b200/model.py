@@ -1,0 +1,114 @@
+"""GeoTransformer coarse-registration model, eval forward
+(reference: experiments/geotransformer.gaussian_splatting.indoor/model.py:19-227).
+
+Differences from the reference, by design:
+  * forward-only (the `if self.training` branches of model.py:74,111,165 are out of scope);
+  * `estimated_transform` is the deterministic LocalGlobalRegistration result; the reference then
+    overwrites it with Open3D RANSAC (model.py:209-215: third-party, randomised, CPU) -- not reproduced;
+  * the random init below consumes the torch / numpy RNG streams exactly like the reference, so
+    `torch.manual_seed(s); np.random.seed(s); create_model(cfg)` yields the reference's weights
+    (checked against tests/golden/weights_checksum.npz).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import (KPConvFPN, GeometricTransformer, SuperPointMatching, LocalGlobalRegistration,
+                      LearnableLogOptimalTransport)
+
+
+class GeoTransformer(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.num_points_in_patch = cfg.model.num_points_in_patch
+        self.matching_radius = cfg.model.ground_truth_matching_radius
+        b = cfg.backbone
+        self.backbone = KPConvFPN(b.input_dim, b.output_dim, b.init_dim, b.kernel_size, b.init_radius, b.init_sigma, b.group_norm)
+        g = cfg.geotransformer
+        self.transformer = GeometricTransformer(g.input_dim, g.output_dim, g.hidden_dim, g.num_heads, g.blocks, g.sigma_d,
+                                                g.sigma_a, g.angle_k, reduction_a=g.reduction_a)
+        cm = cfg.coarse_matching
+        self.coarse_matching = SuperPointMatching(cm.num_correspondences, cm.dual_normalization)
+        f = cfg.fine_matching
+        self.fine_matching = LocalGlobalRegistration(
+            f.topk, f.acceptance_radius, mutual=f.mutual, confidence_threshold=f.confidence_threshold,
+            use_dustbin=f.use_dustbin, use_global_score=f.use_global_score,
+            correspondence_threshold=f.correspondence_threshold, correspondence_limit=f.correspondence_limit,
+            num_refinement_steps=f.num_refinement_steps)
+        self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+
+    @torch.no_grad()
+    def forward(self, data_dict):
+        if self.training:
+            raise RuntimeError("gaussreg_b200 implements the eval forward only: call model.eval()")
+        out = {}
+        feats = data_dict["features"]
+        lengths = data_dict["lengths"]
+        # stage lengths are needed on the host to slice ref / src (model.py:77-79 does three .item() syncs)
+        lens = torch.stack([lengths[-1], lengths[1], lengths[0]]).cpu()
+        ref_length_c, ref_length_f, ref_length = int(lens[0, 0]), int(lens[1, 0]), int(lens[2, 0])
+        points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
+        ref_points_c, src_points_c = points_c[:ref_length_c], points_c[ref_length_c:]
+        ref_points_f, src_points_f = points_f[:ref_length_f], points_f[ref_length_f:]
+        out["ref_points_c"], out["src_points_c"] = ref_points_c, src_points_c
+        out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
+        out["ref_points"], out["src_points"] = points[:ref_length], points[ref_length:]
+
+        # 1. point-to-node partition (model.py:99-109)
+        K = self.num_points_in_patch
+        _, ref_node_masks, ref_node_knn_indices, ref_node_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, K)
+        _, src_node_masks, src_node_knn_indices, src_node_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, K)
+
+        # 2. KPConv FPN (model.py:129-132)
+        feats_list = self.backbone(feats, data_dict)
+        feats_c, feats_f = feats_list[-1], feats_list[0]
+
+        # 3. geometric transformer (model.py:135-147)
+        ref_feats_c, src_feats_c = self.transformer(ref_points_c, src_points_c, feats_c[:ref_length_c], feats_c[ref_length_c:])
+        ref_feats_c_norm = ops.l2_normalize_rows(ref_feats_c)
+        src_feats_c_norm = ops.l2_normalize_rows(src_feats_c)
+        out["ref_feats_c"], out["src_feats_c"] = ref_feats_c_norm, src_feats_c_norm
+        ref_feats_f, src_feats_f = feats_f[:ref_length_f], feats_f[ref_length_f:]
+        out["ref_feats_f"], out["src_feats_f"] = ref_feats_f, src_feats_f
+
+        # 6. superpoint correspondences (model.py:156-163)
+        ref_ci, src_ci, node_corr_scores = self.coarse_matching(ref_feats_c_norm, src_feats_c_norm, ref_node_masks, src_node_masks)
+        out["ref_node_corr_indices"], out["src_node_corr_indices"] = ref_ci, src_ci
+        out["node_corr_scores"] = node_corr_scores
+
+        # 7.2 patch gathers (model.py:171-186)
+        P = ref_ci.shape[0]
+        ref_knn_idx = ops_gather_index(ref_node_knn_indices, ref_ci)
+        src_knn_idx = ops_gather_index(src_node_knn_indices, src_ci)
+        ref_knn_masks = ref_knn_idx != ref_points_f.shape[0]
+        src_knn_masks = src_knn_idx != src_points_f.shape[0]
+        ref_knn_points = ops.gather_rows(ref_points_f, ref_knn_idx)
+        src_knn_points = ops.gather_rows(src_points_f, src_knn_idx)
+        ref_knn_feats = ops.gather_rows(ref_feats_f, ref_knn_idx)
+        src_knn_feats = ops.gather_rows(src_feats_f, src_knn_idx)
+        out["ref_node_corr_knn_points"], out["src_node_corr_knn_points"] = ref_knn_points, src_knn_points
+        out["ref_node_corr_knn_masks"], out["src_node_corr_knn_masks"] = ref_knn_masks, src_knn_masks
+
+        # 8. optimal transport (model.py:189-193)
+        C = feats_f.shape[1]
+        scores = torch.empty((P, K, K), dtype=torch.float32, device=feats.device)
+        ops.gemm_batched(ref_knn_feats.data_ptr(), C, K * C, src_knn_feats.data_ptr(), C, K * C, True, scores.data_ptr(), K,
+                         K * K, K, K, C, P, alpha=1.0 / C ** 0.5)
+        matching_scores = self.optimal_transport(scores, ref_knn_masks, src_knn_masks)
+        out["matching_scores"] = matching_scores
+
+        # 9. local-to-global registration (model.py:196-207); the dustbin row/col is skipped inside the kernel
+        ref_corr, src_corr, corr_scores, T = self.fine_matching(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks,
+                                                                matching_scores, node_corr_scores)
+        out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_corr, src_corr, corr_scores
+        out["estimated_transform"] = T
+        return out
+
+
+def ops_gather_index(table, rows):
+    """table[rows] for an int64 (M,K) table: a row gather (model.py:171-172); knn masks follow from the sentinel."""
+    return table.index_select(0, rows)
+
+
+def create_model(config):
+    return GeoTransformer(config)

@@ -1,0 +1,52 @@
+"""KPConvFPN (reference: experiments/geotransformer.gaussian_splatting.indoor/backbone.py:95-212)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .kpconv import ConvBlock, ResidualBlock, UnaryBlock, LastUnaryBlock
+
+
+class KPConvFPN(nn.Module):
+    def __init__(self, input_dim, output_dim, init_dim, kernel_size, init_radius, init_sigma, group_norm):
+        super().__init__()
+        d, r, s, g, k = init_dim, init_radius, init_sigma, group_norm, kernel_size
+        self.encoder1_1 = ConvBlock(input_dim, d, k, r, s, g)
+        self.encoder1_2 = ResidualBlock(d, d * 2, k, r, s, g)
+        self.encoder2_1 = ResidualBlock(d * 2, d * 2, k, r, s, g, strided=True)
+        self.encoder2_2 = ResidualBlock(d * 2, d * 4, k, r * 2, s * 2, g)
+        self.encoder2_3 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, g)
+        self.encoder3_1 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, g, strided=True)
+        self.encoder3_2 = ResidualBlock(d * 4, d * 8, k, r * 4, s * 4, g)
+        self.encoder3_3 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, g)
+        self.encoder4_1 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, g, strided=True)
+        self.encoder4_2 = ResidualBlock(d * 8, d * 16, k, r * 8, s * 8, g)
+        self.encoder4_3 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, g)
+        self.encoder5_1 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, g, strided=True)
+        self.encoder5_2 = ResidualBlock(d * 16, d * 32, k, r * 16, s * 16, g)
+        self.encoder5_3 = ResidualBlock(d * 32, d * 32, k, r * 16, s * 16, g)
+        self.decoder4 = UnaryBlock(d * 48, d * 16, g)
+        self.decoder3 = UnaryBlock(d * 24, d * 8, g)
+        self.decoder2 = LastUnaryBlock(d * 12, output_dim)
+
+    @torch.no_grad()
+    def forward(self, feats, data_dict):
+        P, NB = data_dict["points"], data_dict["neighbors"]
+        SUB, UP = data_dict["subsampling"], data_dict["upsampling"]
+        f1 = self.encoder1_1(feats, P[0], P[0], NB[0])
+        f1 = self.encoder1_2(f1, P[0], P[0], NB[0])
+        f2 = self.encoder2_1(f1, P[1], P[0], SUB[0])
+        f2 = self.encoder2_2(f2, P[1], P[1], NB[1])
+        f2 = self.encoder2_3(f2, P[1], P[1], NB[1])
+        f3 = self.encoder3_1(f2, P[2], P[1], SUB[1])
+        f3 = self.encoder3_2(f3, P[2], P[2], NB[2])
+        f3 = self.encoder3_3(f3, P[2], P[2], NB[2])
+        f4 = self.encoder4_1(f3, P[3], P[2], SUB[2])
+        f4 = self.encoder4_2(f4, P[3], P[3], NB[3])
+        f4 = self.encoder4_3(f4, P[3], P[3], NB[3])
+        f5 = self.encoder5_1(f4, P[4], P[3], SUB[3])
+        f5 = self.encoder5_2(f5, P[4], P[4], NB[4])
+        f5 = self.encoder5_3(f5, P[4], P[4], NB[4])
+        l4 = self.decoder4(ops.upsample_concat(f5, UP[3], f4))
+        l3 = self.decoder3(ops.upsample_concat(l4, UP[2], f3))
+        l2 = self.decoder2(ops.upsample_concat(l3, UP[1], f2))
+        return [l2, l3, l4, f5]

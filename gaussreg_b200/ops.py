@@ -1,0 +1,309 @@
+"""Functional front-ends of the C ABI (include/gaussreg_b200.h) on torch CUDA tensors.
+
+PyTorch is used for device memory and the current stream only; every function below launches the
+library's own sm_100a kernels and raises RuntimeError if the call fails.  Mirrors
+geotransformer/modules/ops/*.py where the reference has an equivalent.
+"""
+import torch
+
+from . import _lib
+from .ext import _stream, _workspace, radius_neighbors_device, grid_subsample_device  # noqa: F401
+
+_F32 = torch.float32
+
+
+def _req(t, dtype=_F32):
+    if not t.is_cuda:
+        raise RuntimeError("gaussreg_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _u8(mask):
+    """bool / uint8 mask tensor -> contiguous uint8 view (no copy for bool)."""
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return _req(mask, torch.uint8)
+
+
+ACT = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2}
+
+
+def gemm(a, b, trans_b=True, bias=None, alpha=1.0, row_div=None, residual=None, act=None, out=None):
+    """2-D product with fused epilogue.  a (M,K); b (N,K) if trans_b else (K,N).  Rows of a / b / out may be
+    strided views (last dim contiguous)."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    assert (b.shape[1] if trans_b else b.shape[0]) == K
+    if out is None:
+        out = torch.empty((M, N), dtype=_F32, device=a.device)
+    assert out.stride(1) == 1
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.stride(1) == 1
+    st = _lib.lib().gr_gemm(a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 0, int(trans_b), out.data_ptr(),
+                            out.stride(0), 0, M, N, K, 1, float(alpha), _ptr(bias), _ptr(row_div), _ptr(residual),
+                            residual.stride(0) if residual is not None else 0, 0, ACT[act], _stream())
+    _lib.check(st, "gemm")
+    return out
+
+
+def gemm_batched(a_ptr, lda, sa, b_ptr, ldb, sb, trans_b, c_ptr, ldc, sc, M, N, K, batch, alpha=1.0, bias=None):
+    """Raw strided-batched product (pointers + element strides); used for per-head attention products."""
+    st = _lib.lib().gr_gemm(a_ptr, lda, sa, b_ptr, ldb, sb, int(trans_b), c_ptr, ldc, sc, M, N, K, batch, float(alpha),
+                            _ptr(bias), None, None, 0, 0, 0, _stream())
+    _lib.check(st, "gemm_batched")
+
+
+def linear(x, weight, bias=None, act=None, residual=None, out=None):
+    """nn.Linear forward: x (rows, in) @ weight (out, in)^T + bias."""
+    return gemm(x, weight, True, bias=bias, act=act, residual=residual, out=out)
+
+
+def kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_points, sigma):
+    """K1 first half -> (A (M, 15*C), row_div (M))."""
+    s_feats, q_points, s_points = _req(s_feats), _req(q_points), _req(s_points)
+    kernel_points = _req(kernel_points)
+    assert neighbor_indices.dtype == torch.int64 and neighbor_indices.stride(1) == 1
+    M, H = neighbor_indices.shape
+    Ns, C = s_feats.shape
+    L = _lib.lib()
+    A = torch.empty((M, kernel_points.shape[0] * C), dtype=_F32, device=s_feats.device)
+    row_div = torch.empty((M,), dtype=_F32, device=s_feats.device)
+    ws = _workspace(L.gr_kpconv_aggregate_workspace_size(Ns), s_feats.device)
+    st = L.gr_kpconv_aggregate(s_feats.data_ptr(), C, q_points.data_ptr(), s_points.data_ptr(), neighbor_indices.data_ptr(),
+                               H, neighbor_indices.stride(0), M, Ns, kernel_points.data_ptr(), kernel_points.shape[0],
+                               float(sigma), A.data_ptr(), row_div.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "kpconv_aggregate")
+    return A, row_div
+
+
+def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_points, sigma):
+    """KPConv.forward (kpconv.py:79-122): (M, C_out)."""
+    A, row_div = kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_points, sigma)
+    K, C, Co = weights.shape
+    return gemm(A, weights.view(K * C, Co), False, bias=bias, row_div=row_div)
+
+
+def group_norm(x, groups, gamma, beta, eps=1e-5, add=None, act=None, out=None):
+    x = _req(x)
+    n, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    if add is not None:
+        add = _req(add)
+    L = _lib.lib()
+    ws = _workspace(L.gr_group_norm_workspace_size(n, groups), x.device)
+    st = L.gr_group_norm(x.data_ptr(), n, C, groups, gamma.data_ptr(), beta.data_ptr(), float(eps), _ptr(add), ACT[act],
+                         out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "group_norm")
+    return out
+
+
+def layer_norm_add(a, b, gamma, beta, eps=1e-5):
+    a = _req(a)
+    if b is not None:
+        b = _req(b)
+    out = torch.empty_like(a)
+    st = _lib.lib().gr_layer_norm_add(a.data_ptr(), _ptr(b), a.shape[0], a.shape[1], gamma.data_ptr(), beta.data_ptr(),
+                                      float(eps), out.data_ptr(), _stream())
+    _lib.check(st, "layer_norm_add")
+    return out
+
+
+def maxpool(x, neighbor_indices):
+    """kpconv/functional.py:54-67."""
+    x = _req(x)
+    assert neighbor_indices.dtype == torch.int64 and neighbor_indices.stride(1) == 1
+    M, H = neighbor_indices.shape
+    out = torch.empty((M, x.shape[1]), dtype=_F32, device=x.device)
+    st = _lib.lib().gr_maxpool(x.data_ptr(), x.shape[0], x.shape[1], neighbor_indices.data_ptr(), H,
+                               neighbor_indices.stride(0), M, out.data_ptr(), _stream())
+    _lib.check(st, "maxpool")
+    return out
+
+
+def upsample_concat(coarse, upsample_indices, skip):
+    """cat([nearest_upsample(coarse, idx), skip], dim=1) (functional.py:6-22, backbone.py:195-197)."""
+    coarse, skip = _req(coarse), _req(skip)
+    assert upsample_indices.dtype == torch.int64
+    M = upsample_indices.shape[0]
+    out = torch.empty((M, coarse.shape[1] + skip.shape[1]), dtype=_F32, device=coarse.device)
+    st = _lib.lib().gr_upsample_concat(coarse.data_ptr(), coarse.shape[0], coarse.shape[1], upsample_indices.data_ptr(),
+                                       upsample_indices.stride(0), skip.data_ptr(), skip.shape[1], M, out.data_ptr(), _stream())
+    _lib.check(st, "upsample_concat")
+    return out
+
+
+def nearest_upsample(x, upsample_indices):
+    """functional.py:6-22."""
+    idx = upsample_indices[:, 0].contiguous()
+    return gather_rows(x, idx)
+
+
+def gather_rows(x, index):
+    """index_select(cat([x, 0]), index, dim=0) for an index of any shape; rows >= len(x) read as zeros."""
+    x = _req(x.view(x.shape[0], -1))
+    index = _req(index, torch.int64)
+    rows = index.numel()
+    out = torch.empty((rows, x.shape[1]), dtype=_F32, device=x.device)
+    st = _lib.lib().gr_gather_rows(x.data_ptr(), x.shape[0], x.shape[1], index.data_ptr(), rows, out.data_ptr(), _stream())
+    _lib.check(st, "gather_rows")
+    return out.view(*index.shape, x.shape[1])
+
+
+def point_to_node_partition(points, nodes, point_limit):
+    """modules/ops/pointcloud_partition.py:61-111 -> (point_to_node i64, node_masks bool, knn_indices i64, knn_masks bool)."""
+    points, nodes = _req(points), _req(nodes)
+    N, M = points.shape[0], nodes.shape[0]
+    dev = points.device
+    p2n = torch.empty((N,), dtype=torch.int32, device=dev)
+    node_masks = torch.empty((M,), dtype=torch.uint8, device=dev)
+    knn_idx = torch.empty((M, point_limit), dtype=torch.int64, device=dev)
+    knn_masks = torch.empty((M, point_limit), dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.gr_point_to_node_workspace_size(N, M), dev)
+    st = L.gr_point_to_node_partition(points.data_ptr(), N, nodes.data_ptr(), M, point_limit, p2n.data_ptr(),
+                                      node_masks.data_ptr(), knn_idx.data_ptr(), knn_masks.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _stream())
+    _lib.check(st, "point_to_node_partition")
+    return p2n.long(), node_masks.view(torch.bool), knn_idx, knn_masks.view(torch.bool)
+
+
+def embedding_indices(points, sigma_d, sigma_a, angle_k):
+    points = _req(points)
+    N = points.shape[0]
+    dev = points.device
+    d_idx = torch.empty((N, N), dtype=_F32, device=dev)
+    a_idx = torch.empty((N, N, angle_k), dtype=_F32, device=dev)
+    knn = torch.empty((N, angle_k), dtype=torch.int32, device=dev)
+    st = _lib.lib().gr_embedding_indices(points.data_ptr(), N, float(sigma_d), float(sigma_a), angle_k, d_idx.data_ptr(),
+                                         a_idx.data_ptr(), knn.data_ptr(), _stream())
+    _lib.check(st, "embedding_indices")
+    return d_idx, a_idx, knn
+
+
+def sinusoid_rows(x, div_term, out=None):
+    x = _req(x)
+    rows = x.numel()
+    if out is None:
+        out = torch.empty((rows, 2 * div_term.numel()), dtype=_F32, device=x.device)
+    st = _lib.lib().gr_sinusoid_rows(x.data_ptr(), rows, div_term.data_ptr(), div_term.numel(), out.data_ptr(), _stream())
+    _lib.check(st, "sinusoid_rows")
+    return out
+
+
+def embedding_combine(D, A, k, out):
+    st = _lib.lib().gr_embedding_combine(D.data_ptr(), A.data_ptr(), D.shape[0], D.shape[1], k, out.data_ptr(), _stream())
+    _lib.check(st, "embedding_combine")
+    return out
+
+
+def rpe_attention_probs(q, k, U, qb, emb, num_heads):
+    N, C = q.shape
+    P = torch.empty((num_heads, N, N), dtype=_F32, device=q.device)
+    st = _lib.lib().gr_rpe_attention_probs(q.data_ptr(), k.data_ptr(), U.data_ptr(), qb.data_ptr(), emb.data_ptr(), N, C,
+                                           num_heads, P.data_ptr(), _stream())
+    _lib.check(st, "rpe_attention_probs")
+    return P
+
+
+def softmax_rows_(x):
+    x2 = x.view(-1, x.shape[-1])
+    st = _lib.lib().gr_softmax_rows(x2.data_ptr(), x2.shape[0], x2.shape[1], _stream())
+    _lib.check(st, "softmax_rows")
+    return x
+
+
+def l2_normalize_rows(x, eps=1e-12):
+    x = _req(x)
+    out = torch.empty_like(x)
+    st = _lib.lib().gr_l2_normalize_rows(x.data_ptr(), x.shape[0], x.shape[1], float(eps), out.data_ptr(), _stream())
+    _lib.check(st, "l2_normalize_rows")
+    return out
+
+
+def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, k, dual_normalization=True):
+    """superpoint_matching.py:13-50 -> (ref_idx (k) i64, src_idx (k) i64, scores (k), count device i32)."""
+    ref_feats, src_feats = _req(ref_feats), _req(src_feats)
+    Nr, Ns = ref_feats.shape[0], src_feats.shape[0]
+    dev = ref_feats.device
+    xy = gemm(ref_feats, src_feats, True)
+    ref_idx = torch.empty((k,), dtype=torch.int64, device=dev)
+    src_idx = torch.empty((k,), dtype=torch.int64, device=dev)
+    scores = torch.empty((k,), dtype=_F32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.gr_superpoint_matching_workspace_size(Nr, Ns, k), dev)
+    st = L.gr_superpoint_matching(xy.data_ptr(), Nr, Ns, _u8(ref_masks).data_ptr(), _u8(src_masks).data_ptr(), k,
+                                  int(dual_normalization), ref_idx.data_ptr(), src_idx.data_ptr(), scores.data_ptr(),
+                                  count.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "superpoint_matching")
+    return ref_idx, src_idx, scores, count
+
+
+def sinkhorn(scores, row_masks, col_masks, alpha, num_iterations, inf=1e12):
+    """learnable_sinkhorn.py:20-66: (P,K,K) -> (P,K+1,K+1)."""
+    scores = _req(scores)
+    P, K, K2 = scores.shape
+    assert K == K2
+    out = torch.empty((P, K + 1, K + 1), dtype=_F32, device=scores.device)
+    rm, cm = _u8(row_masks), _u8(col_masks)
+    alpha = alpha.detach().reshape(1)
+    st = _lib.lib().gr_sinkhorn(scores.data_ptr(), rm.data_ptr(), cm.data_ptr(), alpha.data_ptr(), P, K, num_iterations,
+                                float(inf), out.data_ptr(), _stream())
+    _lib.check(st, "sinkhorn")
+    return out
+
+
+def local_global_registration(matching_scores, ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, topk,
+                              acceptance_radius, mutual, confidence_threshold, correspondence_threshold, num_refinement_steps):
+    """local_global_registration.py:196-235 -> (ref_corr (cap,3), src_corr (cap,3), scores (cap), num_corr i32[1], T (4,4))."""
+    ms = _req(matching_scores)
+    P, ld, _ = ms.shape
+    K = ref_knn_points.shape[1]
+    dev = ms.device
+    cap = P * K * topk
+    ref_corr = torch.empty((cap, 3), dtype=_F32, device=dev)
+    src_corr = torch.empty((cap, 3), dtype=_F32, device=dev)
+    scores = torch.empty((cap,), dtype=_F32, device=dev)
+    num = torch.empty((1,), dtype=torch.int32, device=dev)
+    T = torch.empty((4, 4), dtype=_F32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.gr_lgr_workspace_size(P, K, topk), dev)
+    st = L.gr_local_global_registration(ms.data_ptr(), P, K, ld, _req(ref_knn_points).data_ptr(), _req(src_knn_points).data_ptr(),
+                                        _u8(ref_knn_masks).data_ptr(), _u8(src_knn_masks).data_ptr(), topk,
+                                        float(acceptance_radius), int(mutual), float(confidence_threshold),
+                                        int(correspondence_threshold), int(num_refinement_steps), ref_corr.data_ptr(),
+                                        src_corr.data_ptr(), scores.data_ptr(), num.data_ptr(), T.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream())
+    _lib.check(st, "local_global_registration")
+    return ref_corr, src_corr, scores, num, T
+
+
+def weighted_procrustes(src_points, ref_points, weights, eps=1e-5):
+    """procrustes.py:6-82 with return_transform=True."""
+    squeeze = src_points.dim() == 2
+    if squeeze:
+        src_points, ref_points, weights = src_points[None], ref_points[None], weights[None]
+    src_points, ref_points, weights = _req(src_points), _req(ref_points), _req(weights)
+    B, n = weights.shape
+    T = torch.empty((B, 4, 4), dtype=_F32, device=src_points.device)
+    st = _lib.lib().gr_weighted_procrustes(src_points.data_ptr(), ref_points.data_ptr(), weights.data_ptr(), B, n, float(eps),
+                                           T.data_ptr(), _stream())
+    _lib.check(st, "weighted_procrustes")
+    return T[0] if squeeze else T
+
+
+def apply_transform(points, transform):
+    """modules/ops/transformation.py:7-60 for (*,3) points and a (4,4) transform (3x3 product through gr_gemm)."""
+    shape = points.shape
+    p = _req(points.reshape(-1, 3))
+    R = transform[:3, :3].contiguous()
+    t = transform[:3, 3].contiguous()
+    return gemm(p, R, True, bias=t).view(shape)

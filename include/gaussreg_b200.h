@@ -79,6 +79,87 @@ int gr_radius_neighbors(const float* q_points, const float* s_points, const int6
                         const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius, int64_t* out_idx,
                         int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense fp32 product with fused epilogue (used by K1 contraction, K2 Linear, T1-T3 projections,
+ * attention products, M1/M2 similarity).  Replaces the ATen/cuBLAS calls behind nn.Linear
+ * (kpconv/modules.py:73,98), torch.matmul (kpconv.py:105,109), torch.einsum (model.py:189,
+ * rpe_transformer.py:56-57, vanilla_transformer.py:55).
+ *   C[b] = act(alpha * A[b] . op(B[b]) / row_div[:,None] + bias[None,:] + residual[b])
+ *   A (M,K) ld lda; B (N,K) if trans_b else (K,N); batch strides in elements; act 0 none 1 relu 2 leaky(0.1).
+ * --------------------------------------------------------------------------------------------- */
+int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB, int trans_b,
+            float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha, const float* bias,
+            const float* row_div, const float* residual, int64_t ldr, int64_t strideR, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  KPConv gather + kernel-point correlation (geotransformer/modules/kpconv/kpconv.py:79-122).
+ *   A[m, k*C + c] = sum_h max(0, 1 - |(s_h - q_m) - kp_k| / sigma) * s_feats[idx[m,h], c]
+ *   row_div[m]    = max(1, #{h : sum_c s_feats[idx[m,h], c] > 0})
+ * The contraction with weights (15*C, C_out) and the /row_div + bias epilogue are one gr_gemm call.
+ * --------------------------------------------------------------------------------------------- */
+size_t gr_kpconv_aggregate_workspace_size(int64_t n_support);
+int gr_kpconv_aggregate(const float* s_feats, int C, const float* q_points, const float* s_points,
+                        const int64_t* neighbor_idx, int H, int64_t ld_idx, int M, int Ns, const float* kernel_points,
+                        int n_kernel_points, float sigma, float* A, float* row_div, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* K2  GroupNorm over all rows of the stacked pair (kpconv/modules.py:33-50) + optional add + activation. */
+size_t gr_group_norm_workspace_size(int64_t n_rows, int groups);
+int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, const float* gamma, const float* beta, float eps,
+                  const float* add, int act, float* y, void* ws, size_t ws_bytes, void* stream);
+/* T2/T3  y = LayerNorm(a + b) (rpe_transformer.py:101-103, output_layer.py:14-21); b may be NULL. */
+int gr_layer_norm_add(const float* a, const float* b, int64_t rows, int C, const float* gamma, const float* beta,
+                      float eps, float* y, void* stream);
+
+/* K3  neighbourhood max-pool (kpconv/functional.py:54-67), nearest-upsample + skip concat
+ * (functional.py:6-22, backbone.py:195-208), zero-padded row gather (modules/ops/index_select.py). */
+int gr_maxpool(const float* x, int Ns, int C, const int64_t* idx, int H, int64_t ld_idx, int M, float* out, void* stream);
+int gr_upsample_concat(const float* coarse, int Nc, int C1, const int64_t* idx, int64_t ld_idx, const float* skip,
+                       int C2, int M, float* out, void* stream);
+int gr_gather_rows(const float* x, int n, int C, const int64_t* idx, int64_t rows, float* out, void* stream);
+
+/* P1  point-to-node partition (modules/ops/pointcloud_partition.py:61-111). */
+size_t gr_point_to_node_workspace_size(int64_t n_points, int64_t n_nodes);
+int gr_point_to_node_partition(const float* points, int N, const float* nodes, int M, int point_limit,
+                               int32_t* point_to_node, uint8_t* node_masks, int64_t* knn_indices, uint8_t* knn_masks,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/* T1  geometric structure embedding pieces (modules/geotransformer/geotransformer.py:26-72,
+ * modules/transformer/positional_embedding.py:19-35). */
+int gr_embedding_indices(const float* points, int N, float sigma_d, float sigma_a, int angle_k, float* d_idx, float* a_idx,
+                         int32_t* knn, void* stream);
+int gr_sinusoid_rows(const float* x, int64_t rows, const float* div_term, int n_div, float* E, void* stream);
+int gr_embedding_combine(const float* D, const float* A, int64_t rows, int C, int k, float* out, void* stream);
+
+/* T2  RPE attention probabilities with the p-term reassociated (rpe_transformer.py:50-66), row softmax
+ * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */
+int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,
+                           int num_heads, float* P, void* stream);
+int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
+int gr_l2_normalize_rows(const float* x, int64_t rows, int C, float eps, float* y, void* stream);
+
+/* M1  superpoint matching (modules/geotransformer/superpoint_matching.py:13-50). */
+size_t gr_superpoint_matching_workspace_size(int Nr, int Ns, int k);
+int gr_superpoint_matching(float* xy, int Nr, int Ns, const uint8_t* ref_masks, const uint8_t* src_masks, int k,
+                           int dual_normalization, int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* count,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* S1  log-domain Sinkhorn with learnable dustbin (modules/sinkhorn/learnable_sinkhorn.py:5-66). */
+int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_t* col_masks, const float* alpha, int P, int K,
+                int num_iterations, float inf, float* out, void* stream);
+
+/* L1  local-to-global registration (modules/geotransformer/local_global_registration.py:11-235) and
+ * L2  weighted Procrustes (modules/registration/procrustes.py:6-82), SVD on the device. */
+size_t gr_lgr_workspace_size(int P, int K, int topk);
+int gr_local_global_registration(const float* matching_scores, int P, int K, int ld, const float* ref_knn_points,
+                                 const float* src_knn_points, const uint8_t* ref_knn_masks, const uint8_t* src_knn_masks,
+                                 int topk, float acceptance_radius, int mutual, float confidence_threshold,
+                                 int correspondence_threshold, int num_refinement_steps, float* ref_corr_points,
+                                 float* src_corr_points, float* corr_scores, int32_t* num_corr, float* transform, void* ws,
+                                 size_t ws_bytes, void* stream);
+int gr_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int B, int n, float eps,
+                           float* transforms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ def read_disposition_ply(path):
         lines = header.decode().splitlines()
         n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
         props = [l.split()[1] for l in lines if l.startswith("property")]
-        fmt = {"double": "d", "float": "f"}
+        fmt = {"double": "d", "float64": "d", "float": "f", "float32": "f"}
         rec = struct.Struct("<" + "".join(fmt[p] for p in props))
         data = [rec.unpack(f.read(rec.size)) for _ in range(n)]
     return np.asarray(data, dtype=np.float64)[:, :3]
