@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) angle_index_kernel(const float* __restric
   const float cy = __fsub_rn(__fmul_rn(rz, ax), __fmul_rn(rx, az));
   const float cz = __fsub_rn(__fmul_rn(rx, ay), __fmul_rn(ry, ax));
   const float sinv = sqrtf(sq_norm3f(cx, cy, cz));
-  const float cosv = __fadd_rn(__fadd_rn(__fmul_rn(rx, ax), __fmul_rn(ry, ay)), __fmul_rn(rz, az));
+  // torch.sum starts from +0: (+0) + (-0) = +0, so a zero anchor vector gives atan2(0, +0) = 0 (not pi)
+  const float cosv = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(rx, ax)), __fmul_rn(ry, ay)), __fmul_rn(rz, az));
   a_idx[t] = __fmul_rn(atan2f(sinv, cosv), factor_a);
 }
 

@@ -14,7 +14,9 @@ constexpr int kLgrThreads = 128;
 
 // ---- 3x3 SVD based weighted Kabsch --------------------------------------------------------------
 // H = sum_i w_i (s_i - sc)(r_i - rc)^T ;  R = V diag(1,1,det(V U^T)) U^T ;  t = rc - R sc
-__device__ void kabsch_from_H(const double H[9], const double sc[3], const double rc[3], float T[12]) {
+// __noinline__ on purpose: inlined into the single-thread branch of block_procrustes, nvcc 12.9 -O3 produced
+// wrong rotations for 128-thread CTAs (verified on B200; the same source is correct on the host and out of line).
+__device__ __noinline__ void kabsch_from_H(const double H[9], const double sc[3], const double rc[3], float T[12]) {
   double A[9], V[9];
   for (int i = 0; i < 9; ++i) { A[i] = H[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
   for (int sweep = 0; sweep < 30; ++sweep) {
@@ -126,6 +128,10 @@ __device__ void block_procrustes(const float* __restrict__ src, const float* __r
   for (int k = 0; k < 9; ++k) H[k] = block_sum_double(h[k], sh);
   if (threadIdx.x == 0) {
     const double sc[3] = {(double)scx, (double)scy, (double)scz}, rc[3] = {(double)rcx, (double)rcy, (double)rcz};
+#ifdef GR_DEBUG_PROCRUSTES
+    printf("denom %g sc %g %g %g rc %g %g %g\nH %g %g %g / %g %g %g / %g %g %g\n", denom, sc[0], sc[1], sc[2], rc[0], rc[1], rc[2],
+           H[0], H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]);
+#endif
     kabsch_from_H(H, sc, rc, T_out);
   }
   __syncthreads();

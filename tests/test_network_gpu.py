@@ -1,0 +1,293 @@
+"""GPU parity tests for the network half of the hot path (SURVEY.md section 8 rows P1, K1-K4, T1-T4, M1,
+M2, S1, L1, L2): every CUDA kernel, called through the C ABI behind the reference's module interface,
+against the CPU oracle (oracle/network.py, itself pinned to reference goldens) on the same seeded
+inputs -- teacher-forced per stage, then end to end against the reference's golden transform.
+
+Tolerances (fp32 path): rel-L2 <= 1e-5 for single kernels, <= 2e-4 after the 14-block backbone /
+6-layer transformer; index outputs exact (ties aside); transform: 1e-4 Frobenius (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gaussreg_b200 import ops
+from gaussreg_b200 import modules as gm
+from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+from gaussreg_b200.data import registration_collate_fn_stack_mode
+from gaussreg_b200.synthetic import make_pair_inputs
+from oracle import network as onet
+from tests.helpers import GOLDEN_DIR, golden_spec, oracle_data, rel_l2, seeded_model, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,trans_b", [(1, 1, 1, True), (37, 53, 19, True), (300, 256, 60, False), (1000, 64, 480, False),
+                                           (5000, 128, 64, True), (460, 256, 2048, True), (129, 257, 515, False),
+                                           (20000, 256, 256, True)])
+def test_gemm_epilogues(M, N, K, trans_b):
+    a = _rand(M, K, seed=1)
+    b = _rand(N, K, seed=2) if trans_b else _rand(K, N, seed=2)
+    bias, div, res = _rand(N, seed=3), torch.rand(M, generator=torch.Generator().manual_seed(4)) * 5 + 1, _rand(M, N, seed=5)
+    ref = (a.double() @ (b.double().t() if trans_b else b.double()))
+    got = ops.gemm(a.cuda(), b.cuda(), trans_b).cpu()
+    assert rel_l2(got, ref) < 2e-6
+    full = torch.nn.functional.leaky_relu(0.5 * ref / div.double()[:, None] + bias.double() + res.double(), 0.1)
+    got = ops.gemm(a.cuda(), b.cuda(), trans_b, bias=bias.cuda(), alpha=0.5, row_div=div.cuda(), residual=res.cuda(),
+                   act="leaky_relu").cpu()
+    assert rel_l2(got, full) < 2e-6
+
+
+def test_gemm_batched_head_slices():
+    H, N, M, dh = 4, 77, 91, 64
+    C = H * dh
+    q, k = _rand(N, C, seed=1).cuda(), _rand(M, C, seed=2).cuda()
+    P = torch.empty((H, N, M), device="cuda")
+    ops.gemm_batched(q.data_ptr(), C, dh, k.data_ptr(), C, dh, True, P.data_ptr(), M, N * M, N, M, dh, H, alpha=0.125)
+    want = torch.einsum("nhc,mhc->hnm", q.view(N, H, dh).double(), k.view(M, H, dh).double()) * 0.125
+    assert rel_l2(P.cpu(), want.cpu()) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------- K1-K3
+@pytest.mark.parametrize("C,Co,H", [(4, 64, 20), (32, 32, 20), (64, 64, 30), (128, 128, 43), (256, 256, 47), (512, 512, 12),
+                                    (16, 24, 89), (8, 8, 5)])
+def test_kpconv_vs_oracle(C, Co, H):
+    g = torch.Generator().manual_seed(C + H)
+    Ns, M = 700, 500
+    s_pts = torch.rand(Ns, 3, generator=g)
+    q_pts = s_pts[:M] + 0.01 * torch.randn(M, 3, generator=g)
+    idx = torch.randint(0, Ns + 1, (M, H), generator=g)  # includes the shadow index Ns
+    idx[::7, H // 2:] = Ns
+    feats = torch.randn(Ns, C, generator=g)
+    feats[::5] = -feats[::5].abs()  # rows with non-positive sums: exercise the neighbour-count rule
+    W = torch.randn(15, C, Co, generator=g) / (15 * C) ** 0.5
+    bias = torch.randn(Co, generator=g)
+    kp = (torch.rand(15, 3, generator=g) - 0.5) * 0.3
+    kp[0] = 0
+    sigma = 0.25
+    sd = {"k.weights": W, "k.bias": bias, "k.kernel_points": kp}
+    want = onet.kpconv(sd, "k", feats, q_pts, s_pts, idx, sigma)
+    got = ops.kpconv(feats.cuda(), q_pts.cuda(), s_pts.cuda(), idx.cuda(), W.cuda(), bias.cuda(), kp.cuda(), sigma).cpu()
+    assert rel_l2(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("N,C", [(1000, 32), (5003, 64), (777, 2048), (300, 1024)])
+def test_group_norm_and_fusions(N, C):
+    x, add = _rand(N, C, seed=1) * 3 + 0.5, _rand(N, C, seed=2)
+    gamma, beta = _rand(C, seed=3), _rand(C, seed=4)
+    sd = {"n.norm.weight": gamma, "n.norm.bias": beta}
+    want = onet.group_norm(sd, "n", x, 32)
+    got = ops.group_norm(x.cuda(), 32, gamma.cuda(), beta.cuda()).cpu()
+    assert rel_l2(got, want) < 1e-5
+    want2 = torch.nn.functional.leaky_relu(want + add, 0.1)
+    got2 = ops.group_norm(x.cuda(), 32, gamma.cuda(), beta.cuda(), add=add.cuda(), act="leaky_relu").cpu()
+    assert rel_l2(got2, want2) < 1e-5
+
+
+def test_layer_norm_maxpool_upsample_gather():
+    x, y = _rand(333, 256, seed=1), _rand(333, 256, seed=2)
+    gamma, beta = _rand(256, seed=3), _rand(256, seed=4)
+    want = torch.nn.functional.layer_norm(x + y, (256,), gamma, beta)
+    assert rel_l2(ops.layer_norm_add(x.cuda(), y.cuda(), gamma.cuda(), beta.cuda()).cpu(), want) < 1e-5
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(400, 96, generator=g)
+    idx = torch.randint(0, 401, (250, 17), generator=g)
+    assert torch.equal(ops.maxpool(feats.cuda(), idx.cuda()).cpu(), onet.maxpool(feats, idx))
+    skip = torch.randn(250, 40, generator=g)
+    want = torch.cat([onet.nearest_upsample(feats, idx), skip], 1)
+    assert torch.equal(ops.upsample_concat(feats.cuda(), idx.cuda(), skip.cuda()).cpu(), want)
+    pad = torch.cat([feats, torch.zeros(1, 96)], 0)
+    assert torch.equal(ops.gather_rows(feats.cuda(), idx.cuda()).cpu(), onet.gather_rows(pad, idx))
+
+
+# ---------------------------------------------------------------------------------------------- P1
+def test_point_to_node_partition_vs_oracle():
+    d = make_pair_inputs(3, 6000)
+    data = oracle_data(dict(seed=3, n_points=6000))
+    n_c, n_f = int(data["lengths"][-1][0]), int(data["lengths"][1][0])
+    nodes, pts = data["points"][-1][:n_c], data["points"][1][:n_f]
+    p2n, nm, ki, km = onet.point_to_node_partition(pts, nodes, 128)
+    g_p2n, g_nm, g_ki, g_km = [t.cpu() for t in ops.point_to_node_partition(pts.cuda(), nodes.cuda(), 128)]
+    agree = (g_p2n == p2n).float().mean().item()
+    assert agree > 0.999, agree
+    assert torch.equal(g_nm, nm)
+    rows_ok = (g_ki == ki).all(1).float().mean().item()
+    assert rows_ok > 0.99, rows_ok
+    assert torch.equal(g_km, g_ki != n_f)
+    # small limit: truncation keeps the nearest ones
+    _, _, ki8, km8 = onet.point_to_node_partition(pts, nodes, 8)
+    _, _, g_ki8, g_km8 = [t.cpu() for t in ops.point_to_node_partition(pts.cuda(), nodes.cuda(), 8)]
+    assert (g_ki8 == ki8).all(1).float().mean().item() > 0.99
+
+
+# ---------------------------------------------------------------------------------------------- T1-T4
+def _transformer_pair(seed=0):
+    m = seeded_model(0)
+    return m, m.state_dict()
+
+
+def test_structure_embedding_vs_oracle():
+    m, sd = _transformer_pair()
+    g = torch.Generator().manual_seed(1)
+    pts = (torch.rand(311, 3, generator=g) - 0.5) * torch.tensor([4.0, 3.0, 2.5])
+    want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
+    emb = m.transformer.embedding.cuda()
+    emb.CHUNK_ROWS = 20000  # exercise the chunked path
+    got = emb(pts.cuda()).cpu()
+    assert rel_l2(got, want) < 1e-5
+    d_idx, a_idx, knn = onet.embedding_indices(pts, 0.2, 15, 3)
+    gd, ga, gk = [t.cpu() for t in ops.embedding_indices(pts.cuda(), 0.2, 15, 3)]
+    assert torch.equal(gk.long(), knn)
+    assert rel_l2(gd, d_idx) < 1e-6 and float((ga - a_idx).abs().max()) < 1e-4
+
+
+def test_transformer_layers_vs_oracle():
+    m, sd = _transformer_pair()
+    g = torch.Generator().manual_seed(2)
+    n0, n1 = 203, 157
+    p0, p1 = torch.rand(n0, 3, generator=g) * 3, torch.rand(n1, 3, generator=g) * 3
+    f0, f1 = torch.randn(n0, 256, generator=g), torch.randn(n1, 256, generator=g)
+    e0 = onet.structure_embedding(sd, p0, 0.2, 15, 3)
+    want_self = onet.rpe_layer(sd, "transformer.transformer.layers.0", f0, e0, 4)
+    want_cross = onet.cross_layer(sd, "transformer.transformer.layers.1", f0, f1, 4)
+    tr = m.transformer.cuda()
+    got_self, _ = tr.transformer.layers[0](f0.cuda(), f0.cuda(), e0.cuda())
+    got_cross, _ = tr.transformer.layers[1](f0.cuda(), f1.cuda())
+    assert rel_l2(got_self.cpu(), want_self) < 1e-5
+    assert rel_l2(got_cross.cpu(), want_cross) < 1e-5
+    # whole transformer (2048-d inputs)
+    x0, x1 = torch.randn(n0, 2048, generator=g), torch.randn(n1, 2048, generator=g)
+    cfg = {"geotransformer": dict(make_cfg().geotransformer)}
+    w0, w1 = onet.geometric_transformer(sd, p0, p1, x0, x1, cfg)
+    g0, g1 = tr(p0.cuda()[None], p1.cuda()[None], x0.cuda()[None], x1.cuda()[None])
+    assert g0.shape == (1, n0, 256)
+    assert rel_l2(g0[0].cpu(), w0) < 5e-5 and rel_l2(g1[0].cpu(), w1) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------- M1 / S1 / L1 / L2
+def test_superpoint_matching_vs_oracle():
+    g = torch.Generator().manual_seed(4)
+    rf = torch.nn.functional.normalize(torch.randn(431, 256, generator=g), dim=1)
+    sf = torch.nn.functional.normalize(torch.randn(397, 256, generator=g) + 0.5 * rf[:397], dim=1)
+    rm, sm = torch.ones(431, dtype=torch.bool), torch.ones(397, dtype=torch.bool)
+    rm[[5, 77]] = False
+    sm[[0, 396]] = False
+    wr, ws, wsc = onet.superpoint_matching(rf, sf, rm, sm, 256)
+    gr, gs, gsc = gm.SuperPointMatching(256)(rf.cuda(), sf.cuda(), rm.cuda(), sm.cuda())
+    assert set(zip(gr.tolist(), gs.tolist())) == set(zip(wr.tolist(), ws.tolist()))
+    assert rel_l2(gsc.cpu(), wsc) < 1e-5
+    assert torch.equal(gr.cpu(), wr) and torch.equal(gs.cpu(), ws)
+    # fewer valid pairs than k
+    wr, ws, wsc = onet.superpoint_matching(rf[:9], sf[:7], rm[:9], sm[:7], 256)
+    gr, gs, gsc = gm.SuperPointMatching(256)(rf[:9].cuda(), sf[:7].cuda(), rm[:9].cuda(), sm[:7].cuda())
+    assert gr.shape == wr.shape and set(zip(gr.tolist(), gs.tolist())) == set(zip(wr.tolist(), ws.tolist()))
+
+
+def _patch_problem(P=64, K=128, seed=6):
+    g = torch.Generator().manual_seed(seed)
+    ref_pts = torch.rand(P, K, 3, generator=g)
+    ang = 0.3
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
+    perm = torch.stack([torch.randperm(K, generator=g) for _ in range(P)])
+    src_pts = torch.gather((ref_pts - 0.1) @ R, 1, perm[..., None].expand(-1, -1, 3)) + 0.002 * torch.randn(P, K, 3, generator=g)
+    rm = torch.rand(P, K, generator=g) > 0.15
+    sm = torch.rand(P, K, generator=g) > 0.15
+    rf = torch.randn(P, K, 32, generator=g)
+    sf = torch.gather(rf, 1, perm[..., None].expand(-1, -1, 32)) + 0.3 * torch.randn(P, K, 32, generator=g)
+    scores = torch.einsum("bnd,bmd->bnm", rf, sf) / 32 ** 0.5
+    return ref_pts, src_pts, rm, sm, scores
+
+
+def test_sinkhorn_vs_oracle():
+    _, _, rm, sm, scores = _patch_problem()
+    alpha = torch.tensor(1.0)
+    want = onet.log_optimal_transport(scores, rm, sm, alpha, 100)
+    got = ops.sinkhorn(scores.cuda(), rm.cuda(), sm.cuda(), alpha.cuda(), 100).cpu()
+    valid = want > -1e11
+    assert torch.equal(valid, got > -1e11)
+    assert float((got[valid] - want[valid]).abs().max()) < 2e-3
+    assert rel_l2(got[valid].exp(), want[valid].exp()) < 1e-4
+
+
+def test_lgr_and_procrustes_vs_oracle():
+    ref_pts, src_pts, rm, sm, scores = _patch_problem()
+    ms = onet.log_optimal_transport(scores, rm, sm, torch.tensor(1.0), 100)
+    cfg = {"fine_matching": dict(make_cfg().fine_matching)}
+    taps = {}
+    w_ref, w_src, w_sc, w_T = onet.local_global_registration(ref_pts, src_pts, rm, sm, ms[:, :-1, :-1], cfg, taps=taps)
+    lgr = gm.LocalGlobalRegistration(3, 0.1, True, 0.05, False, False, 3, None, 5)
+    g_ref, g_src, g_sc, g_T = [t.cpu() for t in lgr(ref_pts.cuda(), src_pts.cuda(), rm.cuda(), sm.cuda(), ms.cuda(), None)]
+    assert g_sc.shape == w_sc.shape and w_sc.shape[0] > 500
+    assert torch.equal(g_ref, w_ref) and torch.equal(g_src, w_src)
+    assert rel_l2(g_sc, w_sc) < 1e-5
+    assert float((g_T - w_T).norm()) < 1e-4, (g_T, w_T)
+    # batched Procrustes incl. planar (rank-2), collinear-ish and zero-weight problems
+    g = torch.Generator().manual_seed(8)
+    src = torch.randn(40, 50, 3, generator=g)
+    src[:10, :, 2] = 0.0  # planar
+    Rz = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    ref = src @ Rz.t() + torch.tensor([0.5, -0.25, 1.0]) + 0.01 * torch.randn(40, 50, 3, generator=g)
+    ref[:10, :, 2] = 1.0
+    w = torch.rand(40, 50, generator=g)
+    w[20:25, 10:] = 0.0
+    want = onet.weighted_procrustes(src, ref, w)
+    got = ops.weighted_procrustes(src.cuda(), ref.cuda(), w.cuda()).cpu()
+    assert float((got - want).abs().max()) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- end to end
+TAP_BLOCKS = ["encoder1_1", "encoder1_2", "encoder2_1", "encoder2_3", "encoder3_3", "encoder4_3", "encoder5_3",
+              "decoder4", "decoder3", "decoder2"]
+
+
+def _run_gpu_model(spec):
+    model = seeded_model(0).cuda()
+    d = make_pair_inputs(**spec)
+    dd = {k: d[k] for k in ("ref_points", "src_points", "ref_feats", "src_feats")}
+    cfg = make_cfg()
+    data = registration_collate_fn_stack_mode([dd], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                              cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    taps = {}
+    hooks = [getattr(model.backbone, n).register_forward_hook(lambda m, i, o, n=n: taps.__setitem__(n, o)) for n in TAP_BLOCKS]
+    out = model(data)
+    torch.cuda.synchronize()
+    for h in hooks:
+        h.remove()
+    return model, data, out, taps
+
+
+@pytest.mark.parametrize("case", ["room5k", "textured3k"])
+def test_full_forward_vs_oracle_and_reference_golden(case):
+    gold = np.load(os.path.join(GOLDEN_DIR, f"network_golden_{case}.npz"))
+    spec = golden_spec(gold)
+    model, data, out, taps = _run_gpu_model(spec)
+    assert np.array_equal(torch.stack(data["lengths"]).cpu().numpy(), gold["lengths"])
+    odata = oracle_data(spec)
+    otaps = {}
+    with torch.no_grad():
+        want = onet.forward(seeded_model(0).state_dict(), odata, taps=otaps)
+    report = {}
+    for n in TAP_BLOCKS:
+        report[n] = rel_l2(taps[n].cpu(), otaps[n])
+        assert report[n] < 2e-4, (n, report)
+    report["ref_feats_c"] = rel_l2(out["ref_feats_c"].cpu(), want["ref_feats_c"])
+    report["src_feats_c"] = rel_l2(out["src_feats_c"].cpu(), want["src_feats_c"])
+    assert report["ref_feats_c"] < 2e-4 and report["src_feats_c"] < 2e-4, report
+    got_pairs = set(zip(out["ref_node_corr_indices"].tolist(), out["src_node_corr_indices"].tolist()))
+    want_pairs = set(zip(gold["ref_node_corr_indices"].tolist(), gold["src_node_corr_indices"].tolist()))
+    report["pair_agreement"] = len(got_pairs & want_pairs) / max(len(want_pairs), 1)
+    report["num_corr"] = (int(out["corr_scores"].shape[0]), int(gold["corr_scores"].shape[0]))
+    T = out["estimated_transform"].cpu().numpy()
+    report["T_err_vs_reference"] = float(np.linalg.norm(T - gold["estimated_transform"]))
+    report["T_err_vs_oracle"] = float(np.linalg.norm(T - want["estimated_transform"].numpy()))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/e2e_parity_{case}.txt", "w") as f:
+        f.write(repr(report) + "\n")
+    assert report["pair_agreement"] >= 0.98, report
+    assert report["T_err_vs_reference"] < 1e-4, report
