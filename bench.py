@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the coarse-registration forward path (BASELINE.json metric:
+"scene-pairs/sec coarse-reg fwd, 30k-Gaussian clouds; HBM GB/s %peak").
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (oracle)
+
+A step = one pass of the hot path (neighbour pyramid G1/G2/G3 -> KPConvFPN -> GeometricTransformer ->
+SuperPointMatching -> Sinkhorn -> LocalGlobalRegistration) over one synthetic 30k+30k Gaussian pair
+(BASELINE.json configs[1]).  `value` times it with the pair resident in HBM, `e2e` through the public
+API with pinned host buffers (H2D of points/features, D2H of the 4x4 transform inside the timed region).
+Multi-GPU: pairs are sharded rank-wise (weak scaling), one NCCL all-gather of the transforms per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "scene-pairs/sec coarse-reg fwd, 30k-Gaussian clouds"
+UNIT = "pairs/s"
+N_POINTS = 30000
+WORKLOAD = "configs[1]: single 30k-Gaussian pair, full pyramid+KPConvFPN+GeometricTransformer+LGR fwd"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: reference C++ ext (oracle/_ref) + torch-CPU restatement of the network
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_setup():
+    from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+    from gaussreg_b200.model import create_model
+    from oracle import neighbors as on
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    sd = {k: v.clone() for k, v in create_model(make_cfg()).state_dict().items()}
+    impl = on.ref() if on.have_ref() else on.port()
+    return sd, impl, make_cfg(), NEIGHBOR_LIMITS
+
+
+def cpu_reference_step(sd, impl, cfg, limits, pair):
+    """One pair through the reference's CPU path; returns seconds."""
+    from oracle import network as onet
+    from oracle import neighbors as on
+
+    t0 = time.perf_counter()
+    pts = np.concatenate([pair["ref_points"], pair["src_points"]]).astype(np.float32)
+    lens = np.array([pair["ref_points"].shape[0], pair["src_points"].shape[0]], np.int64)
+    pyr = on.precompute_data_stack_mode(impl, pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                        cfg.backbone.init_radius, limits)
+    data = {k: [torch.from_numpy(np.ascontiguousarray(a)) for a in v] for k, v in pyr.items()}
+    data["features"] = torch.from_numpy(np.concatenate([pair["ref_feats"], pair["src_feats"]]).astype(np.float32))
+    with torch.no_grad():
+        out = onet.forward(sd, data)
+    _ = out["estimated_transform"].numpy()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from gaussreg_b200.synthetic import make_pair_inputs
+
+    sd, impl, cfg, limits = cpu_reference_setup()
+    pair = make_pair_inputs(0, N_POINTS)
+    # bounded: each step is one full pair (about 10 s of CPU work); cap the count so the run ends in minutes
+    steps, warmup = max(1, min(args.steps, 6)), min(args.warmup, 1)
+    for _ in range(warmup):
+        cpu_reference_step(sd, impl, cfg, limits, pair)
+    times = [cpu_reference_step(sd, impl, cfg, limits, pair) for _ in range(steps)]
+    total = sum(times)
+    value = steps / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "requested_steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_points_per_cloud": N_POINTS, "pairs_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": impl.kind,
+                         "sample": f"{steps} x one 30k+30k pair: neighbour pyramid through the reference's own C++ "
+                                   f"(oracle/_ref, 1 thread) + network through the torch-CPU restatement ({cores} threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class OpProfiler:
+    """Wraps the ctypes library: CUDA events around every C-ABI call of one step (launch stream)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self.records = []
+        self.enabled = False
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("gr_") or name.endswith("_workspace_size") or name in ("gr_version", "gr_last_error", "gr_launch_count"):
+            return fn
+
+        def wrapped(*a):
+            if not self.enabled:
+                return fn(*a)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a)
+            e.record()
+            work = 0.0
+            if name == "gr_gemm":  # (A,lda,sA,B,ldb,sB,transB,C,ldc,sC,M,N,K,batch,...)
+                work = 2.0 * a[10] * a[11] * a[12] * a[13]
+            self.records.append((name, s, e, work))
+            return r
+
+        return wrapped
+
+
+def clocks_sampler_start(dev_index):
+    try:
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def clocks_sampler_stop(proc):
+    if proc is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    proc.terminate()
+    try:
+        out, _ = proc.communicate(timeout=5)
+    except Exception:
+        proc.kill()
+        out = ""
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in out.splitlines():
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 8:
+            continue
+        try:
+            sm.append(float(f[0])); mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for nm, v in zip(names, f[4:8]):
+            if v.lower().startswith("active"):
+                reasons.add(nm)
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from gaussreg_b200 import _lib, ext
+    from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+    from gaussreg_b200.data import precompute_data_stack_mode, registration_collate_fn_stack_mode
+    from gaussreg_b200.model import create_model
+    from gaussreg_b200.synthetic import make_pair_inputs
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: gaussreg_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = OpProfiler(_lib.lib())
+    _lib._lib = lib  # route every call through the (disabled) profiler
+
+    cfg = make_cfg()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = create_model(cfg).eval().to(dev)
+
+    # rank r owns pairs r, r + world, ...: a small pool of distinct synthetic pairs per rank
+    pool = 2
+    pairs = [make_pair_inputs(rank + world * i, N_POINTS) for i in range(pool)]
+    host = [{k: torch.from_numpy(p[k]).pin_memory() for k in ("ref_points", "src_points", "ref_feats", "src_feats")} for p in pairs]
+    resident = []
+    for h in host:
+        pts = torch.cat([h["ref_points"], h["src_points"]]).to(dev)
+        feats = torch.cat([h["ref_feats"], h["src_feats"]]).to(dev)
+        lens = torch.tensor([h["ref_points"].shape[0], h["src_points"].shape[0]], dtype=torch.int64, device=dev)
+        resident.append((pts, feats, lens))
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values()) + 16
+    gather_buf = torch.empty((world, 4, 4), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident(i):
+        pts, feats, lens = resident[i % pool]
+        data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                          cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+        data["features"] = feats
+        T = model(data)["estimated_transform"]
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, T.unsqueeze(0))
+        return T
+
+    def step_e2e(i):
+        h = host[i % pool]
+        data = registration_collate_fn_stack_mode([dict(h)], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                                  cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+        T = model(data)["estimated_transform"]
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, T.unsqueeze(0))
+            return gather_buf.cpu()
+        return T.cpu()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        launches0 = _lib.launch_count()
+        for i in range(steps):
+            flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the event pair)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_fn(i)
+            e.record()
+            evs.append((s, e))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - launches0
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    warm = max(args.warmup, 3)
+    sampler = clocks_sampler_start(local_rank) if rank == 0 else None
+    total_ms, launches = timed(step_resident, args.steps, warm)
+    clocks = clocks_sampler_stop(sampler) if rank == 0 else None
+    e2e_ms, _ = timed(step_e2e, args.steps, 1)
+
+    # one profiled step: per-op device time on the launch stream
+    torch.cuda.synchronize()
+    lib.enabled = True
+    lib.records = []
+    flush.fill_(1)
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    step_resident(0)
+    e0.record()
+    torch.cuda.synchronize()
+    lib.enabled = False
+    per_op, work = {}, {}
+    for name, s, e, w in lib.records:
+        per_op[name] = per_op.get(name, 0.0) + s.elapsed_time(e)
+        work[name] = work.get(name, 0.0) + w
+    prof_step_ms = s0.elapsed_time(e0)
+
+    if rank == 0:
+        peaks = read_peaks()
+        value = world * args.steps / (total_ms / 1e3)
+        e2e_value = world * args.steps / (e2e_ms / 1e3)
+        top = max(per_op, key=per_op.get)
+        gemm_ms = per_op.get("gr_gemm", 0.0)
+        n_gemm = sum(1 for r in lib.records if r[0] == "gr_gemm")
+        achieved_tf = work.get("gr_gemm", 0.0) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {
+            "kernel": "sgemm_kernel (gr_gemm: fp32 FFMA path; all dense contractions of K1/K2/T1-T3/M2)",
+            "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+            "launches_per_step": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
+            "flop_per_step": work.get("gr_gemm", 0.0), "share_of_step": gemm_ms / max(sum(per_op.values()), 1e-9),
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sd, impl, ccfg, limits = cpu_reference_setup()
+            sec = cpu_reference_step(sd, impl, ccfg, limits, pairs[0])
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": impl.kind,
+                   "sample": "1 x the same 30k+30k pair: pyramid via the reference C++ (oracle/_ref, 1 thread) + "
+                             "network via the torch-CPU restatement (all threads); %.1f s" % sec}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_points_per_cloud": N_POINTS, "pairs_per_step_per_gpu": 1,
+                       "l2_flush_between_steps": True, "weights": "seeded random init (no checkpoint offline)",
+                       "parallelism": f"pairs sharded over {world} rank(s), all-gather of transforms"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64 * world,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "per_op_ms": {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+            "profiled_step_ms": prof_step_ms, "top_op": top,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
