@@ -127,7 +127,8 @@ class OpProfiler:
             work = 0.0
             if name == "gr_gemm":  # (A,lda,sA,B,ldb,sB,transB,C,ldc,sC,M,N,K,batch,...)
                 work = 2.0 * a[10] * a[11] * a[12] * a[13]
-            self.records.append((name, s, e, work))
+            shape = (a[10], a[11], a[12], a[13], a[6]) if name == "gr_gemm" else None
+            self.records.append((name, s, e, work, shape))
             return r
 
         return wrapped
@@ -269,9 +270,15 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     lib.enabled = False
     per_op, work = {}, {}
-    for name, s, e, w in lib.records:
-        per_op[name] = per_op.get(name, 0.0) + s.elapsed_time(e)
+    gemm_shapes = {}
+    for name, s, e, w, shape in lib.records:
+        ms = s.elapsed_time(e)
+        per_op[name] = per_op.get(name, 0.0) + ms
         work[name] = work.get(name, 0.0) + w
+        if shape is not None:
+            g = gemm_shapes.setdefault(shape, [0, 0.0])
+            g[0] += 1
+            g[1] += ms
     prof_step_ms = s0.elapsed_time(e0)
 
     if rank == 0:
@@ -311,6 +318,8 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "per_op_ms": {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
             "profiled_step_ms": prof_step_ms, "top_op": top,
+            "gemm_shapes_MNKbatchT_count_ms": [[list(k), v[0], round(v[1], 4)] for k, v in
+                                               sorted(gemm_shapes.items(), key=lambda kv: -kv[1][1])[:24]],
         }
         print(json.dumps(line))
     if world > 1:

@@ -7,6 +7,8 @@
 // "b n (h c)" head slices are addressed without copies.  fp32 accumulate in K order: this is the
 // selection-safe path (top-k / argmin steps follow most of these products, SURVEY.md section 7 hard
 // part 2); the tcgen05 3xTF32 path for the large products lives in gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gr {
@@ -157,9 +159,26 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   return launch_sgemm<32, 32, 8, 4, 4>(p, batch, transb, st);
 }
 
+// gemm_tc.cu
+int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
+                long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
+                const float* residual, long long ldr, long long sR, int act, cudaStream_t st);
+
+static int g_gemm_mode = -1;  // 0: SIMT only, 1: tensor cores where the problem qualifies
+
 }  // namespace gr
 
 using namespace gr;
+
+/* mode 0 = fp32 FFMA kernels only, 1 = tcgen05 3xTF32 for large K-major products (default; env GAUSSREG_GEMM=simt|tc). */
+extern "C" void gr_set_gemm_mode(int mode) { g_gemm_mode = mode ? 1 : 0; }
+extern "C" int gr_get_gemm_mode(void) {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("GAUSSREG_GEMM");
+    g_gemm_mode = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+  }
+  return g_gemm_mode;
+}
 
 extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
                        int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
@@ -168,6 +187,11 @@ extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float
   if (M < 0 || N < 0 || K < 0 || batch < 0 || act < 0 || act > 2) return GR_ERR_BAD_ARG;
   if (M == 0 || N == 0 || batch == 0) return GR_OK;
   if (!A || !B || !C) return GR_ERR_BAD_ARG;
+  if (trans_b && gr_get_gemm_mode() == 1) {
+    const int rc = gemm_tf32x3(A, lda, strideA, B, ldb, strideB, C, ldc, strideC, M, N, K, batch, alpha, bias, row_div, residual,
+                               ldr, strideR, act, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr;

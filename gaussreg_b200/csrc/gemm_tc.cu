@@ -1,0 +1,284 @@
+// Tensor-core GEMM for sm_100a: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-accurate).
+//
+//   C = act(alpha * A . B^T / row_div + bias + residual),  A (M,K) and B (N,K) both K-major fp32.
+//
+// Every fp32 operand x is split on the fly into  hi = tf32(x)  and  lo = tf32(x - hi); the product is
+// accumulated as  lo*hi + hi*lo + hi*hi  in a TMEM fp32 accumulator, which restores ~fp32 accuracy
+// (the top-k / argmin selections that follow these products do not tolerate single-pass TF32, see
+// DESIGN.md).  Warp roles per CTA (one 128 x BN output tile):
+//   warps 0-7  producers: ld.global (float4) -> split -> st.shared into the UMMA canonical K-major
+//              SWIZZLE_128B layout (hi and lo tiles), then the epilogue (tcgen05.ld -> registers ->
+//              fused epilogue -> st.global);
+//   warp 8     one elected thread issues the tcgen05.mma chain and tcgen05.commit's.
+// Stage hand-over is by mbarriers: full[s] (256 producer arrivals) / empty[s] (tcgen05.commit).
+#include "common.cuh"
+
+namespace gr {
+
+struct GemmParams;  // gemm.cu
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                       // 32 fp32 = 128 bytes = one SWIZZLE_128B row
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 | layout [61,64) = 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct Params {
+  const float* A; const float* B; float* C;
+  const float* bias; const float* row_div; const float* residual;
+  long long lda, ldb, ldc, ldr;
+  long long sA, sB, sC, sR;
+  int M, N, K;
+  float alpha;
+  int act;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int kABytes = BM * BK * 4;      // one A tile (hi or lo)
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// load `rows` x 32 fp32 (K-major, ld elements) into the swizzled hi / lo tiles
+template <int ROWS>
+__device__ __forceinline__ void produce_tile(const float* __restrict__ g, long long ld, int row0, int row_limit, int k0, int K,
+                                             unsigned char* s_hi, unsigned char* s_lo, int tid) {
+  constexpr int kChunks = ROWS * 8;                       // 16-byte chunks
+  constexpr int kPer = kChunks / kProducerThreads;
+  float4 v[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int ch = tid + i * kProducerThreads;
+    const int r = ch >> 3, c = ch & 7;
+    const int gr = row0 + r, gk = k0 + c * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < row_limit && gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(g + (long long)gr * ld + gk));
+  }
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int ch = tid + i * kProducerThreads;
+    const int r = ch >> 3, c = ch & 7;
+    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    float4 hi, lo;
+    hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
+    lo.x = tf32_rna(v[i].x - hi.x); lo.y = tf32_rna(v[i].y - hi.y); lo.z = tf32_rna(v[i].z - hi.z); lo.w = tf32_rna(v[i].w - hi.w);
+    *reinterpret_cast<float4*>(s_hi + off) = hi;
+    *reinterpret_cast<float4*>(s_lo + off) = lo;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);  // full[st], empty[st], accum, tmem slot
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * C::kStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {  // TMEM allocation (power of two >= 32 columns), owned by the MMA warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ producers
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % C::kStages;
+      if (kb >= C::kStages) mbar_wait(empty_bar(s), ((kb / C::kStages) - 1) & 1);
+      unsigned char* st = smem + s * C::kStageBytes;
+      produce_tile<BM>(A, p.lda, m0, p.M, kb * BK, p.K, st, st + C::kABytes, tid);
+      produce_tile<BN>(B, p.ldb, n0, p.N, kb * BK, p.K, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(s));
+    }
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int m = m0 + q * 32 + lane;
+    float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;
+    const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+    const float rd = (p.row_div && m < p.M) ? p.row_div[m] : 1.f;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (m < p.M) {
+        const int nbase = n0 + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = nbase + j;
+          float x = __uint_as_float(r[j]) * p.alpha;
+          if (p.row_div) x = x / rd;
+          if (n < p.N) {
+            if (p.bias) x += p.bias[n];
+            if (R) x += R[(long long)m * p.ldr + n];
+          }
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          else if (p.act == 2) x = x > 0.f ? x : 0.1f * x;
+          v[j] = x;
+        }
+        float* dst = Cp + (long long)m * p.ldc + nbase;
+        if (vec_ok && nbase + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < p.N) dst[j] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::kStages;
+        mbar_wait(full_bar(s), (kb / C::kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t a_lo = a_hi + C::kABytes;
+        const uint32_t b_hi = a_hi + 2 * C::kABytes;
+        const uint32_t b_lo = b_hi + C::kBBytes;
+#pragma unroll
+        for (int k8 = 0; k8 < BK / 8; ++k8) {
+          const uint32_t ko = k8 * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
+          umma_tf32(tmem_acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN));
+  }
+}
+
+template <int BN>
+static int launch(const Params& p, int batch, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
+  gemm_tf32x3_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(p);
+  GR_CHECK_LAUNCH("gemm_tf32x3_kernel");
+  return GR_OK;
+}
+
+}  // namespace tc
+
+// Returns GR_OK when the tensor-core path ran, 1 when the problem does not qualify (caller falls back to SIMT).
+int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
+                long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
+                const float* residual, long long ldr, long long sR, int act, cudaStream_t st) {
+  const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
+  tc::Params p;
+  p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.sA = sA; p.sB = sB; p.sC = sC; p.sR = sR;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
+  if (N > 128) return tc::launch<256>(p, batch, st);
+  if (N > 64) return tc::launch<128>(p, batch, st);
+  return tc::launch<64>(p, batch, st);
+}
+
+}  // namespace gr

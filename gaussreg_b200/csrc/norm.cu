@@ -6,57 +6,106 @@
 
 namespace gr {
 
-constexpr int kGnRowsPerBlock = 256;
+constexpr int kGnMaxBlocks = 148 * 4;
 
-// partial[blk][g] = (sum, sumsq) over the block's rows and the group's channels
+__host__ __device__ inline int gn_rows_per_block(long long n_rows) {
+  long long r = (n_rows + kGnMaxBlocks - 1) / kGnMaxBlocks;
+  r = (r + 7) / 8 * 8;  // multiple of the widest row-lane count
+  return (int)(r < 8 ? 8 : r);
+}
+
+// partial[blk][g] = (sum, sumsq) over the block's rows and the group's channels.
+// Thread layout: consecutive threads walk consecutive channels (coalesced); for C <= 256 the remaining
+// thread bits walk rows.  Per-thread accumulation in fp32 over at most a few dozen values, then double.
 __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const float* __restrict__ x, int N, int C, int G,
-                                                                double2* __restrict__ partial) {
-  extern __shared__ double2 sh[];  // [C]
-  const int r0 = blockIdx.x * kGnRowsPerBlock, r1 = min(N, r0 + kGnRowsPerBlock);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                                                                int rows_per_block, double2* __restrict__ partial) {
+  extern __shared__ double2 sh[];  // [max(C, 256)]
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  const int tid = threadIdx.x;
+  if (C <= 256) {
+    const int R = 256 / C;  // row lanes (C is a multiple of G=32, typically a power of two)
+    const int c = tid % C, rs = tid / C;
     double s = 0.0, q = 0.0;
-    for (int r = r0; r < r1; ++r) {
-      const double v = (double)x[(long long)r * C + c];
-      s += v; q += v * v;
+    if (rs < R) {
+      float fs = 0.f, fq = 0.f;
+      int cnt = 0;
+      for (int r = r0 + rs; r < r1; r += R) {
+        const float v = x[(long long)r * C + c];
+        fs += v; fq = fmaf(v, v, fq);
+        if (++cnt == 32) { s += (double)fs; q += (double)fq; fs = 0.f; fq = 0.f; cnt = 0; }
+      }
+      s += (double)fs; q += (double)fq;
     }
-    sh[c] = make_double2(s, q);
+    sh[tid] = make_double2(s, q);
+    __syncthreads();
+    if (tid < C) {  // fold the row lanes (fixed order)
+      double2 a = sh[tid];
+      for (int k = 1; k < R; ++k) { const double2 b = sh[tid + k * C]; a.x += b.x; a.y += b.y; }
+      sh[tid] = a;
+    }
+    __syncthreads();
+  } else {
+    for (int c = tid; c < C; c += 256) {
+      double s = 0.0, q = 0.0;
+      for (int r = r0; r < r1; ++r) {
+        const double v = (double)x[(long long)r * C + c];
+        s += v; q += v * v;
+      }
+      sh[c] = make_double2(s, q);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int cg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+  for (int g = tid; g < G; g += 256) {
     double s = 0.0, q = 0.0;
     for (int c = g * cg; c < (g + 1) * cg; ++c) { s += sh[c].x; q += sh[c].y; }
     partial[(long long)blockIdx.x * G + g] = make_double2(s, q);
   }
 }
 
-// stats[g] = (mean, rstd)
-__global__ void groupnorm_finalize_kernel(const double2* __restrict__ partial, int nblk, int G, long long count, float eps,
-                                          float2* __restrict__ stats) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { const double2 p = partial[(long long)b * G + g]; s += p.x; q += p.y; }
-  const double mean = s / (double)count;
-  double var = q / (double)count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+// stats[g] = (mean, rstd); one warp per group, lanes stride over the block partials (fixed order)
+__global__ void __launch_bounds__(1024) groupnorm_finalize_kernel(const double2* __restrict__ partial, int nblk, int G, long long count,
+                                                                  float eps, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  for (int g = threadIdx.x >> 5; g < G; g += (blockDim.x >> 5)) {
+    double s = 0.0, q = 0.0;
+    for (int b = lane; b < nblk; b += 32) { const double2 p = partial[(long long)b * G + g]; s += p.x; q += p.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+      const double mean = s / (double)count;
+      double var = q / (double)count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+  }
 }
 
-// y = act( (x - mean) * rstd * gamma + beta  [+ add] )
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, long long total, int C, int G,
+// y = act( (x - mean) * rstd * gamma + beta  [+ add] ); one thread per 4 consecutive channels (C % 4 == 0)
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, int n_rows, int C, int G,
                                                               const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ add,
                                                               int act, float* __restrict__ y) {
-  const int cg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const float2 st = stats[c / cg];
-    float v = (x[i] - st.x) * st.y * gamma[c] + beta[c];
-    if (add) v += add[i];
-    if (act == 2) v = v > 0.f ? v : 0.1f * v;
-    else if (act == 1) v = fmaxf(v, 0.f);
-    y[i] = v;
+  const int c4 = C >> 2, cg = C / G;
+  const long long total4 = (long long)n_rows * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float g4[4] = {gm.x, gm.y, gm.z, gm.w}, b4[4] = {bt.x, bt.y, bt.z, bt.w};
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (add) { const float4 av = reinterpret_cast<const float4*>(add)[i]; a4[0] = av.x; a4[1] = av.y; a4[2] = av.z; a4[3] = av.w; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 st = stats[(c + k) / cg];
+      float t = (v[k] - st.x) * st.y * g4[k] + b4[k];
+      if (add) t += a4[k];
+      if (act == 2) t = t > 0.f ? t : 0.1f * t;
+      else if (act == 1) t = fmaxf(t, 0.f);
+      v[k] = t;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -97,30 +146,32 @@ __global__ void __launch_bounds__(256) layernorm_add_kernel(const float* __restr
 using namespace gr;
 
 extern "C" size_t gr_group_norm_workspace_size(int64_t n_rows, int groups) {
-  const size_t nblk = (size_t)((n_rows + kGnRowsPerBlock - 1) / kGnRowsPerBlock);
+  const size_t nblk = (size_t)kGnMaxBlocks + 1;
+  (void)n_rows;
   return nblk * groups * sizeof(double2) + groups * sizeof(float2) + 512;
 }
 
 /* K2: y = act(GroupNorm_G(x over all n_rows) [+ add]); act: 0 none, 1 relu, 2 leaky(0.1).  y may alias x. */
 extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, const float* gamma, const float* beta,
                              float eps, const float* add, int act, float* y, void* ws, size_t ws_bytes, void* stream) {
-  if (n_rows < 0 || C <= 0 || groups <= 0 || C % groups != 0 || C > 4096) return GR_ERR_BAD_ARG;
+  if (n_rows < 0 || C <= 0 || groups <= 0 || C % groups != 0 || C > 4096 || C % 4 != 0) return GR_ERR_BAD_ARG;
   if (n_rows == 0) return GR_OK;
   if (!x || !y || !gamma || !beta) return GR_ERR_BAD_ARG;
   if (!ws || ws_bytes < gr_group_norm_workspace_size(n_rows, groups)) return GR_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nblk = ceil_div(n_rows, kGnRowsPerBlock);
+  const int rpb = gn_rows_per_block(n_rows);
+  const int nblk = ceil_div(n_rows, rpb);
   double2* partial = static_cast<double2*>(ws);
   float2* stats = reinterpret_cast<float2*>(static_cast<char*>(ws) + (((size_t)nblk * groups * sizeof(double2) + 255) & ~size_t(255)));
-  const size_t smem = (size_t)C * sizeof(double2);
+  const size_t smem = (size_t)(C > 256 ? C : 256) * sizeof(double2);
   if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(groupnorm_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  groupnorm_partial_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, partial);
+  groupnorm_partial_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
   GR_CHECK_LAUNCH("groupnorm_partial_kernel");
-  groupnorm_finalize_kernel<<<ceil_div(groups, 64), 64, 0, st>>>(partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats);
+  groupnorm_finalize_kernel<<<1, 1024, 0, st>>>(partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats);
   GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
-  const long long total = (long long)n_rows * C;
-  const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, total, C, groups, stats, gamma, beta, add, act, y);
+  const long long total4 = (long long)n_rows * (C / 4);
+  const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
+  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y);
   GR_CHECK_LAUNCH("groupnorm_apply_kernel");
   return GR_OK;
 }

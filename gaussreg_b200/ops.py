@@ -83,10 +83,28 @@ def kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_point
     return A, row_div
 
 
+_wt_cache = {}
+
+
+def _kmajor_weights(weights):
+    """(K, C, C_out) KPConv weights -> cached (C_out, K*C) K-major copy for the tensor-core GEMM (static weights:
+    one transpose per parameter version, load-time plumbing)."""
+    key = (weights.data_ptr(), tuple(weights.shape), weights._version)
+    wt = _wt_cache.get(key)
+    if wt is None:
+        K, C, Co = weights.shape
+        wt = weights.detach().reshape(K * C, Co).t().contiguous()
+        _wt_cache.clear() if len(_wt_cache) > 256 else None
+        _wt_cache[key] = wt
+    return wt
+
+
 def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_points, sigma):
     """KPConv.forward (kpconv.py:79-122): (M, C_out)."""
     A, row_div = kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_points, sigma)
     K, C, Co = weights.shape
+    if _lib.lib().gr_get_gemm_mode() == 1 and (K * C) % 4 == 0:
+        return gemm(A, _kmajor_weights(weights), True, bias=bias, row_div=row_div)
     return gemm(A, weights.view(K * C, Co), False, bias=bias, row_div=row_div)
 
 

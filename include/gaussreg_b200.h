@@ -90,6 +90,10 @@ int gr_radius_neighbors(const float* q_points, const float* s_points, const int6
 int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB, int trans_b,
             float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha, const float* bias,
             const float* row_div, const float* residual, int64_t ldr, int64_t strideR, int act, void* stream);
+/* 0 = fp32 FFMA kernels only; 1 (default) = tcgen05 kind::tf32 with the 3xTF32 split for large trans_b products
+ * (env GAUSSREG_GEMM=simt|tc selects the initial mode). */
+void gr_set_gemm_mode(int mode);
+int gr_get_gemm_mode(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  KPConv gather + kernel-point correlation (geotransformer/modules/kpconv/kpconv.py:79-122).

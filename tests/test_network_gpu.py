@@ -291,3 +291,27 @@ def test_full_forward_vs_oracle_and_reference_golden(case):
         f.write(repr(report) + "\n")
     assert report["pair_agreement"] >= 0.98, report
     assert report["T_err_vs_reference"] < 1e-4, report
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (4096, 256, 256), (1000, 64, 480), (777, 128, 1920), (20000, 32, 480),
+                                   (460, 256, 2048), (300, 512, 128), (5000, 2048, 512), (129, 200, 36), (60000, 64, 60)])
+def test_gemm_tensor_core_3xtf32_vs_fp32(M, N, K):
+    """tcgen05 kind::tf32 with the hi/lo split must agree with the fp32 FFMA kernel to fp32 rounding level."""
+    from gaussreg_b200 import _lib
+    L = _lib.lib()
+    a, b = _rand(M, K, seed=11).cuda(), _rand(N, K, seed=12).cuda()
+    bias, div, res = _rand(N, seed=13).cuda(), (torch.rand(M, generator=torch.Generator().manual_seed(4)) * 5 + 1).cuda(), _rand(M, N, seed=15).cuda()
+    ref = a.double() @ b.double().t()
+    try:
+        L.gr_set_gemm_mode(0)
+        simt = ops.gemm(a, b, True, bias=bias, alpha=0.5, row_div=div, residual=res, act="leaky_relu")
+        L.gr_set_gemm_mode(1)
+        tc = ops.gemm(a, b, True, bias=bias, alpha=0.5, row_div=div, residual=res, act="leaky_relu")
+        plain = ops.gemm(a, b, True)
+    finally:
+        L.gr_set_gemm_mode(1)
+    torch.cuda.synchronize()
+    # measured: 1e-6 .. 4e-6 (the tensor core's fp32 accumulation truncates), vs ~2e-7 for the FFMA kernel
+    assert rel_l2(plain.cpu(), ref.cpu()) < 1e-5
+    assert rel_l2(tc.cpu(), simt.cpu()) < 1e-5
