@@ -11,6 +11,9 @@
 //              fused epilogue -> st.global);
 //   warp 8     one elected thread issues the tcgen05.mma chain and tcgen05.commit's.
 // Stage hand-over is by mbarriers: full[s] (256 producer arrivals) / empty[s] (tcgen05.commit).
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gr {
@@ -93,6 +96,7 @@ struct Params {
   int M, N, K;
   float alpha;
   int act;
+  int k_split;  // 0: blockIdx.z is a batch index; > 0: blockIdx.z selects the K slice [z*k_split, (z+1)*k_split)
 };
 
 template <int BN>
@@ -146,9 +150,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
-  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
-  const int nkb = (p.K + BK - 1) / BK;
+  const bool split = p.k_split > 0;
+  const int kbeg = split ? blockIdx.z * p.k_split : 0;
+  const int kend = split ? min(p.K, kbeg + p.k_split) : p.K;
+  const float* __restrict__ A = p.A + (split ? 0ll : (long long)blockIdx.z * p.sA);
+  const float* __restrict__ B = p.B + (split ? 0ll : (long long)blockIdx.z * p.sB);
+  const int nkb = (kend - kbeg + BK - 1) / BK;
 
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
@@ -170,8 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
       const int s = kb % C::kStages;
       if (kb >= C::kStages) mbar_wait(empty_bar(s), ((kb / C::kStages) - 1) & 1);
       unsigned char* st = smem + s * C::kStageBytes;
-      produce_tile<BM>(A, p.lda, m0, p.M, kb * BK, p.K, st, st + C::kABytes, tid);
-      produce_tile<BN>(B, p.ldb, n0, p.N, kb * BK, p.K, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
+      produce_tile<BM>(A, p.lda, m0, p.M, kbeg + kb * BK, kend, st, st + C::kABytes, tid);
+      produce_tile<BN>(B, p.ldb, n0, p.N, kbeg + kb * BK, kend, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(full_bar(s));
     }
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + q * 32 + lane;
-    float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;
+    float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;  // split-K: sC = M*N, raw partial sums
     const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
     const float rd = (p.row_div && m < p.M) ? p.row_div[m] : 1.f;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
@@ -249,6 +256,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
   }
 }
 
+// C = epilogue(sum_z partial[z]) in a fixed order; one thread per 4 consecutive columns (N % 4 == 0)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, Params p) {
+  const int n4 = p.N >> 2;
+  const long long total = (long long)p.M * n4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+  const long long plane = (long long)p.M * p.N;
+  float4 acc = reinterpret_cast<const float4*>(partial)[i];
+  for (int z = 1; z < splits; ++z) {
+    const float4 v = reinterpret_cast<const float4*>(partial + z * plane)[i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float rd = p.row_div ? p.row_div[m] : 1.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = v[j] * p.alpha;
+    if (p.row_div) x = x / rd;
+    if (p.bias) x += p.bias[n + j];
+    if (p.residual) x += p.residual[(long long)m * p.ldr + n + j];
+    if (p.act == 1) x = fmaxf(x, 0.f);
+    else if (p.act == 2) x = x > 0.f ? x : 0.1f * x;
+    p.C[(long long)m * p.ldc + n + j] = x;
+  }
+}
+
 template <int BN>
 static int launch(const Params& p, int batch, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -265,6 +299,35 @@ static int launch(const Params& p, int batch, cudaStream_t st) {
 
 }  // namespace tc
 
+// Grow-only scratch for the split-K partial sums, one buffer per (device, stream): reuse is stream-ordered, so
+// successive calls on the same stream may share it without synchronisation.
+static float* splitk_scratch(cudaStream_t st, size_t bytes) {
+  struct Entry { int dev; cudaStream_t st; float* ptr; size_t bytes; };
+  static std::mutex mu;
+  static std::vector<Entry> entries;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : entries) {
+    if (e.dev == dev && e.st == st) {
+      if (e.bytes >= bytes) return e.ptr;
+      cudaStreamSynchronize(st);
+      cudaFree(e.ptr);
+      e.ptr = nullptr; e.bytes = 0;
+      const size_t want = bytes + bytes / 2;
+      if (cudaMalloc(&e.ptr, want) != cudaSuccess) { set_last_error("split-K scratch cudaMalloc", cudaGetLastError()); return nullptr; }
+      e.bytes = want;
+      return e.ptr;
+    }
+  }
+  Entry e{dev, st, nullptr, 0};
+  const size_t want = bytes < (size_t(64) << 20) ? (size_t(64) << 20) : bytes + bytes / 2;
+  if (cudaMalloc(&e.ptr, want) != cudaSuccess) { set_last_error("split-K scratch cudaMalloc", cudaGetLastError()); return nullptr; }
+  e.bytes = want;
+  entries.push_back(e);
+  return e.ptr;
+}
+
 // Returns GR_OK when the tensor-core path ran, 1 when the problem does not qualify (caller falls back to SIMT).
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
@@ -275,7 +338,27 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   tc::Params p;
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.sA = sA; p.sB = sB; p.sC = sC; p.sR = sR;
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act; p.k_split = 0;
+  // The tensor core's fp32 accumulation truncates, so the error grows linearly with the number of MMA steps
+  // chained into one accumulator.  Long K is therefore cut into slices of kSlice, each accumulated in its own
+  // TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.
+  constexpr int kSlice = 256;
+  if (batch == 1 && K > kSlice + kSlice / 2 && N % 4 == 0) {
+    const int splits = (K + kSlice - 1) / kSlice;
+    float* partial = splitk_scratch(st, (size_t)splits * M * N * sizeof(float));
+    if (partial == nullptr) return GR_ERR_CUDA;
+    tc::Params q = p;
+    q.C = partial; q.ldc = N; q.sC = (long long)M * N; q.bias = nullptr; q.row_div = nullptr; q.residual = nullptr;
+    q.alpha = 1.f; q.act = 0; q.k_split = kSlice;
+    int rc = N > 128 ? tc::launch<256>(q, splits, st) : (N > 64 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
+    if (rc == GR_OK) {
+      const long long total = (long long)M * (N / 4);
+      tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) rc = GR_ERR_CUDA;
+    }
+    return rc;
+  }
   if (N > 128) return tc::launch<256>(p, batch, st);
   if (N > 64) return tc::launch<128>(p, batch, st);
   return tc::launch<64>(p, batch, st);

@@ -32,7 +32,8 @@ def _device():
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of the current stream (torch.cuda.current_stream() costs ~10 us per call)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 _ws_cache = {}
@@ -40,7 +41,7 @@ _ws_cache = {}
 
 def _workspace(nbytes, dev):
     """Grow-only scratch buffer per device (stream-ordered reuse on the current stream)."""
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    key = (dev.index, _stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)

@@ -83,20 +83,20 @@ def kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_point
     return A, row_div
 
 
-_wt_cache = {}
-
-
 def _kmajor_weights(weights):
-    """(K, C, C_out) KPConv weights -> cached (C_out, K*C) K-major copy for the tensor-core GEMM (static weights:
-    one transpose per parameter version, load-time plumbing)."""
-    key = (weights.data_ptr(), tuple(weights.shape), weights._version)
-    wt = _wt_cache.get(key)
-    if wt is None:
+    """(K, C, C_out) KPConv weights -> (C_out, K*C) K-major copy for the tensor-core GEMM.  Static weights: one
+    transpose per parameter version (load-time plumbing), cached ON the parameter object so that the cache can
+    never outlive or alias the tensor it was made from."""
+    cached = getattr(weights, "_gr_kmajor", None)
+    if cached is None or cached[0] != weights._version or cached[1].device != weights.device:
         K, C, Co = weights.shape
         wt = weights.detach().reshape(K * C, Co).t().contiguous()
-        _wt_cache.clear() if len(_wt_cache) > 256 else None
-        _wt_cache[key] = wt
-    return wt
+        cached = (weights._version, wt)
+        try:
+            weights._gr_kmajor = cached
+        except AttributeError:
+            pass
+    return cached[1]
 
 
 def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_points, sigma):

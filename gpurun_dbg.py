@@ -1,19 +1,32 @@
-import sys, torch, time
+import sys, time, torch, numpy as np
 sys.path.insert(0, '.')
-from gaussreg_b200 import ops, _lib
-L = _lib.lib()
-shapes = [(262144,256,256),(786432,256,256),(60000,64,60),(60000,32,480),(60000,128,32),(60000,128,64),(42000,32,480),(42000,64,960),(42000,256,64),(15400,128,1920),(15400,512,128),(3700,256,3840),(3700,1024,256),(967,512,7680),(967,2048,512),(967,256,2048),(3700,1024,3072),(15400,512,1536),(42000,256,768)]
-for (M,N,K) in shapes:
-    a=torch.randn(M,K,device='cuda'); b=torch.randn(N,K,device='cuda'); out=torch.empty(M,N,device='cuda')
-    res=[]
-    for mode in (0,1):
-        L.gr_set_gemm_mode(mode)
-        for _ in range(2): ops.gemm(a,b,True,out=out)
-        torch.cuda.synchronize()
-        s=torch.cuda.Event(enable_timing=True); e=torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(5): ops.gemm(a,b,True,out=out)
-        e.record(); torch.cuda.synchronize()
-        ms=s.elapsed_time(e)/5
-        res.append((ms, 2*M*N*K/ms/1e9))
-    print(f"{M:7d} {N:5d} {K:5d}  simt {res[0][0]:8.3f} ms {res[0][1]:7.1f} TF/s | tc {res[1][0]:8.3f} ms {res[1][1]:7.1f} TF/s")
+from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+from gaussreg_b200.data import precompute_data_stack_mode
+from gaussreg_b200.model import create_model
+from gaussreg_b200.synthetic import make_pair_inputs
+cfg = make_cfg(); torch.manual_seed(0); np.random.seed(0)
+model = create_model(cfg).eval().cuda()
+p = make_pair_inputs(0, 30000)
+pts = torch.from_numpy(np.concatenate([p['ref_points'], p['src_points']])).cuda(); feats = torch.from_numpy(np.concatenate([p['ref_feats'], p['src_feats']])).cuda()
+lens = torch.tensor([30000,30000], device='cuda')
+def step():
+    data = precompute_data_stack_mode(pts, lens, 5, 0.025, 0.0625, NEIGHBOR_LIMITS); data['features']=feats
+    return data, model(data)
+for _ in range(3): step()
+torch.cuda.synchronize()
+t=time.perf_counter()
+for _ in range(5): d,o = step()
+t_issue=(time.perf_counter()-t)/5
+torch.cuda.synchronize(); t_all=(time.perf_counter()-t)/5
+print('wall per step %.2f ms (issue-side %.2f ms)'%(t_all*1e3, t_issue*1e3))
+# phases
+def timeit(fn, n=5):
+    torch.cuda.synchronize(); t=time.perf_counter()
+    for _ in range(n): r=fn()
+    torch.cuda.synchronize(); return (time.perf_counter()-t)/n*1e3
+print('pyramid %.2f ms'%timeit(lambda: precompute_data_stack_mode(pts, lens, 5, 0.025, 0.0625, NEIGHBOR_LIMITS)))
+data,_=step()
+print('backbone %.2f ms'%timeit(lambda: model.backbone(feats, data)))
+import cProfile, pstats
+pr=cProfile.Profile(); pr.enable(); step(); torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(18)

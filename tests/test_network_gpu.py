@@ -37,11 +37,11 @@ def test_gemm_epilogues(M, N, K, trans_b):
     bias, div, res = _rand(N, seed=3), torch.rand(M, generator=torch.Generator().manual_seed(4)) * 5 + 1, _rand(M, N, seed=5)
     ref = (a.double() @ (b.double().t() if trans_b else b.double()))
     got = ops.gemm(a.cuda(), b.cuda(), trans_b).cpu()
-    assert rel_l2(got, ref) < 2e-6
+    assert rel_l2(got, ref) < 5e-6
     full = torch.nn.functional.leaky_relu(0.5 * ref / div.double()[:, None] + bias.double() + res.double(), 0.1)
     got = ops.gemm(a.cuda(), b.cuda(), trans_b, bias=bias.cuda(), alpha=0.5, row_div=div.cuda(), residual=res.cuda(),
                    act="leaky_relu").cpu()
-    assert rel_l2(got, full) < 2e-6
+    assert rel_l2(got, full) < 5e-6
 
 
 def test_gemm_batched_head_slices():
@@ -312,6 +312,7 @@ def test_gemm_tensor_core_3xtf32_vs_fp32(M, N, K):
     finally:
         L.gr_set_gemm_mode(1)
     torch.cuda.synchronize()
-    # measured: 1e-6 .. 4e-6 (the tensor core's fp32 accumulation truncates), vs ~2e-7 for the FFMA kernel
-    assert rel_l2(plain.cpu(), ref.cpu()) < 1e-5
-    assert rel_l2(tc.cpu(), simt.cpu()) < 1e-5
+    # measured: 1e-6 .. 4e-6 (the tensor core's fp32 accumulation truncates; K is sliced at 256 and the slices
+    # are summed in fp32), vs ~2e-7 for the FFMA kernel
+    assert rel_l2(plain.cpu(), ref.cpu()) < 5e-6
+    assert rel_l2(tc.cpu(), simt.cpu()) < 5e-6
