@@ -1,0 +1,219 @@
+// T1 fused: geometric structure embedding on the tensor cores, without any (N*N*k, C) intermediate.
+//
+//   emb[r, :] = (W_d E(d_r) + b_d) + max_k (W_a E(a_{r,k}) + b_a),   r = n*N + m,  C = 256
+//   E(x)[2i] = sin(x * div_i), E(x)[2i+1] = cos(x * div_i)
+//
+// Reference: geotransformer/modules/geotransformer/geotransformer.py:57-72 materialises E(d) (N^2 x 256),
+// E(a) (N^2 x 3 x 256) and both projections before the max.  Here one CTA owns a 128-row x 128-column
+// output tile: producer warps GENERATE the sinusoid operand tiles (hi / lo TF32 split) straight into the UMMA
+// canonical shared-memory layout, the weight tiles arrive pre-split and pre-swizzled by one bulk async copy
+// per k-block, four fp32 accumulators (d, a0, a1, a2) live side by side in TMEM (4 x 128 = 512 columns), and
+// the epilogue applies the bias / max-over-k / sum directly on the accumulators.
+#include "tc_common.cuh"
+
+namespace gr {
+namespace tc {
+
+constexpr int kEmbC = 256;             // hidden dim (= K of the projections and total N)
+constexpr int kEmbBN = 128;            // output columns per CTA
+constexpr int kEmbBM = 128;
+constexpr int kEmbBK = 32;
+constexpr int kEmbKB = kEmbC / kEmbBK;  // 8 k-blocks per projection
+constexpr int kEmbStages = 3;
+constexpr int kEmbTile = kEmbBM * kEmbBK * 4;           // 16 KB (one hi or lo tile, A or B)
+constexpr int kEmbStageBytes = 4 * kEmbTile;            // A hi, A lo, B hi, B lo
+constexpr int kEmbSmem = kEmbStages * kEmbStageBytes + 1024 + 256;
+constexpr int kEmbThreads = 288;
+
+// W (N, K) row-major -> for every (n-tile of 128, k-block of 32): [hi tile 16 KB][lo tile 16 KB] in the
+// K-major SWIZZLE_128B byte order the tensor core reads.
+__global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out) {
+  const int nt = blockIdx.y, kb = blockIdx.x;
+  unsigned char* base = reinterpret_cast<unsigned char*>(out) + ((size_t)(nt * (K / 32) + kb)) * 2 * kEmbTile;
+  for (int ch = threadIdx.x; ch < 128 * 8; ch += blockDim.x) {
+    const int r = ch >> 3, c = ch & 7;
+    const float4 v = *reinterpret_cast<const float4*>(W + (size_t)(nt * 128 + r) * K + kb * 32 + c * 4);
+    float4 hi, lo;
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + kEmbTile + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
+    const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
+    const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
+    const float* __restrict__ bias_d, const float* __restrict__ bias_a, float* __restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEmbStages * kEmbStageBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kEmbStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kEmbStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEmbStages + 1);
+  __shared__ float s_div[kEmbC / 2];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nhalf = blockIdx.x;                         // which 128 output columns
+  const long long r0 = (long long)blockIdx.y * kEmbBM;  // first pair-row of the tile
+  const int n_gemm = 1 + angle_k;                       // d, a_0 .. a_{k-1}
+  const int n_iter = n_gemm * kEmbKB;
+
+  if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kEmbStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < 8) {
+    // ---------------------------------------------------------------- producers: sinusoid operand tiles
+    const int row = tid >> 1, h16 = tid & 1;  // two threads per row, 16 consecutive k each (8 sin/cos pairs)
+    const long long r = r0 + row;
+    const bool valid = r < rows;
+    float xg[4] = {0.f, 0.f, 0.f, 0.f};  // embedding indices of this row for d, a0, a1, a2
+    if (valid) {
+      xg[0] = d_idx[r];
+      for (int k = 0; k < angle_k; ++k) xg[1 + k] = a_idx[r * angle_k + k];
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kEmbStages;
+      const int g = it / kEmbKB, kb = it % kEmbKB;
+      if (it >= kEmbStages) mbar_wait(empty_bar(s), ((it / kEmbStages) - 1) & 1);
+      unsigned char* st = smem + s * kEmbStageBytes;
+      if (tid == 0) {  // weight tile: one bulk copy of the pre-packed [hi | lo] pair
+        const float* src = (g == 0 ? wd_packed : wa_packed) + ((size_t)(nhalf * kEmbKB + kb)) * (2 * kEmbTile / 4);
+        mbar_expect_tx(full_bar(s), 2 * kEmbTile);  // registered before the copy; thread 0 still arrives below
+        bulk_copy_g2s(smem_u32(st + 2 * kEmbTile), src, 2 * kEmbTile, full_bar(s));
+      }
+      const float x = g == 0 ? xg[0] : (g == 1 ? xg[1] : (g == 2 ? xg[2] : xg[3]));
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {  // 4 chunks of 16 B = 2 (sin, cos) pairs each
+        const int c = h16 * 4 + jj;
+        const int i0 = kb * 16 + c * 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          sincosf(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+          sincosf(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+        }
+        float4 hi, lo;
+        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+        lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + kEmbTile + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const long long rr = r0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = half * (kEmbBN / 2); c0 < (half + 1) * (kEmbBN / 2); c0 += 32) {
+      const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      uint32_t t[32];
+      float mx[32];
+      tmem_ld32(lane_addr + 1 * kEmbBN, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx[j] = __uint_as_float(t[j]);
+      for (int k = 1; k < angle_k; ++k) {
+        tmem_ld32(lane_addr + (1 + k) * kEmbBN, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx[j] = fmaxf(mx[j], __uint_as_float(t[j]));
+      }
+      tmem_ld32(lane_addr, t);
+      if (rr < rows) {
+        const int nbase = nhalf * kEmbBN + c0;
+        float* dst = out + rr * kEmbC + nbase;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = (__uint_as_float(t[j]) + bias_d[nbase + j]) + (mx[j] + bias_a[nbase + j]);
+          o.y = (__uint_as_float(t[j + 1]) + bias_d[nbase + j + 1]) + (mx[j + 1] + bias_a[nbase + j + 1]);
+          o.z = (__uint_as_float(t[j + 2]) + bias_d[nbase + j + 2]) + (mx[j + 2] + bias_a[nbase + j + 2]);
+          o.w = (__uint_as_float(t[j + 3]) + bias_d[nbase + j + 3]) + (mx[j + 3] + bias_a[nbase + j + 3]);
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kEmbBN >> 3) << 17) | ((uint32_t)(kEmbBM >> 4) << 24);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kEmbStages;
+        const int g = it / kEmbKB, kb = it % kEmbKB;
+        mbar_wait(full_bar(s), (it / kEmbStages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kEmbStageBytes);
+        const uint32_t a_lo = a_hi + kEmbTile, b_hi = a_hi + 2 * kEmbTile, b_lo = a_hi + 3 * kEmbTile;
+        const uint32_t acc = tmem_acc + (uint32_t)(g * kEmbBN);
+#pragma unroll
+        for (int k8 = 0; k8 < kEmbBK / 8; ++k8) {
+          const uint32_t ko = k8 * 32;
+          umma_tf32(acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(512));
+  }
+}
+
+}  // namespace tc
+}  // namespace gr
+
+using namespace gr;
+
+/* Packs a (N,K) fp32 weight (N % 128 == 0, K % 32 == 0) into the tensor-core operand format: 2*N*K floats. */
+extern "C" int gr_pack_weight_tf32x3(const float* W, int N, int K, float* out, void* stream) {
+  if (N <= 0 || K <= 0 || N % 128 != 0 || K % 32 != 0 || !W || !out) return GR_ERR_BAD_ARG;
+  dim3 grid(K / 32, N / 128);
+  tc::pack_weight_tf32x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, N, K, out);
+  GR_CHECK_LAUNCH("pack_weight_tf32x3_kernel");
+  return GR_OK;
+}
+
+/* T1 fused.  d_idx (rows), a_idx (rows, angle_k), div_term (128), packed proj_d / proj_a weights
+ * (gr_pack_weight_tf32x3 of the (256,256) Linear weights), biases (256) -> out (rows, 256). */
+extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t rows, int angle_k,
+                                            const float* div_term, int hidden_dim, const float* wd_packed,
+                                            const float* wa_packed, const float* bias_d, const float* bias_a, float* out,
+                                            void* stream) {
+  if (rows < 0 || angle_k < 1 || angle_k > 3 || hidden_dim != tc::kEmbC) return GR_ERR_BAD_ARG;
+  if (rows == 0) return GR_OK;
+  if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
+    attr_set = true;
+  }
+  dim3 grid(tc::kEmbC / tc::kEmbBN, (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM));
+  tc::structure_embedding_tc_kernel<<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
+      d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+  GR_CHECK_LAUNCH("structure_embedding_tc_kernel");
+  return GR_OK;
+}

@@ -35,6 +35,7 @@ class GeometricStructureEmbedding(nn.Module):
 
     # rows of the (N*N, C) embedding processed per chunk: bounds the sinusoid / projection temporaries
     CHUNK_ROWS = 1 << 18
+    use_fused = True  # tensor-core kernel with in-kernel sinusoid generation (csrc/embedding_tc.cu)
 
     def __init__(self, hidden_dim, sigma_d, sigma_a, angle_k, reduction_a="max"):
         super().__init__()
@@ -60,6 +61,10 @@ class GeometricStructureEmbedding(nn.Module):
         C = self.embedding.d_model
         k = self.angle_k
         d_idx, a_idx = self.get_embedding_indices(pts)
+        if self.use_fused and C == 256 and k <= 3 and ops._lib.lib().gr_get_gemm_mode() == 1:
+            out = ops.structure_embedding_fused(d_idx, a_idx, self.embedding.div_term, self.proj_d.weight, self.proj_d.bias,
+                                                self.proj_a.weight, self.proj_a.bias)
+            return out.unsqueeze(0) if batched else out
         d_flat, a_flat = d_idx.view(-1), a_idx.view(-1)
         out = torch.empty((N * N, C), dtype=torch.float32, device=pts.device)
         rows = N * N

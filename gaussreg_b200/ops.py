@@ -222,6 +222,35 @@ def embedding_combine(D, A, k, out):
     return out
 
 
+def packed_weight_tf32x3(weight):
+    """(N,K) Linear weight -> tensor-core operand format (hi/lo TF32 tiles, pre-swizzled); cached on the parameter."""
+    cached = getattr(weight, "_gr_packed", None)
+    if cached is None or cached[0] != weight._version or cached[1].device != weight.device:
+        N, K = weight.shape
+        out = torch.empty((2 * N * K,), dtype=_F32, device=weight.device)
+        st = _lib.lib().gr_pack_weight_tf32x3(weight.detach().contiguous().data_ptr(), N, K, out.data_ptr(), _stream())
+        _lib.check(st, "pack_weight_tf32x3")
+        cached = (weight._version, out)
+        try:
+            weight._gr_packed = cached
+        except AttributeError:
+            pass
+    return cached[1]
+
+
+def structure_embedding_fused(d_idx, a_idx, div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b):
+    """geotransformer.py:57-72 in one tensor-core kernel: (N,N), (N,N,k) indices -> (N,N,C)."""
+    N = d_idx.shape[0]
+    k = a_idx.shape[-1]
+    C = proj_d_w.shape[0]
+    out = torch.empty((N, N, C), dtype=_F32, device=d_idx.device)
+    st = _lib.lib().gr_structure_embedding_fused(d_idx.data_ptr(), a_idx.data_ptr(), N * N, k, div_term.data_ptr(), C,
+                                                 packed_weight_tf32x3(proj_d_w).data_ptr(), packed_weight_tf32x3(proj_a_w).data_ptr(),
+                                                 proj_d_b.data_ptr(), proj_a_b.data_ptr(), out.data_ptr(), _stream())
+    _lib.check(st, "structure_embedding_fused")
+    return out
+
+
 def rpe_attention_probs(q, k, U, qb, emb, num_heads):
     N, C = q.shape
     P = torch.empty((num_heads, N, N), dtype=_F32, device=q.device)

@@ -134,6 +134,13 @@ int gr_embedding_indices(const float* points, int N, float sigma_d, float sigma_
                          int32_t* knn, void* stream);
 int gr_sinusoid_rows(const float* x, int64_t rows, const float* div_term, int n_div, float* E, void* stream);
 int gr_embedding_combine(const float* D, const float* A, int64_t rows, int C, int k, float* out, void* stream);
+/* T1 fused on the tensor cores (geotransformer.py:57-72 in one kernel): sinusoid operand tiles are generated in
+ * shared memory, proj_d / proj_a run as tcgen05 3xTF32 MMAs into four TMEM accumulators, bias + max_k + sum in the
+ * epilogue.  Weights must first be packed with gr_pack_weight_tf32x3 ((N,K) -> 2*N*K floats, N%128==0, K%32==0). */
+int gr_pack_weight_tf32x3(const float* W, int N, int K, float* out, void* stream);
+int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t rows, int angle_k, const float* div_term,
+                                 int hidden_dim, const float* wd_packed, const float* wa_packed, const float* bias_d,
+                                 const float* bias_a, float* out, void* stream);
 
 /* T2  RPE attention probabilities with the p-term reassociated (rpe_transformer.py:50-66), row softmax
  * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */

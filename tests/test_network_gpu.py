@@ -138,8 +138,12 @@ def test_structure_embedding_vs_oracle():
     pts = (torch.rand(311, 3, generator=g) - 0.5) * torch.tensor([4.0, 3.0, 2.5])
     want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
     emb = m.transformer.embedding.cuda()
-    emb.CHUNK_ROWS = 20000  # exercise the chunked path
+    got = emb(pts.cuda()).cpu()  # fused tensor-core kernel
+    assert rel_l2(got, want) < 1e-5
+    emb.use_fused = False
+    emb.CHUNK_ROWS = 20000  # unfused path, chunked
     got = emb(pts.cuda()).cpu()
+    emb.use_fused = True
     assert rel_l2(got, want) < 1e-5
     d_idx, a_idx, knn = onet.embedding_indices(pts, 0.2, 15, 3)
     gd, ga, gk = [t.cpu() for t in ops.embedding_indices(pts.cuda(), 0.2, 15, 3)]
