@@ -155,8 +155,8 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   const long long ctas128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * batch;
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
   if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
-  if (ctas64 >= 148 || p.M > 32) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
-  return launch_sgemm<32, 32, 8, 4, 4>(p, batch, transb, st);
+  if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
+  return launch_sgemm<32, 32, 8, 4, 4>(p, batch, transb, st);  // superpoint-sized problems: fill the SMs with small tiles
 }
 
 // gemm_tc.cu

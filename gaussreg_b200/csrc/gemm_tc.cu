@@ -273,6 +273,14 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
+  {
+    // superpoint-sized products (M ~ 500) yield a handful of 128-row tiles: the FFMA kernel with 32x32 tiles
+    // fills the machine better than 4 tensor-core CTAs
+    const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * batch;
+    const long long slices = (batch == 1 && K > 384 && N % 4 == 0) ? (K + 255) / 256 : 1;
+    if (tiles * slices < 24) return 1;
+  }
   tc::Params p;
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.sA = sA; p.sB = sB; p.sC = sC; p.sR = sR;

@@ -105,8 +105,53 @@ __global__ void match_decode_kernel(const unsigned long long* __restrict__ keys,
 // S1
 // ---------------------------------------------------------------------------------------------
 
-// one CTA per patch pair; the (K+1)x(K+1) padded score matrix stays in shared memory for all iterations
-__global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+// one CTA per patch pair; the (K+1)x(K+1) padded score matrix stays in shared memory for all iterations.
+// 16 warps; every warp owns rows (columns) w, w+16, ... and reduces four of them at a time so that the
+// shuffle / exp latencies of independent rows overlap.
+constexpr int kSinkThreads = 512;
+constexpr int kSinkIlp = 4;
+
+// out[i] = bias[i] - logsumexp_j(ps[i*si + j*sj] + add[j]) for the lines owned by this warp
+__device__ __forceinline__ void sinkhorn_lse_pass(const float* __restrict__ ps, int K1, int si, int sj,
+                                                  const float* __restrict__ add, const float* __restrict__ bias,
+                                                  float* __restrict__ out, int warp, int nwarp, int lane) {
+  for (int i0 = warp; i0 < K1; i0 += nwarp * kSinkIlp) {
+    float mx[kSinkIlp], sm[kSinkIlp];
+#pragma unroll
+    for (int r = 0; r < kSinkIlp; ++r) {
+      const int i = i0 + r * nwarp;
+      float m = -INFINITY;
+      if (i < K1)
+        for (int j = lane; j < K1; j += 32) m = fmaxf(m, ps[i * si + j * sj] + add[j]);
+      mx[r] = m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kSinkIlp; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+#pragma unroll
+    for (int r = 0; r < kSinkIlp; ++r) {
+      const int i = i0 + r * nwarp;
+      float s = 0.f;
+      if (i < K1)
+        for (int j = lane; j < K1; j += 32) s += __expf(ps[i * si + j * sj] + add[j] - mx[r]);  // ex2.approx: |rel err| ~1e-6 here
+      sm[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kSinkIlp; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kSinkIlp; ++r) {
+        const int i = i0 + r * nwarp;
+        if (i < K1) out[i] = bias[i] - (logf(sm[r]) + mx[r]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
                                                        const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
                                                        int K, int iters, float inf, float* __restrict__ out) {
   extern __shared__ float sm[];
@@ -148,27 +193,9 @@ __global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__
   }
   __syncthreads();
   for (int it = 0; it < iters; ++it) {
-    // u_i = log_mu_i - logsumexp_j(ps_ij + v_j)
-    for (int i = warp; i < K1; i += nwarp) {
-      float mx = -INFINITY;
-      for (int j = lane; j < K1; j += 32) mx = fmaxf(mx, ps[i * K1 + j] + v[j]);
-      mx = warp_max(mx);
-      float s = 0.f;
-      for (int j = lane; j < K1; j += 32) s += expf(ps[i * K1 + j] + v[j] - mx);
-      s = warp_sum(s);
-      if (lane == 0) u[i] = lmu[i] - (logf(s) + mx);
-    }
+    sinkhorn_lse_pass(ps, K1, K1, 1, v, lmu, u, warp, nwarp, lane);  // u_i = log_mu_i - logsumexp_j(ps_ij + v_j)
     __syncthreads();
-    // v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
-    for (int j = warp; j < K1; j += nwarp) {
-      float mx = -INFINITY;
-      for (int i = lane; i < K1; i += 32) mx = fmaxf(mx, ps[i * K1 + j] + u[i]);
-      mx = warp_max(mx);
-      float s = 0.f;
-      for (int i = lane; i < K1; i += 32) s += expf(ps[i * K1 + j] + u[i] - mx);
-      s = warp_sum(s);
-      if (lane == 0) v[j] = lnu[j] - (logf(s) + mx);
-    }
+    sinkhorn_lse_pass(ps, K1, 1, K1, u, lnu, v, warp, nwarp, lane);  // v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
     __syncthreads();
   }
   float* o = out + (long long)b * K1 * K1;
@@ -245,7 +272,7 @@ extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const 
   const size_t smem = ((size_t)(K + 1) * (K + 1) + 4 * (size_t)(K + 1)) * sizeof(float);
   if (smem > 220 * 1024) return GR_ERR_CAPACITY;
   if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sinkhorn_kernel<<<P, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K, num_iterations, inf, out);
+  sinkhorn_kernel<<<P, kSinkThreads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K, num_iterations, inf, out);
   GR_CHECK_LAUNCH("sinkhorn_kernel");
   return GR_OK;
 }
