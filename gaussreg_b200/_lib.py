@@ -29,6 +29,7 @@ _SIGNATURES = {
                        _vp, _i64, _i64, _i32, _vp]),
     "gr_set_gemm_mode": (None, [_i32]),
     "gr_get_gemm_mode": (_i32, []),
+    "gr_last_gemm_path": (_i32, []),
     "gr_kpconv_aggregate_workspace_size": (_sz, [_i64]),
     "gr_kpconv_aggregate": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "gr_group_norm_workspace_size": (_sz, [_i64, _i32]),

@@ -156,7 +156,8 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
   if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
   if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
-  return launch_sgemm<32, 32, 8, 4, 4>(p, batch, transb, st);  // superpoint-sized problems: fill the SMs with small tiles
+  // superpoint-sized problems: fill the SMs with small tiles; a deep K tile keeps enough bytes in flight per barrier
+  return launch_sgemm<32, 32, 32, 4, 4>(p, batch, transb, st);
 }
 
 // gemm_tc.cu
@@ -165,6 +166,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
                 const float* residual, long long ldr, long long sR, int act, cudaStream_t st);
 
 static int g_gemm_mode = -1;  // 0: SIMT only, 1: tensor cores where the problem qualifies
+static thread_local int g_last_path = 0;
 
 }  // namespace gr
 
@@ -180,6 +182,9 @@ extern "C" int gr_get_gemm_mode(void) {
   return g_gemm_mode;
 }
 
+/* 1 if the calling thread's last gr_gemm ran on the tensor cores (tcgen05), 0 if on the FFMA kernel. */
+extern "C" int gr_last_gemm_path(void) { return g_last_path; }
+
 extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
                        int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
                        const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
@@ -190,8 +195,9 @@ extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float
   if (trans_b && gr_get_gemm_mode() == 1) {
     const int rc = gemm_tf32x3(A, lda, strideA, B, ldb, strideB, C, ldc, strideC, M, N, K, batch, alpha, bias, row_div, residual,
                                ldr, strideR, act, static_cast<cudaStream_t>(stream));
-    if (rc <= 0) return rc;
+    if (rc <= 0) { g_last_path = 1; return rc; }
   }
+  g_last_path = 0;
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr;

@@ -1,0 +1,34 @@
+"""Multi-GPU sharding of scene pairs: pairs are independent, rank r owns pairs
+r, r+W, r+2W, ...; the only collective is one all-gather of the (P_local,4,4) transforms (NCCL over NVLink on
+GPUs, gloo in the CPU tests).  The reference has no inference-time parallelism (test.py:146-161 is a
+single-process loop), so this replaces nothing and adds one collective per batch."""
+import torch
+import torch.distributed as dist
+
+
+def shard_pairs(n_pairs, rank, world):
+    """Indices of the pairs rank `rank` processes (static round-robin: all pairs cost the same)."""
+    return list(range(rank, n_pairs, world))
+
+
+def local_count(n_pairs, rank, world):
+    return len(range(rank, n_pairs, world))
+
+
+def gather_transforms(local_transforms, n_pairs, rank=None, world=None):
+    """All-gather per-rank (P_local,4,4) transforms and re-interleave them into pair order -> (n_pairs,4,4).
+
+    Every rank pads to ceil(n_pairs / world) rows so that one fixed-size all_gather_into_tensor suffices."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        return local_transforms
+    per = (n_pairs + world - 1) // world
+    buf = torch.zeros((per, 4, 4), dtype=local_transforms.dtype, device=local_transforms.device)
+    buf[: local_transforms.shape[0]] = local_transforms
+    out = torch.empty((world * per, 4, 4), dtype=buf.dtype, device=buf.device)
+    dist.all_gather_into_tensor(out, buf)
+    # out[r*per + i] is pair r + i*world
+    return out.view(world, per, 4, 4).transpose(0, 1).reshape(world * per, 4, 4)[:n_pairs].contiguous()

@@ -94,6 +94,8 @@ int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_
  * (env GAUSSREG_GEMM=simt|tc selects the initial mode). */
 void gr_set_gemm_mode(int mode);
 int gr_get_gemm_mode(void);
+/* 1 if the calling thread's last gr_gemm ran on the tensor cores, 0 if on the FFMA kernel (bench bookkeeping). */
+int gr_last_gemm_path(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  KPConv gather + kernel-point correlation (geotransformer/modules/kpconv/kpconv.py:79-122).
