@@ -27,6 +27,7 @@ _SIGNATURES = {
     "gr_radius_neighbors": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     "gr_gemm": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                        _vp, _i64, _i64, _i32, _vp]),
+    "gr_linear_packed": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "gr_set_gemm_mode": (None, [_i32]),
     "gr_get_gemm_mode": (_i32, []),
     "gr_last_gemm_path": (_i32, []),

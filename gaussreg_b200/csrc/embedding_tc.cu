@@ -29,10 +29,17 @@ constexpr int kEmbThreads = 288;
 // K-major SWIZZLE_128B byte order the tensor core reads.
 __global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out) {
   const int nt = blockIdx.y, kb = blockIdx.x;
-  unsigned char* base = reinterpret_cast<unsigned char*>(out) + ((size_t)(nt * (K / 32) + kb)) * 2 * kEmbTile;
+  const int kblocks = (K + 31) / 32;
+  unsigned char* base = reinterpret_cast<unsigned char*>(out) + ((size_t)(nt * kblocks + kb)) * 2 * kEmbTile;
   for (int ch = threadIdx.x; ch < 128 * 8; ch += blockDim.x) {
     const int r = ch >> 3, c = ch & 7;
-    const float4 v = *reinterpret_cast<const float4*>(W + (size_t)(nt * 128 + r) * K + kb * 32 + c * 4);
+    const int gn = nt * 128 + r, gk = kb * 32 + c * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // rows / columns beyond (N, K) are zero padding
+    if (gn < N) {
+      const float* src = W + (size_t)gn * K + gk;
+      if (gk + 3 < K) { v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3]; }
+      else { if (gk < K) v.x = src[0]; if (gk + 1 < K) v.y = src[1]; if (gk + 2 < K) v.z = src[2]; }
+    }
     float4 hi, lo;
     hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
     lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
@@ -188,10 +195,11 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
 
 using namespace gr;
 
-/* Packs a (N,K) fp32 weight (N % 128 == 0, K % 32 == 0) into the tensor-core operand format: 2*N*K floats. */
+/* Packs a (N,K) fp32 weight into the tensor-core operand format, zero-padded to 256 rows x 32 columns:
+ * out holds 2 * roundup(N,256) * roundup(K,32) floats. */
 extern "C" int gr_pack_weight_tf32x3(const float* W, int N, int K, float* out, void* stream) {
-  if (N <= 0 || K <= 0 || N % 128 != 0 || K % 32 != 0 || !W || !out) return GR_ERR_BAD_ARG;
-  dim3 grid(K / 32, N / 128);
+  if (N <= 0 || K <= 0 || !W || !out) return GR_ERR_BAD_ARG;
+  dim3 grid((K + 31) / 32, ((N + 255) / 256) * 2);
   tc::pack_weight_tf32x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, N, K, out);
   GR_CHECK_LAUNCH("pack_weight_tf32x3_kernel");
   return GR_OK;

@@ -163,7 +163,7 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
 // gemm_tc.cu
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
-                const float* residual, long long ldr, long long sR, int act, cudaStream_t st);
+                const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed);
 
 static int g_gemm_mode = -1;  // 0: SIMT only, 1: tensor cores where the problem qualifies
 static thread_local int g_last_path = 0;
@@ -185,16 +185,16 @@ extern "C" int gr_get_gemm_mode(void) {
 /* 1 if the calling thread's last gr_gemm ran on the tensor cores (tcgen05), 0 if on the FFMA kernel. */
 extern "C" int gr_last_gemm_path(void) { return g_last_path; }
 
-extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
-                       int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
-                       const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
-                       int act, void* stream) {
+static int gemm_dispatch(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
+                         int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
+                         const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
+                         int act, void* stream, const float* B_packed) {
   if (M < 0 || N < 0 || K < 0 || batch < 0 || act < 0 || act > 2) return GR_ERR_BAD_ARG;
   if (M == 0 || N == 0 || batch == 0) return GR_OK;
   if (!A || !B || !C) return GR_ERR_BAD_ARG;
   if (trans_b && gr_get_gemm_mode() == 1) {
     const int rc = gemm_tf32x3(A, lda, strideA, B, ldb, strideB, C, ldc, strideC, M, N, K, batch, alpha, bias, row_div, residual,
-                               ldr, strideR, act, static_cast<cudaStream_t>(stream));
+                               ldr, strideR, act, static_cast<cudaStream_t>(stream), B_packed);
     if (rc <= 0) { g_last_path = 1; return rc; }
   }
   g_last_path = 0;
@@ -204,4 +204,21 @@ extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float
   p.sA = strideA; p.sB = strideB; p.sC = strideC; p.sR = strideR;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
   return sgemm(p, batch, trans_b != 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
+                       int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
+                       const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
+                       int act, void* stream) {
+  return gemm_dispatch(A, lda, strideA, B, ldb, strideB, trans_b, C, ldc, strideC, M, N, K, batch, alpha, bias, row_div, residual,
+                       ldr, strideR, act, stream, nullptr);
+}
+
+/* C = act(alpha * A . W^T / row_div + bias + residual) for a static weight W (N,K): `W_packed` is its
+ * gr_pack_weight_tf32x3 image (tensor-core operand format), `W` the plain matrix (used when the problem is routed
+ * to the FFMA kernel). */
+extern "C" int gr_linear_packed(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_packed, float* C,
+                                int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* row_div,
+                                const float* residual, int64_t ldr, int act, void* stream) {
+  return gemm_dispatch(A, lda, 0, W, ldw, 0, 1, C, ldc, 0, M, N, K, 1, alpha, bias, row_div, residual, ldr, 0, act, stream, W_packed);
 }

@@ -35,47 +35,60 @@ struct Params {
   float alpha;
   int act;
   int k_split;  // 0: blockIdx.z is a batch index; > 0: blockIdx.z selects the K slice [z*k_split, (z+1)*k_split)
+  // optional: B pre-split into hi/lo TF32 tiles in the shared-memory byte order (gr_pack_weight_tf32x3, padded to
+  // 128 rows x 32 k): the B tiles then arrive by bulk async copies instead of being converted by the producers
+  const float* B_packed;
+  int packed_kblocks;  // ceil(K / 32) of the packed matrix
 };
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 2);  // BN = 64: 2 stages so that two CTAs share an SM
   static constexpr int kABytes = BM * BK * 4;      // one A tile (hi or lo)
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// load `rows` x 32 fp32 (K-major, ld elements) into the swizzled hi / lo tiles
+// Operand tile = ROWS x 32 fp32 (K-major, ld elements).  The producers first issue all their 16-byte global loads
+// (tile_load), and convert / store them one k-block later (tile_store), so the L2/HBM latency of k-block kb+1
+// overlaps the TF32 split of k-block kb.
 template <int ROWS>
-__device__ __forceinline__ void produce_tile(const float* __restrict__ g, long long ld, int row0, int row_limit, int k0, int K,
-                                             unsigned char* s_hi, unsigned char* s_lo, int tid) {
-  constexpr int kChunks = ROWS * 8;                       // 16-byte chunks
-  constexpr int kPer = kChunks / kProducerThreads;
-  float4 v[kPer];
+struct TileRegs { float4 v[ROWS * 8 / kProducerThreads]; };
+
+template <int ROWS>
+__device__ __forceinline__ void tile_load(TileRegs<ROWS>& t, const float* __restrict__ g, long long ld, int row0, int row_limit,
+                                          int k0, int K, int tid) {
+  constexpr int kPer = ROWS * 8 / kProducerThreads;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     const int ch = tid + i * kProducerThreads;
     const int r = ch >> 3, c = ch & 7;
     const int gr = row0 + r, gk = k0 + c * 4;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < row_limit && gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(g + (long long)gr * ld + gk));
+    t.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < row_limit && gk < K) t.v[i] = __ldg(reinterpret_cast<const float4*>(g + (long long)gr * ld + gk));
   }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void tile_store(const TileRegs<ROWS>& t, unsigned char* s_hi, unsigned char* s_lo, int tid) {
+  constexpr int kPer = ROWS * 8 / kProducerThreads;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     const int ch = tid + i * kProducerThreads;
     const int r = ch >> 3, c = ch & 7;
     const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    const float4 v = t.v[i];
     float4 hi, lo;
-    hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
-    lo.x = tf32_rna(v[i].x - hi.x); lo.y = tf32_rna(v[i].y - hi.y); lo.z = tf32_rna(v[i].z - hi.z); lo.w = tf32_rna(v[i].w - hi.w);
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
     *reinterpret_cast<float4*>(s_hi + off) = hi;
     *reinterpret_cast<float4*>(s_lo + off) = lo;
   }
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel(Params p) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,14 +124,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Params p) {
 
   if (warp < 8) {
     // ------------------------------------------------------------------ producers
+    TileRegs<BM> ra;
+    TileRegs<BN> rb;
+    const bool packed = p.B_packed != nullptr;
+    tile_load<BM>(ra, A, p.lda, m0, p.M, kbeg, kend, tid);
+    if (!packed) tile_load<BN>(rb, B, p.ldb, n0, p.N, kbeg, kend, tid);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % C::kStages;
       if (kb >= C::kStages) mbar_wait(empty_bar(s), ((kb / C::kStages) - 1) & 1);
       unsigned char* st = smem + s * C::kStageBytes;
-      produce_tile<BM>(A, p.lda, m0, p.M, kbeg + kb * BK, kend, st, st + C::kABytes, tid);
-      produce_tile<BN>(B, p.ldb, n0, p.N, kbeg + kb * BK, kend, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
+      if (packed && tid == 0) {
+        // packed layout: tile (nt, kblock) -> [hi 16 KB][lo 16 KB], nt over 128-row groups; this CTA needs BN rows
+        constexpr uint32_t kRowBytes = BN < 128 ? BN * 128 : 128 * 128;  // bytes per copy (rows x 128 B)
+        constexpr int kCopies = BN / 128 > 0 ? BN / 128 : 1;
+        mbar_expect_tx(full_bar(s), 2u * kCopies * kRowBytes);
+        const int kblock = (kbeg / BK) + kb;
+        const uint32_t b_hi_s = smem_u32(st + 2 * C::kABytes), b_lo_s = b_hi_s + C::kBBytes;
+#pragma unroll
+        for (int c = 0; c < kCopies; ++c) {
+          const int row0 = n0 + c * 128;               // first B row of this copy
+          const int nt = row0 >> 7, rin = row0 & 127;   // packed tile and row offset inside it (multiple of 8)
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.B_packed) +
+                                     ((size_t)nt * p.packed_kblocks + kblock) * (2 * 16384) + (size_t)rin * 128;
+          bulk_copy_g2s(b_hi_s + c * 16384, src, kRowBytes, full_bar(s));
+          bulk_copy_g2s(b_lo_s + c * 16384, src + 16384, kRowBytes, full_bar(s));
+        }
+      }
+      TileRegs<BM> ra_next;
+      TileRegs<BN> rb_next;
+      if (kb + 1 < nkb) {  // prefetch the next k-block before converting this one
+        tile_load<BM>(ra_next, A, p.lda, m0, p.M, kbeg + (kb + 1) * BK, kend, tid);
+        if (!packed) tile_load<BN>(rb_next, B, p.ldb, n0, p.N, kbeg + (kb + 1) * BK, kend, tid);
+      }
+      tile_store<BM>(ra, st, st + C::kABytes, tid);
+      if (!packed) tile_store<BN>(rb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(full_bar(s));
+      if (kb + 1 < nkb) {
+        ra = ra_next;
+        if (!packed) rb = rb_next;
+      }
     }
     // ------------------------------------------------------------------ epilogue
     mbar_wait(accum_bar, 0);
@@ -269,7 +314,7 @@ static float* splitk_scratch(cudaStream_t st, size_t bytes) {
 // Returns GR_OK when the tensor-core path ran, 1 when the problem does not qualify (caller falls back to SIMT).
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
-                const float* residual, long long ldr, long long sR, int act, cudaStream_t st) {
+                const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed) {
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
@@ -285,6 +330,8 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.sA = sA; p.sB = sB; p.sC = sC; p.sR = sR;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act; p.k_split = 0;
+  p.B_packed = (batch == 1) ? B_packed : nullptr;
+  p.packed_kblocks = (K + 31) / 32;
   // The tensor core's fp32 accumulation truncates, so the error grows linearly with the number of MMA steps
   // chained into one accumulator.  Long K is therefore cut into slices of kSlice, each accumulated in its own
   // TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.

@@ -60,9 +60,22 @@ def gemm_batched(a_ptr, lda, sa, b_ptr, ldb, sb, trans_b, c_ptr, ldc, sc, M, N, 
     _lib.check(st, "gemm_batched")
 
 
-def linear(x, weight, bias=None, act=None, residual=None, out=None):
-    """nn.Linear forward: x (rows, in) @ weight (out, in)^T + bias."""
-    return gemm(x, weight, True, bias=bias, act=act, residual=residual, out=out)
+def linear(x, weight, bias=None, act=None, residual=None, out=None, row_div=None):
+    """nn.Linear forward: x (rows, in) @ weight (out, in)^T + bias.  Large products take the tensor-core kernel
+    with the weight pre-packed (cached on the parameter)."""
+    M, K = x.shape
+    N = weight.shape[0]
+    if M < 2048 or not weight.is_contiguous() or _lib.lib().gr_get_gemm_mode() != 1:
+        return gemm(x, weight, True, bias=bias, act=act, residual=residual, out=out, row_div=row_div)
+    assert x.stride(1) == 1 and weight.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=_F32, device=x.device)
+    st = _lib.lib().gr_linear_packed(x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
+                                     packed_weight_tf32x3(weight).data_ptr(), out.data_ptr(), out.stride(0), M, N, K, 1.0,
+                                     _ptr(bias), _ptr(row_div), _ptr(residual),
+                                     residual.stride(0) if residual is not None else 0, ACT[act], _stream())
+    _lib.check(st, "linear_packed")
+    return out
 
 
 def kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_points, sigma):
@@ -104,7 +117,7 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_
     A, row_div = kpconv_aggregate(s_feats, q_points, s_points, neighbor_indices, kernel_points, sigma)
     K, C, Co = weights.shape
     if _lib.lib().gr_get_gemm_mode() == 1 and (K * C) % 4 == 0:
-        return gemm(A, _kmajor_weights(weights), True, bias=bias, row_div=row_div)
+        return linear(A, _kmajor_weights(weights), bias=bias, row_div=row_div)
     return gemm(A, weights.view(K * C, Co), False, bias=bias, row_div=row_div)
 
 
@@ -227,7 +240,7 @@ def packed_weight_tf32x3(weight):
     cached = getattr(weight, "_gr_packed", None)
     if cached is None or cached[0] != weight._version or cached[1].device != weight.device:
         N, K = weight.shape
-        out = torch.empty((2 * N * K,), dtype=_F32, device=weight.device)
+        out = torch.empty((2 * ((N + 255) // 256 * 256) * ((K + 31) // 32 * 32),), dtype=_F32, device=weight.device)
         st = _lib.lib().gr_pack_weight_tf32x3(weight.detach().contiguous().data_ptr(), N, K, out.data_ptr(), _stream())
         _lib.check(st, "pack_weight_tf32x3")
         cached = (weight._version, out)

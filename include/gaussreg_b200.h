@@ -92,6 +92,11 @@ int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_
             const float* row_div, const float* residual, int64_t ldr, int64_t strideR, int act, void* stream);
 /* 0 = fp32 FFMA kernels only; 1 (default) = tcgen05 kind::tf32 with the 3xTF32 split for large trans_b products
  * (env GAUSSREG_GEMM=simt|tc selects the initial mode). */
+/* Same product for a static weight W (N,K) whose gr_pack_weight_tf32x3 image is supplied: the weight tiles reach
+ * shared memory by bulk async copies (no conversion work in the kernel). */
+int gr_linear_packed(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_packed, float* C, int64_t ldc,
+                     int M, int N, int K, float alpha, const float* bias, const float* row_div, const float* residual,
+                     int64_t ldr, int act, void* stream);
 void gr_set_gemm_mode(int mode);
 int gr_get_gemm_mode(void);
 /* 1 if the calling thread's last gr_gemm ran on the tensor cores, 0 if on the FFMA kernel (bench bookkeeping). */
@@ -138,7 +143,7 @@ int gr_sinusoid_rows(const float* x, int64_t rows, const float* div_term, int n_
 int gr_embedding_combine(const float* D, const float* A, int64_t rows, int C, int k, float* out, void* stream);
 /* T1 fused on the tensor cores (geotransformer.py:57-72 in one kernel): sinusoid operand tiles are generated in
  * shared memory, proj_d / proj_a run as tcgen05 3xTF32 MMAs into four TMEM accumulators, bias + max_k + sum in the
- * epilogue.  Weights must first be packed with gr_pack_weight_tf32x3 ((N,K) -> 2*N*K floats, N%128==0, K%32==0). */
+ * epilogue.  Weights must first be packed with gr_pack_weight_tf32x3 ((N,K) -> 2*roundup(N,256)*roundup(K,32) floats). */
 int gr_pack_weight_tf32x3(const float* W, int N, int K, float* out, void* stream);
 int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t rows, int angle_k, const float* div_term,
                                  int hidden_dim, const float* wd_packed, const float* wa_packed, const float* bias_d,

@@ -320,3 +320,13 @@ def test_gemm_tensor_core_3xtf32_vs_fp32(M, N, K):
     # are summed in fp32), vs ~2e-7 for the FFMA kernel
     assert rel_l2(plain.cpu(), ref.cpu()) < 5e-6
     assert rel_l2(tc.cpu(), simt.cpu()) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (5000, 384, 480), (3000, 64, 960), (2500, 2048, 512), (2048, 96, 36), (60000, 32, 480)])
+def test_linear_with_packed_weights(M, N, K):
+    """Static weights pre-packed into the tensor-core operand format (bulk-copied B tiles) == plain product."""
+    x, w, b = _rand(M, K, seed=21).cuda(), _rand(N, K, seed=22).cuda(), _rand(N, seed=23).cuda()
+    div = (torch.rand(M, generator=torch.Generator().manual_seed(4)) * 3 + 1).cuda()
+    ref = (x.double() @ w.double().t()) / div.double()[:, None] + b.double()
+    got = ops.linear(x, w, bias=b, row_div=div)
+    assert rel_l2(got.cpu(), ref.cpu()) < 5e-6
