@@ -31,28 +31,33 @@ __global__ void __launch_bounds__(256) rpe_scores_softmax_kernel(const float* __
 #pragma unroll
   for (int h = 0; h < H; ++h) qbh[h] = qb[(long long)h * N + n];
 
+  // one thread per key m: the thread walks its own embedding row e[n,m,:] and key row k[m,:] sequentially
+  // (float4), U / q come from shared memory as warp broadcasts -> no cross-lane reduction at all
   const float* erow = emb + (long long)n * N * C;
-  for (int m = warp; m < N; m += nwarp) {
+  const int c4_per_head = DH >> 2;
+  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+    const float4* e4 = reinterpret_cast<const float4*>(erow + (long long)m * C);
+    const float4* k4 = reinterpret_cast<const float4*>(kmat + (long long)m * C);
     float accp[H], acce[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) { accp[h] = 0.f; acce[h] = 0.f; }
-    for (int c = lane; c < C; c += 32) {
-      const float e = erow[(long long)m * C + c];
-      const float kv = kmat[(long long)m * C + c];
-      const int hc = c / DH;
-      const float qv = sq[c];
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        accp[h] = fmaf(sU[h * C + c], e, accp[h]);
-        if (h == hc) acce[h] = fmaf(qv, kv, acce[h]);
+    for (int hc = 0; hc < H; ++hc) {
+      for (int i = 0; i < c4_per_head; ++i) {
+        const int c4 = hc * c4_per_head + i;
+        const float4 e = __ldg(e4 + c4);
+        const float4 kv = __ldg(k4 + c4);
+        const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * c4);
+        acce[hc] = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, fmaf(qv.z, kv.z, fmaf(qv.w, kv.w, acce[hc]))));
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float4 u = *reinterpret_cast<const float4*>(sU + h * C + 4 * c4);
+          accp[h] = fmaf(u.x, e.x, fmaf(u.y, e.y, fmaf(u.z, e.z, fmaf(u.w, e.w, accp[h]))));
+        }
       }
     }
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float sp = warp_sum(accp[h]);
-      const float se = warp_sum(acce[h]);
-      if (lane == 0) ss[h * N + m] = (se + (sp + qbh[h])) * scale;
-    }
+    for (int h = 0; h < H; ++h) ss[h * N + m] = (acce[h] + (accp[h] + qbh[h])) * scale;
   }
   __syncthreads();
   // softmax over m for each head
