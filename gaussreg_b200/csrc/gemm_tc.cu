@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {  // TMEM allocation (power of two >= 32 columns), owned by the MMA warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -127,8 +127,13 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
     TileRegs<BM> ra;
     TileRegs<BN> rb;
     const bool packed = p.B_packed != nullptr;
-    tile_load<BM>(ra, A, p.lda, m0, p.M, kbeg, kend, tid);
-    if (!packed) tile_load<BN>(rb, B, p.ldb, n0, p.N, kbeg, kend, tid);
+    // CTAs of different M-tiles walk the k-blocks in rotated order: at any instant they pull DIFFERENT weight tiles
+    // out of L2 instead of all hammering the same few L2 slices (the sum over k-blocks is order-independent per tile
+    // up to fp32 rounding, and stays deterministic)
+    const int rot = (int)(blockIdx.y % (unsigned)nkb);
+    auto kbr = [&](int kb) { int r = kb + rot; return r >= nkb ? r - nkb : r; };
+    tile_load<BM>(ra, A, p.lda, m0, p.M, kbeg + kbr(0) * BK, kend, tid);
+    if (!packed) tile_load<BN>(rb, B, p.ldb, n0, p.N, kbeg + kbr(0) * BK, kend, tid);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % C::kStages;
       if (kb >= C::kStages) mbar_wait(empty_bar(s), ((kb / C::kStages) - 1) & 1);
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
         constexpr uint32_t kRowBytes = BN < 128 ? BN * 128 : 128 * 128;  // bytes per copy (rows x 128 B)
         constexpr int kCopies = BN / 128 > 0 ? BN / 128 : 1;
         mbar_expect_tx(full_bar(s), 2u * kCopies * kRowBytes);
-        const int kblock = (kbeg / BK) + kb;
+        const int kblock = (kbeg / BK) + kbr(kb);
         const uint32_t b_hi_s = smem_u32(st + 2 * C::kABytes), b_lo_s = b_hi_s + C::kBBytes;
 #pragma unroll
         for (int c = 0; c < kCopies; ++c) {
@@ -153,8 +158,8 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
       TileRegs<BM> ra_next;
       TileRegs<BN> rb_next;
       if (kb + 1 < nkb) {  // prefetch the next k-block before converting this one
-        tile_load<BM>(ra_next, A, p.lda, m0, p.M, kbeg + (kb + 1) * BK, kend, tid);
-        if (!packed) tile_load<BN>(rb_next, B, p.ldb, n0, p.N, kbeg + (kb + 1) * BK, kend, tid);
+        tile_load<BM>(ra_next, A, p.lda, m0, p.M, kbeg + kbr(kb + 1) * BK, kend, tid);
+        if (!packed) tile_load<BN>(rb_next, B, p.ldb, n0, p.N, kbeg + kbr(kb + 1) * BK, kend, tid);
       }
       tile_store<BM>(ra, st, st + C::kABytes, tid);
       if (!packed) tile_store<BN>(rb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
@@ -176,15 +181,16 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
 #pragma unroll 1
     for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-      uint32_t r[32];
+      uint32_t r[32], rc[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
       if (m < p.M) {
         const int nbase = n0 + c0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = nbase + j;
-          float x = __uint_as_float(r[j]) * p.alpha;
+          float x = (__uint_as_float(r[j]) + __uint_as_float(rc[j])) * p.alpha;
           if (p.row_div) x = x / rd;
           if (n < p.N) {
             if (p.bias) x += p.bias[n];
@@ -222,9 +228,14 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
 #pragma unroll
         for (int k8 = 0; k8 < BK / 8; ++k8) {
           const uint32_t ko = k8 * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
-          umma_tf32(tmem_acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, (kb | k8) != 0 ? 1u : 0u);
-          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
-          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+          // two accumulators: columns [0,BN) take the hi*hi products, columns [BN,2BN) the small correction terms.
+          // The tensor core truncates on every accumulation, so keeping the large partial sum on a chain of K/8
+          // steps (instead of 3K/8) cuts its rounding error threefold; the correction sum is ~2^-11 smaller and
+          // its truncation is irrelevant.  The epilogue adds the two.
+          const uint32_t first = (kb | k8) != 0 ? 1u : 0u;
+          umma_tf32(tmem_acc + BN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
+          umma_tf32(tmem_acc + BN, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
         }
         umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
       }
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(2 * BN));
   }
 }
 
@@ -323,7 +334,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     // fills the machine better than 4 tensor-core CTAs
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * batch;
-    const long long slices = (batch == 1 && K > 384 && N % 4 == 0) ? (K + 255) / 256 : 1;
+    const long long slices = (batch == 1 && K > 1152 && N % 4 == 0) ? (K + 767) / 768 : 1;
     if (tiles * slices < 24) return 1;
   }
   tc::Params p;
@@ -335,7 +346,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   // The tensor core's fp32 accumulation truncates, so the error grows linearly with the number of MMA steps
   // chained into one accumulator.  Long K is therefore cut into slices of kSlice, each accumulated in its own
   // TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.
-  constexpr int kSlice = 256;
+  constexpr int kSlice = 768;
   if (batch == 1 && K > kSlice + kSlice / 2 && N % 4 == 0) {
     const int splits = (K + kSlice - 1) / kSlice;
     float* partial = splitk_scratch(st, (size_t)splits * M * N * sizeof(float));

@@ -97,41 +97,57 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh /* >= 32
   return t;
 }
 
+__device__ __forceinline__ float block_sum_float(float v, float* sh /* >= 32 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nw; ++w) t += sh[w];
+  return t;
+}
+
 // Weighted Procrustes over n correspondences, executed by a whole CTA.  Weights w_i >= 0.
 // procrustes.py:41-70: w <- w / (sum w + eps); centroids; H; SVD.  Result T (3x4 row-major) in shared memory.
+//
+// All sums are accumulated in fp32, as the reference does (torch.sum / bmm on float tensors).  This matters for
+// DEGENERATE patches (H numerically zero or rank one: three nearly coincident correspondences, vanishing weights):
+// there the reference's rotation is whatever the fp32 rounding noise in H dictates.  Accumulating H exactly (fp64)
+// would instead return a clean near-identity rotation for H ~ 0, and such a hypothesis can collect spuriously many
+// inliers whenever the true motion is small -- a systematic deviation from the reference's hypothesis selection
+// (observed on the textured3k golden).  Only the 3x3 factorisation itself runs in fp64.
 __device__ void block_procrustes(const float* __restrict__ src, const float* __restrict__ ref, const float* __restrict__ w, int n,
                                  float eps, double* sh, float* T_out /* shared, 12 */) {
-  double sw = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sw += (double)w[i];
-  sw = block_sum_double(sw, sh);
-  const float denom = (float)sw + eps;
-  double a[6] = {0, 0, 0, 0, 0, 0};
+  float* shf = reinterpret_cast<float*>(sh);
+  float sw = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sw += w[i];
+  sw = block_sum_float(sw, shf);
+  const float denom = sw + eps;
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float wi = w[i] / denom;
-    a[0] += (double)(src[3 * i] * wi); a[1] += (double)(src[3 * i + 1] * wi); a[2] += (double)(src[3 * i + 2] * wi);
-    a[3] += (double)(ref[3 * i] * wi); a[4] += (double)(ref[3 * i + 1] * wi); a[5] += (double)(ref[3 * i + 2] * wi);
+    a[0] += src[3 * i] * wi; a[1] += src[3 * i + 1] * wi; a[2] += src[3 * i + 2] * wi;
+    a[3] += ref[3 * i] * wi; a[4] += ref[3 * i + 1] * wi; a[5] += ref[3 * i + 2] * wi;
   }
-  double cen[6];
-  for (int k = 0; k < 6; ++k) cen[k] = block_sum_double(a[k], sh);
-  const float scx = (float)cen[0], scy = (float)cen[1], scz = (float)cen[2];
-  const float rcx = (float)cen[3], rcy = (float)cen[4], rcz = (float)cen[5];
-  double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float cen[6];
+  for (int k = 0; k < 6; ++k) cen[k] = block_sum_float(a[k], shf);
+  const float scx = cen[0], scy = cen[1], scz = cen[2];
+  const float rcx = cen[3], rcy = cen[4], rcz = cen[5];
+  float h[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float wi = w[i] / denom;
     const float sx = src[3 * i] - scx, sy = src[3 * i + 1] - scy, sz = src[3 * i + 2] - scz;
     const float rx = wi * (ref[3 * i] - rcx), ry = wi * (ref[3 * i + 1] - rcy), rz = wi * (ref[3 * i + 2] - rcz);
-    h[0] += (double)sx * rx; h[1] += (double)sx * ry; h[2] += (double)sx * rz;
-    h[3] += (double)sy * rx; h[4] += (double)sy * ry; h[5] += (double)sy * rz;
-    h[6] += (double)sz * rx; h[7] += (double)sz * ry; h[8] += (double)sz * rz;
+    h[0] += sx * rx; h[1] += sx * ry; h[2] += sx * rz;
+    h[3] += sy * rx; h[4] += sy * ry; h[5] += sy * rz;
+    h[6] += sz * rx; h[7] += sz * ry; h[8] += sz * rz;
   }
   double H[9];
-  for (int k = 0; k < 9; ++k) H[k] = block_sum_double(h[k], sh);
+  for (int k = 0; k < 9; ++k) H[k] = (double)block_sum_float(h[k], shf);
   if (threadIdx.x == 0) {
     const double sc[3] = {(double)scx, (double)scy, (double)scz}, rc[3] = {(double)rcx, (double)rcy, (double)rcz};
-#ifdef GR_DEBUG_PROCRUSTES
-    printf("denom %g sc %g %g %g rc %g %g %g\nH %g %g %g / %g %g %g / %g %g %g\n", denom, sc[0], sc[1], sc[2], rc[0], rc[1], rc[2],
-           H[0], H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]);
-#endif
     kabsch_from_H(H, sc, rc, T_out);
   }
   __syncthreads();

@@ -366,7 +366,8 @@ def correspondence_matrix(score_mat, ref_masks, src_masks, k, conf, mutual=True)
     return torch.logical_and(corr, mask)
 
 
-def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, cfg, taps=None):
+def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, cfg, taps=None,
+                              force_best=None):
     """local_global_registration.py:137-235 with the config of config.py:116-125
     (no dustbin, no global score, no correspondence limit)."""
     f = cfg["fine_matching"]
@@ -399,7 +400,7 @@ def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src
         Ts = weighted_procrustes(bs, br, bw)
         aligned = apply_transform(src_c.unsqueeze(0), Ts)
         inl = torch.linalg.norm(ref_c.unsqueeze(0) - aligned, dim=2) < radius
-        best = inl.sum(dim=1).argmax()
+        best = inl.sum(dim=1).argmax() if force_best is None else torch.as_tensor(force_best)  # test hook: alternative tie-break
         if taps is not None:
             taps["local_transforms"], taps["inlier_counts"], taps["best_index"] = Ts, inl.sum(dim=1), best
         cur = sc * inl[best].float()
