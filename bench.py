@@ -130,6 +130,10 @@ class OpProfiler:
                 work = 2.0 * a[10] * a[11] * a[12] * a[13]
                 shape = (a[10], a[11], a[12], a[13], a[6])
                 key = "gr_gemm[tcgen05]" if self._lib.gr_last_gemm_path() == 1 else "gr_gemm[ffma]"
+            elif name == "gr_linear_packed":  # (A,lda,W,ldw,Wp,C,ldc,M,N,K,...)
+                work = 2.0 * a[7] * a[8] * a[9]
+                shape = (a[7], a[8], a[9], 1, 1)
+                key = "gr_linear_packed[tcgen05]" if self._lib.gr_last_gemm_path() == 1 else "gr_linear_packed[ffma]"
             elif name == "gr_structure_embedding_fused":  # (d_idx, a_idx, rows, angle_k, div, hidden, ...)
                 work = 2.0 * a[2] * (1 + a[3]) * a[5] * a[5]
             self.records.append((key, s, e, work, shape))
@@ -286,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_value = world * args.steps / (e2e_ms / 1e3)
         top = max(per_op, key=per_op.get)
         # dominant kernels: the tcgen05 3xTF32 tensor-core kernels (gemm_tf32x3_kernel + structure_embedding_tc_kernel)
-        tc_keys = ["gr_gemm[tcgen05]", "gr_structure_embedding_fused"]
+        tc_keys = ["gr_gemm[tcgen05]", "gr_linear_packed[tcgen05]", "gr_structure_embedding_fused"]
         tc_ms = sum(per_op.get(k, 0.0) for k in tc_keys)
         tc_flop = sum(work.get(k, 0.0) for k in tc_keys)
         n_tc = sum(1 for r in lib.records if r[0] in tc_keys)

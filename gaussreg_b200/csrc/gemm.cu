@@ -139,6 +139,97 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams
   }
 }
 
+// Superpoint-sized products (M ~ 500): a 32x32 output tile per CTA, the K loop split over four 64-thread groups that
+// each own a private shared-memory tile, partial sums folded in a fixed order at the end.  Four times the loads in
+// flight per CTA: these products are pure latency (a few dozen CTAs of work), not throughput.
+template <bool TRANSB>
+__global__ void __launch_bounds__(256) sgemm_small_kernel(GemmParams p) {
+  constexpr int BM = 32, BN = 32, BK = 32, G = 4, NT = 64;
+  __shared__ __align__(16) float As[G][BK][BM + 4];
+  __shared__ __align__(16) float Bs[G][BK][BN + 4];
+  const int tid = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int tx = tid % 8, ty = tid / 8;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+  float* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = (p.K + BK - 1) / BK;
+  for (int t = grp; t < nk; t += G) {
+    const int k0 = t * BK;
+#pragma unroll
+    for (int i = 0; i < BM * BK / NT; ++i) {
+      const int e = tid + i * NT;
+      const int kk = e % BK, mm = e / BK;
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[grp][kk][mm] = (gm < p.M && gk < p.K) ? A[(long long)gm * p.lda + gk] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < BN * BK / NT; ++i) {
+      const int e = tid + i * NT;
+      if (TRANSB) {
+        const int kk = e % BK, nn = e / BK;
+        const int gn = n0 + nn, gk = k0 + kk;
+        Bs[grp][kk][nn] = (gn < p.N && gk < p.K) ? B[(long long)gn * p.ldb + gk] : 0.f;
+      } else {
+        const int nn = e % BN, kk = e / BN;
+        const int gn = n0 + nn, gk = k0 + kk;
+        Bs[grp][kk][nn] = (gn < p.N && gk < p.K) ? B[(long long)gk * p.ldb + gn] : 0.f;
+      }
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");  // named barrier of this 64-thread group
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[grp][kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[grp][kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+  }
+  // fold the four partial tiles: groups 1..3 park their accumulators in (their own) shared memory
+  __syncthreads();
+  float* park = &As[0][0][0];  // G*BK*(BM+4) floats >= 3 * 64 * 16
+  if (grp > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) park[((grp - 1) * 64 + tid) * 16 + i * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (grp != 0) return;
+#pragma unroll
+  for (int g = 0; g < G - 1; ++g)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += park[(g * 64 + tid) * 16 + i * 4 + j];
+  const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= p.M) continue;
+    const float rd = p.row_div ? p.row_div[gm] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= p.N) continue;
+      float v = acc[i][j] * p.alpha;
+      if (p.row_div) v = v / rd;
+      if (p.bias) v += p.bias[gn];
+      if (R) v += R[(long long)gm * p.ldr + gn];
+      C[(long long)gm * p.ldc + gn] = apply_act(v, p.act);
+    }
+  }
+}
+
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
@@ -156,8 +247,14 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
   if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
   if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
-  // superpoint-sized problems: fill the SMs with small tiles; a deep K tile keeps enough bytes in flight per barrier
-  return launch_sgemm<32, 32, 32, 4, 4>(p, batch, transb, st);
+  // superpoint-sized problems: small tiles, K split over four thread groups inside the CTA
+  {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
+    if (transb) sgemm_small_kernel<true><<<grid, 256, 0, st>>>(p);
+    else sgemm_small_kernel<false><<<grid, 256, 0, st>>>(p);
+    GR_CHECK_LAUNCH("sgemm_small_kernel");
+    return GR_OK;
+  }
 }
 
 // gemm_tc.cu

@@ -63,21 +63,24 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const float* __r
   }
 }
 
-// stats[g] = (mean, rstd); one warp per group, lanes stride over the block partials (fixed order)
-__global__ void __launch_bounds__(1024) groupnorm_finalize_kernel(const double2* __restrict__ partial, int nblk, int G, long long count,
-                                                                  float eps, float2* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  for (int g = threadIdx.x >> 5; g < G; g += (blockDim.x >> 5)) {
-    double s = 0.0, q = 0.0;
-    for (int b = lane; b < nblk; b += 32) { const double2 p = partial[(long long)b * G + g]; s += p.x; q += p.y; }
+// stats[g] = (mean, rstd); one CTA per group, fixed-order tree over the block partials
+__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const double2* __restrict__ partial, int nblk, int G, long long count,
+                                                                 float eps, float2* __restrict__ stats) {
+  __shared__ double shs[8], shq[8];
+  const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s = 0.0, q = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) { const double2 p = partial[(long long)b * G + g]; s += p.x; q += p.y; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) {
-      const double mean = s / (double)count;
-      double var = q / (double)count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-    }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) { shs[warp] = s; shq[warp] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0; q = 0.0;
+    for (int w = 0; w < 8; ++w) { s += shs[w]; q += shq[w]; }
+    const double mean = s / (double)count;
+    double var = q / (double)count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
 }
 
@@ -167,7 +170,7 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
   if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(groupnorm_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   groupnorm_partial_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
   GR_CHECK_LAUNCH("groupnorm_partial_kernel");
-  groupnorm_finalize_kernel<<<1, 1024, 0, st>>>(partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats);
+  groupnorm_finalize_kernel<<<groups, 256, 0, st>>>(partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats);
   GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
   const long long total4 = (long long)n_rows * (C / 4);
   const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
