@@ -305,6 +305,16 @@ def run_ours(args, rank, world, local_rank):
             "launches_per_step": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
             "flop_per_step_fp32_equiv": tc_flop, "share_of_step": tc_ms / max(sum(per_op.values()), 1e-9),
         }
+        t1_ms, t1_flop = per_op.get("gr_structure_embedding_fused", 0.0), work.get("gr_structure_embedding_fused", 0.0)
+        if t1_ms > 0:
+            n_t1 = sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused")
+            roofline["largest_single_kernel"] = {
+                "kernel": "structure_embedding_tc_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                "frac": t1_flop / (t1_ms * 1e-3) / 1e12 / peaks["tf_sustained"], "avg_launch_ms": t1_ms / max(n_t1, 1),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_full_structure_embedding_tc.csv
+                "traffic": 188.1e6, "traffic_source": "ncu --set full capture (N=479 superpoints), not re-measured live",
+                "algorithmic_bytes": 4.0 * (a_rows := int(t1_flop / n_t1 / (2.0 * 4 * 256 * 256))) * (256 + 4),
+            }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sd, impl, ccfg, limits = cpu_reference_setup()
