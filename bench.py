@@ -48,6 +48,8 @@ def cpu_reference_setup():
     from gaussreg_b200.model import create_model
     from oracle import neighbors as on
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     np.random.seed(0)
     sd = {k: v.clone() for k, v in create_model(make_cfg()).state_dict().items()}
@@ -192,7 +194,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ["NCCL_DEBUG_FILE"] = "/tmp/nccl_debug_%h_%p.log"
         dist.init_process_group("nccl", device_id=dev)
     lib = OpProfiler(_lib.lib())
     _lib._lib = lib  # route every call through the (disabled) profiler
@@ -308,12 +312,13 @@ def run_ours(args, rank, world, local_rank):
         t1_ms, t1_flop = per_op.get("gr_structure_embedding_fused", 0.0), work.get("gr_structure_embedding_fused", 0.0)
         if t1_ms > 0:
             n_t1 = sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused")
+            t1_rows = int(t1_flop / max(n_t1, 1) / (2.0 * 4 * 256 * 256))  # pair-rows per launch (N^2)
             roofline["largest_single_kernel"] = {
                 "kernel": "structure_embedding_tc_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                 "frac": t1_flop / (t1_ms * 1e-3) / 1e12 / peaks["tf_sustained"], "avg_launch_ms": t1_ms / max(n_t1, 1),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_full_structure_embedding_tc.csv
                 "traffic": 188.1e6, "traffic_source": "ncu --set full capture (N=479 superpoints), not re-measured live",
-                "algorithmic_bytes": 4.0 * (a_rows := int(t1_flop / n_t1 / (2.0 * 4 * 256 * 256))) * (256 + 4),
+                "algorithmic_bytes": 4.0 * t1_rows * (256 + 4),  # (N^2, 256) output + d/a indices
             }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -11,6 +11,8 @@
 //              fused epilogue -> st.global);
 //   warp 8     one elected thread issues the tcgen05.mma chain and tcgen05.commit's.
 // Stage hand-over is by mbarriers: full[s] (256 producer arrivals) / empty[s] (tcgen05.commit).
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -174,41 +176,61 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
     float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;  // split-K: sC = M*N, raw partial sums
     const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
-    const float rd = (p.row_div && m < p.M) ? p.row_div[m] : 1.f;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) &&
+                        (!R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+    // Each thread holds one accumulator ROW (TMEM lane); storing rows directly would make every warp store hit 32
+    // different lines.  The 32x32 chunk is therefore transposed through shared memory (the operand stages are free
+    // once accum_bar has fired): rows are written with a 36-float pitch, read back as 4 rows x 32 columns per warp
+    // instruction, so that global stores / residual loads are full 128-byte lines.
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
 #pragma unroll 1
     for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
       uint32_t r[32], rc[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
-      if (m < p.M) {
-        const int nbase = n0 + c0;
-        float v[32];
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nbase + j;
-          float x = (__uint_as_float(r[j]) + __uint_as_float(rc[j])) * p.alpha;
-          if (p.row_div) x = x / rd;
-          if (n < p.N) {
-            if (p.bias) x += p.bias[n];
-            if (R) x += R[(long long)m * p.ldr + n];
-          }
-          if (p.act == 1) x = fmaxf(x, 0.f);
-          else if (p.act == 2) x = x > 0.f ? x : 0.1f * x;
-          v[j] = x;
+      for (int j = 0; j < 32; j += 4) {
+        float4 v;
+        v.x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+        v.y = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]);
+        v.z = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]);
+        v.w = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]);
+        *reinterpret_cast<float4*>(stage + lane * 36 + j) = v;
+      }
+      __syncwarp();
+      const int nbase = n0 + c0;
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+      const int n = nbase + c4;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) {
+        if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
+        else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int row = rr + rsub;
+        const int m = m0 + q * 32 + row;
+        if (m >= p.M) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+        float x[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+        if (p.row_div) { const float rd = p.row_div[m]; x[0] /= rd; x[1] /= rd; x[2] /= rd; x[3] /= rd; }
+        x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
+        if (R) {
+          const float* rp = R + (long long)m * p.ldr + n;
+          if (vec_ok && n + 3 < p.N) { const float4 t = *reinterpret_cast<const float4*>(rp); x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w; }
+          else { for (int e = 0; e < 4; ++e) if (n + e < p.N) x[e] += rp[e]; }
         }
-        float* dst = Cp + (long long)m * p.ldc + nbase;
-        if (vec_ok && nbase + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nbase + j < p.N) dst[j] = v[j];
+        for (int e = 0; e < 4; ++e) {
+          if (p.act == 1) x[e] = fmaxf(x[e], 0.f);
+          else if (p.act == 2) x[e] = x[e] > 0.f ? x[e] : 0.1f * x[e];
         }
+        float* dst = Cp + (long long)m * p.ldc + n;
+        if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+        else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
       }
     }
     tc_fence_before();
@@ -322,6 +344,12 @@ static float* splitk_scratch(cudaStream_t st, size_t bytes) {
   return e.ptr;
 }
 
+static bool use_bn256() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_BN256"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 // Returns GR_OK when the tensor-core path ran, 1 when the problem does not qualify (caller falls back to SIMT).
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
@@ -334,7 +362,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     // fills the machine better than 4 tensor-core CTAs
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * batch;
-    const long long slices = (batch == 1 && K > 1152 && N % 4 == 0) ? (K + 767) / 768 : 1;
+    const long long slices = (batch == 1 && K > 1152 && N % 4 == 0) ? (K + 767) / 768 : 1;  // (estimate with the default slice)
     if (tiles * slices < 24) return 1;
   }
   tc::Params p;
@@ -346,7 +374,12 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   // The tensor core's fp32 accumulation truncates, so the error grows linearly with the number of MMA steps
   // chained into one accumulator.  Long K is therefore cut into slices of kSlice, each accumulated in its own
   // TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.
-  constexpr int kSlice = 768;
+  static int kSlice = 0;
+  if (kSlice == 0) {
+    const char* e = getenv("GAUSSREG_KSLICE");  // tuning knob (multiple of 32); default 768
+    kSlice = e ? atoi(e) : 768;
+    if (kSlice < 32 || kSlice % 32 != 0) kSlice = 768;
+  }
   if (batch == 1 && K > kSlice + kSlice / 2 && N % 4 == 0) {
     const int splits = (K + kSlice - 1) / kSlice;
     float* partial = splitk_scratch(st, (size_t)splits * M * N * sizeof(float));
@@ -354,7 +387,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     tc::Params q = p;
     q.C = partial; q.ldc = N; q.sC = (long long)M * N; q.bias = nullptr; q.row_div = nullptr; q.residual = nullptr;
     q.alpha = 1.f; q.act = 0; q.k_split = kSlice;
-    int rc = N > 128 ? tc::launch<256>(q, splits, st) : (N > 64 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
+    int rc = (N > 128 && use_bn256()) ? tc::launch<256>(q, splits, st) : (N > 64 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
     if (rc == GR_OK) {
       const long long total = (long long)M * (N / 4);
       tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);
@@ -363,7 +396,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     }
     return rc;
   }
-  if (N > 128) return tc::launch<256>(p, batch, st);
+  if (N > 128 && use_bn256()) return tc::launch<256>(p, batch, st);
   if (N > 64) return tc::launch<128>(p, batch, st);
   return tc::launch<64>(p, batch, st);
 }
