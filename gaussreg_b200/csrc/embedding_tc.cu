@@ -23,7 +23,8 @@ constexpr int kEmbStages = 3;
 constexpr int kEmbTile = kEmbBM * kEmbBK * 4;           // 16 KB (one hi or lo tile, A or B)
 constexpr int kEmbStageBytes = 4 * kEmbTile;            // A hi, A lo, B hi, B lo
 constexpr int kEmbSmem = kEmbStages * kEmbStageBytes + 1024 + 256;
-constexpr int kEmbThreads = 288;
+constexpr int kEmbProducers = 512;                       // 16 producer / epilogue warps
+constexpr int kEmbThreads = kEmbProducers + 32;          // + the MMA warp
 
 // W (N, K) row-major -> for every (n-tile of 128, k-block of 32): [hi tile 16 KB][lo tile 16 KB] in the
 // K-major SWIZZLE_128B byte order the tensor core reads.
@@ -49,6 +50,26 @@ __global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __
   }
 }
 
+// sin / cos with fp32 accuracy.  Half of the 128 sinusoid frequencies are so low that the argument stays below
+// 0.5 rad for every index the model produces: there a short Taylor polynomial (truncation error < 3e-10) replaces
+// the general routine and its range reduction.  The branch is warp-uniform except in one or two k-blocks.
+__device__ __forceinline__ void sincos_fp32(float a, float* s, float* c) {
+  if (fabsf(a) < 0.5f) {
+    const float a2 = a * a;
+    float ps = fmaf(a2, 2.7557319e-6f, -1.9841270e-4f);
+    ps = fmaf(ps, a2, 8.3333333e-3f);
+    ps = fmaf(ps, a2, -1.6666667e-1f);
+    *s = fmaf(a * a2, ps, a);
+    float pc = fmaf(a2, -2.7557319e-7f, 2.4801587e-5f);
+    pc = fmaf(pc, a2, -1.3888889e-3f);
+    pc = fmaf(pc, a2, 4.1666667e-2f);
+    pc = fmaf(pc, a2, -0.5f);
+    *c = fmaf(pc, a2, 1.0f);
+  } else {
+    sincosf(a, s, c);
+  }
+}
+
 __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
@@ -71,11 +92,12 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
 
   if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
   if (tid == 0) {
-    for (int s = 0; s < kEmbStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kEmbStages; ++s) { mbar_init(full_bar(s), kEmbProducers); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  constexpr int kMmaWarp = kEmbProducers / 32;
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -84,9 +106,9 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < kMmaWarp) {
     // ---------------------------------------------------------------- producers: sinusoid operand tiles
-    const int row = tid >> 1, h16 = tid & 1;  // two threads per row, 16 consecutive k each (8 sin/cos pairs)
+    const int row = tid >> 2, h8 = tid & 3;  // four threads per row, 8 consecutive k each (4 sin/cos pairs)
     const long long r = r0 + row;
     const bool valid = r < rows;
     float xg[4] = {0.f, 0.f, 0.f, 0.f};  // embedding indices of this row for d, a0, a1, a2
@@ -106,13 +128,13 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
       }
       const float x = g == 0 ? xg[0] : (g == 1 ? xg[1] : (g == 2 ? xg[2] : xg[3]));
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {  // 4 chunks of 16 B = 2 (sin, cos) pairs each
-        const int c = h16 * 4 + jj;
+      for (int jj = 0; jj < 2; ++jj) {  // 2 chunks of 16 B = 2 (sin, cos) pairs each
+        const int c = h8 * 2 + jj;
         const int i0 = kb * 16 + c * 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-          sincosf(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
-          sincosf(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          sincos_fp32(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+          sincos_fp32(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
         }
         float4 hi, lo;
         hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
@@ -127,10 +149,12 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
     // ---------------------------------------------------------------- epilogue
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const long long rr = r0 + q * 32 + lane;
-#pragma unroll 1
-    for (int c0 = half * (kEmbBN / 2); c0 < (half + 1) * (kEmbBN / 2); c0 += 32) {
+    const int q = warp & 3, cgrp = warp >> 2;  // TMEM lane quarter, 32-column group (16 warps cover 4 x 4 chunks)
+    // accumulator rows live one per thread (TMEM lane); transpose each 32x32 chunk through shared memory (the operand
+    // stages are free now) so that the global stores are full 128-byte lines instead of 32 scattered 16-byte pieces
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    {
+      const int c0 = cgrp * 32;
       const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       uint32_t t[32];
       float mx[32];
@@ -143,18 +167,25 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
         for (int j = 0; j < 32; ++j) mx[j] = fmaxf(mx[j], __uint_as_float(t[j]));
       }
       tmem_ld32(lane_addr, t);
-      if (rr < rows) {
-        const int nbase = nhalf * kEmbBN + c0;
-        float* dst = out + rr * kEmbC + nbase;
+      const int nbase = nhalf * kEmbBN + c0;
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          o.x = (__uint_as_float(t[j]) + bias_d[nbase + j]) + (mx[j] + bias_a[nbase + j]);
-          o.y = (__uint_as_float(t[j + 1]) + bias_d[nbase + j + 1]) + (mx[j + 1] + bias_a[nbase + j + 1]);
-          o.z = (__uint_as_float(t[j + 2]) + bias_d[nbase + j + 2]) + (mx[j + 2] + bias_a[nbase + j + 2]);
-          o.w = (__uint_as_float(t[j + 3]) + bias_d[nbase + j + 3]) + (mx[j + 3] + bias_a[nbase + j + 3]);
-          *reinterpret_cast<float4*>(dst + j) = o;
-        }
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = (__uint_as_float(t[j]) + bias_d[nbase + j]) + (mx[j] + bias_a[nbase + j]);
+        o.y = (__uint_as_float(t[j + 1]) + bias_d[nbase + j + 1]) + (mx[j + 1] + bias_a[nbase + j + 1]);
+        o.z = (__uint_as_float(t[j + 2]) + bias_d[nbase + j + 2]) + (mx[j + 2] + bias_a[nbase + j + 2]);
+        o.w = (__uint_as_float(t[j + 3]) + bias_d[nbase + j + 3]) + (mx[j + 3] + bias_a[nbase + j + 3]);
+        *reinterpret_cast<float4*>(stage + lane * 36 + j) = o;
+      }
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+      for (int r4 = 0; r4 < 32; r4 += 4) {
+        const int row = r4 + rsub;
+        const long long rr = r0 + q * 32 + row;
+        if (rr < rows)
+          *reinterpret_cast<float4*>(out + rr * kEmbC + nbase + c4) = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
       }
     }
     tc_fence_before();
@@ -184,7 +215,7 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(512));
   }
