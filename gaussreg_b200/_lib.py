@@ -17,6 +17,12 @@ _i32 = ctypes.c_int
 _f32 = ctypes.c_float
 _sz = ctypes.c_size_t
 
+class LayerWeights(ctypes.Structure):
+    """gr_layer_weights (include/gaussreg_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("wq", "bq", "wk", "bk", "wv", "bv", "wp", "bp", "wo", "bo", "ln1_g", "ln1_b",
+                                               "w1", "b1", "w2", "b2", "ln2_g", "ln2_b")] + [("is_self", ctypes.c_int)]
+
+
 _SIGNATURES = {
     "gr_version": (ctypes.c_char_p, []),
     "gr_last_error": (ctypes.c_char_p, []),
@@ -49,6 +55,8 @@ _SIGNATURES = {
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),
     "gr_l2_normalize_rows": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),
+    "gr_conditional_transformer_workspace_size": (_sz, [_i32, _i32, _i32, _i32]),
+    "gr_conditional_transformer": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "gr_superpoint_matching_workspace_size": (_sz, [_i32, _i32, _i32]),
     "gr_superpoint_matching": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_sinkhorn": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),

@@ -111,30 +111,45 @@ __global__ void match_decode_kernel(const unsigned long long* __restrict__ keys,
 constexpr int kSinkThreads = 512;
 constexpr int kSinkIlp = 4;
 
-// out[i] = bias[i] - logsumexp_j(ps[i*si + j*sj] + add[j]) for the lines owned by this warp
+// out[i] = bias[i] - logsumexp_j(ps[i*si + j*sj] + add[j]) for the lines owned by this warp.
+// The log-sum-exp shift is the line's PREVIOUS log-sum-exp (bias[i] - out[i]) instead of a freshly computed
+// maximum: the iterates move slowly and all scores are O(10), so exp(x - shift) can neither overflow nor flush a
+// whole line to zero, and the max pass (half of the work) disappears.  The first iteration uses the true maximum.
+// Fully masked lines (bias = -inf marker): every term equals -inf in fp32, the reference's result is exactly 0.
+template <bool FIRST>
 __device__ __forceinline__ void sinkhorn_lse_pass(const float* __restrict__ ps, int K1, int si, int sj,
                                                   const float* __restrict__ add, const float* __restrict__ bias,
-                                                  float* __restrict__ out, int warp, int nwarp, int lane) {
+                                                  float* __restrict__ out, float masked_below, int warp, int nwarp, int lane) {
   for (int i0 = warp; i0 < K1; i0 += nwarp * kSinkIlp) {
-    float mx[kSinkIlp], sm[kSinkIlp];
+    float shift[kSinkIlp], sm[kSinkIlp];
+    bool live[kSinkIlp];
 #pragma unroll
     for (int r = 0; r < kSinkIlp; ++r) {
       const int i = i0 + r * nwarp;
-      float m = -INFINITY;
-      if (i < K1)
-        for (int j = lane; j < K1; j += 32) m = fmaxf(m, ps[i * si + j * sj] + add[j]);
-      mx[r] = m;
+      live[r] = i < K1 && bias[i] > masked_below;
+      shift[r] = 0.f;
+      if (live[r]) {
+        if (FIRST) {
+          float m = -INFINITY;
+          for (int j = lane; j < K1; j += 32) m = fmaxf(m, ps[i * si + j * sj] + add[j]);
+          shift[r] = m;
+        } else {
+          shift[r] = bias[i] - out[i];
+        }
+      }
     }
+    if (FIRST) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int r = 0; r < kSinkIlp; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+        for (int r = 0; r < kSinkIlp; ++r) shift[r] = fmaxf(shift[r], __shfl_xor_sync(0xffffffffu, shift[r], o));
+    }
 #pragma unroll
     for (int r = 0; r < kSinkIlp; ++r) {
       const int i = i0 + r * nwarp;
       float s = 0.f;
-      if (i < K1)
-        for (int j = lane; j < K1; j += 32) s += __expf(ps[i * si + j * sj] + add[j] - mx[r]);  // ex2.approx: |rel err| ~1e-6 here
+      if (live[r])
+        for (int j = lane; j < K1; j += 32) s += __expf(ps[i * si + j * sj] + add[j] - shift[r]);  // ex2.approx: |rel err| ~1e-6
       sm[r] = s;
     }
 #pragma unroll
@@ -145,7 +160,7 @@ __device__ __forceinline__ void sinkhorn_lse_pass(const float* __restrict__ ps, 
 #pragma unroll
       for (int r = 0; r < kSinkIlp; ++r) {
         const int i = i0 + r * nwarp;
-        if (i < K1) out[i] = bias[i] - (logf(sm[r]) + mx[r]);
+        if (i < K1) out[i] = live[r] ? bias[i] - (logf(sm[r]) + shift[r]) : 0.f;
       }
     }
   }
@@ -192,10 +207,14 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const float* __r
     lmu[i] = mu; lnu[i] = nu; u[i] = 0.f; v[i] = 0.f;
   }
   __syncthreads();
+  const float masked_below = -0.5f * inf;
   for (int it = 0; it < iters; ++it) {
-    sinkhorn_lse_pass(ps, K1, K1, 1, v, lmu, u, warp, nwarp, lane);  // u_i = log_mu_i - logsumexp_j(ps_ij + v_j)
+    // u_i = log_mu_i - logsumexp_j(ps_ij + v_j) ; v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
+    if (it == 0) sinkhorn_lse_pass<true>(ps, K1, K1, 1, v, lmu, u, masked_below, warp, nwarp, lane);
+    else sinkhorn_lse_pass<false>(ps, K1, K1, 1, v, lmu, u, masked_below, warp, nwarp, lane);
     __syncthreads();
-    sinkhorn_lse_pass(ps, K1, 1, K1, u, lnu, v, warp, nwarp, lane);  // v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
+    if (it == 0) sinkhorn_lse_pass<true>(ps, K1, 1, K1, u, lnu, v, masked_below, warp, nwarp, lane);
+    else sinkhorn_lse_pass<false>(ps, K1, 1, K1, u, lnu, v, masked_below, warp, nwarp, lane);
     __syncthreads();
   }
   float* o = out + (long long)b * K1 * K1;

@@ -245,6 +245,7 @@ class RPEConditionalTransformer(nn.Module):
             layers.append(cls(d_model, num_heads, dropout=dropout, activation_fn=activation_fn))
         self.layers = nn.ModuleList(layers)
         self.return_attention_scores, self.parallel = return_attention_scores, parallel
+        self.fused = True
 
     @torch.no_grad()
     def forward(self, feats0, feats1, embeddings0, embeddings1, masks0=None, masks1=None):
@@ -252,6 +253,12 @@ class RPEConditionalTransformer(nn.Module):
         f1, _ = _squeeze(feats1)
         e0, _ = (embeddings0[0], True) if embeddings0.dim() == 4 else (embeddings0, False)
         e1, _ = (embeddings1[0], True) if embeddings1.dim() == 4 else (embeddings1, False)
+        if self.fused and not self.return_attention_scores and not self.parallel and masks0 is None and masks1 is None:
+            # one C-ABI call for all layers (csrc/transformer.cu): same kernels, issued from C++
+            f0, f1 = ops.conditional_transformer(list(self.layers), self.blocks, f0, f1, e0, e1, self.layers[0].attention.attention.num_heads)
+            if b0:
+                f0, f1 = f0.unsqueeze(0), f1.unsqueeze(0)
+            return f0, f1
         scores = []
         for i, block in enumerate(self.blocks):
             if block == "self":

@@ -367,3 +367,36 @@ def apply_transform(points, transform):
     R = transform[:3, :3].contiguous()
     t = transform[:3, 3].contiguous()
     return gemm(p, R, True, bias=t).view(shape)
+
+
+def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, num_heads):
+    """RPEConditionalTransformer.forward in one C-ABI call; feats are updated in place and returned."""
+    import ctypes
+    n = len(layer_modules)
+    arr = (_lib.LayerWeights * n)()
+    for i, (m, block) in enumerate(zip(layer_modules, blocks)):
+        a, o = m.attention, m.output
+        att = a.attention
+        w = arr[i]
+        w.wq, w.bq = att.proj_q.weight.data_ptr(), att.proj_q.bias.data_ptr()
+        w.wk, w.bk = att.proj_k.weight.data_ptr(), att.proj_k.bias.data_ptr()
+        w.wv, w.bv = att.proj_v.weight.data_ptr(), att.proj_v.bias.data_ptr()
+        if block == "self":
+            w.wp, w.bp = att.proj_p.weight.data_ptr(), att.proj_p.bias.data_ptr()
+        else:
+            w.wp, w.bp = None, None
+        w.wo, w.bo = a.linear.weight.data_ptr(), a.linear.bias.data_ptr()
+        w.ln1_g, w.ln1_b = a.norm.weight.data_ptr(), a.norm.bias.data_ptr()
+        w.w1, w.b1 = o.expand.weight.data_ptr(), o.expand.bias.data_ptr()
+        w.w2, w.b2 = o.squeeze.weight.data_ptr(), o.squeeze.bias.data_ptr()
+        w.ln2_g, w.ln2_b = o.norm.weight.data_ptr(), o.norm.bias.data_ptr()
+        w.is_self = 1 if block == "self" else 0
+    f0, f1 = _req(feats0).clone(), _req(feats1).clone()
+    N0, C = f0.shape
+    N1 = f1.shape[0]
+    L = _lib.lib()
+    ws = _workspace(L.gr_conditional_transformer_workspace_size(N0, N1, C, num_heads), f0.device)
+    st = L.gr_conditional_transformer(ctypes.cast(arr, ctypes.c_void_p), n, f0.data_ptr(), f1.data_ptr(), _req(emb0).data_ptr(),
+                                      _req(emb1).data_ptr(), N0, N1, C, num_heads, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "conditional_transformer")
+    return f0, f1

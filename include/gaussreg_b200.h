@@ -156,6 +156,24 @@ int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const
 int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
 int gr_l2_normalize_rows(const float* x, int64_t rows, int C, float eps, float* y, void* stream);
 
+/* T4  the whole RPE-conditional transformer (conditional_transformer.py:97-117: 'self' = RPE self-attention layer on
+ * both clouds, 'cross' = sequential cross-attention layers) in one call: host-side orchestration of the kernels
+ * above, so that the ~130 superpoint-sized launches are issued from C++ rather than from the interpreter.
+ * All pointers are device pointers to the nn.Linear / nn.LayerNorm parameters of one layer. */
+typedef struct {
+  const float *wq, *bq, *wk, *bk, *wv, *bv;  /* attention.attention.proj_{q,k,v} (C,C),(C) */
+  const float *wp, *bp;                      /* attention.attention.proj_p (self layers only, else NULL) */
+  const float *wo, *bo;                      /* attention.linear */
+  const float *ln1_g, *ln1_b;                /* attention.norm */
+  const float *w1, *b1, *w2, *b2;            /* output.expand (2C,C), output.squeeze (C,2C) */
+  const float *ln2_g, *ln2_b;                /* output.norm */
+  int is_self;
+} gr_layer_weights;
+size_t gr_conditional_transformer_workspace_size(int N0, int N1, int C, int num_heads);
+int gr_conditional_transformer(const gr_layer_weights* h_layers, int n_layers, float* feats0, float* feats1,
+                               const float* emb0, const float* emb1, int N0, int N1, int C, int num_heads, void* ws,
+                               size_t ws_bytes, void* stream);
+
 /* M1  superpoint matching (modules/geotransformer/superpoint_matching.py:13-50). */
 size_t gr_superpoint_matching_workspace_size(int Nr, int Ns, int k);
 int gr_superpoint_matching(float* xy, int Nr, int Ns, const uint8_t* ref_masks, const uint8_t* src_masks, int k,
