@@ -20,7 +20,7 @@ _sz = ctypes.c_size_t
 class LayerWeights(ctypes.Structure):
     """gr_layer_weights (include/gaussreg_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("wq", "bq", "wk", "bk", "wv", "bv", "wp", "bp", "wo", "bo", "ln1_g", "ln1_b",
-                                               "w1", "b1", "w2", "b2", "ln2_g", "ln2_b")] + [("is_self", ctypes.c_int)]
+                                               "w1", "b1", "w2", "b2", "ln2_g", "ln2_b", "wqkv", "bqkv")] + [("is_self", ctypes.c_int)]
 
 
 _SIGNATURES = {
@@ -53,6 +53,7 @@ _SIGNATURES = {
     "gr_pack_weight_tf32x3": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "gr_structure_embedding_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "gr_rpe_attention_probs_ld": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),
     "gr_l2_normalize_rows": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "gr_conditional_transformer_workspace_size": (_sz, [_i32, _i32, _i32, _i32]),

@@ -1,5 +1,7 @@
 // M1: superpoint matching (geotransformer/modules/geotransformer/superpoint_matching.py:13-50) and
 // S1: log-domain Sinkhorn with learnable dustbin (modules/sinkhorn/learnable_sinkhorn.py:5-66).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gr {
@@ -166,7 +168,77 @@ __device__ __forceinline__ void sinkhorn_lse_pass(const float* __restrict__ ps, 
   }
 }
 
-__global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+// K = 128 form of the pass: 17 warps.  Warps 0-15 own the 128 regular lines (8 each, all eight reduced together so
+// that 32 independent exp chains per lane are in flight), warp 16 owns the dustbin line; the dustbin COLUMN term
+// (j = 128) is added by lane 0 after its four strided terms, which is exactly the order of the generic loop
+// (j = lane, lane+32, ...), so both forms produce identical bits.
+template <bool FIRST>
+__device__ __forceinline__ void sinkhorn_lse_pass128(const float* __restrict__ ps, int si, int sj, const float* __restrict__ add,
+                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                     float masked_below, int warp, int lane) {
+  constexpr int K = 128;
+  if (warp > 16) return;
+  const int nl = warp < 16 ? 8 : 1;          // lines of this warp
+  const int ibase = warp < 16 ? warp : K;    // line r -> ibase + 16 r
+  float a[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) a[t] = add[lane + 32 * t];
+  const float ad = add[K];
+  float shift[8], sm[8];
+  bool live[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = ibase + 16 * r;
+    live[r] = r < nl && bias[i] > masked_below;
+    shift[r] = 0.f;
+    if (live[r]) {
+      if (FIRST) {
+        float m = ps[i * si + K * sj] + ad;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m = fmaxf(m, ps[i * si + (lane + 32 * t) * sj] + a[t]);
+        shift[r] = m;
+      } else {
+        shift[r] = bias[i] - out[i];
+      }
+    }
+  }
+  if (FIRST) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) shift[r] = fmaxf(shift[r], __shfl_xor_sync(0xffffffffu, shift[r], o));
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = ibase + 16 * r;
+    float s = 0.f;
+    if (live[r]) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s += __expf(ps[i * si + (lane + 32 * t) * sj] + a[t] - shift[r]);
+      if (lane == 0) s += __expf(ps[i * si + K * sj] + ad - shift[r]);
+    }
+    sm[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+  // lane r finishes line r (every lane holds all eight totals)
+  float my_sum = sm[0], my_shift = shift[0];
+  bool my_live = live[0];
+#pragma unroll
+  for (int r = 1; r < 8; ++r)
+    if (lane == r) { my_sum = sm[r]; my_shift = shift[r]; my_live = live[r]; }
+  if (lane < nl) {
+    const int i = ibase + 16 * lane;
+    out[i] = my_live ? bias[i] - (logf(my_sum) + my_shift) : 0.f;
+  }
+}
+
+constexpr int kSink128Threads = 17 * 32;
+
+template <bool FAST128>
+__global__ void __launch_bounds__(FAST128 ? kSink128Threads : kSinkThreads, FAST128 ? 2 : 1) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
                                                        const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
                                                        int K, int iters, float inf, float* __restrict__ out) {
   extern __shared__ float sm[];
@@ -210,6 +282,15 @@ __global__ void __launch_bounds__(kSinkThreads) sinkhorn_kernel(const float* __r
   const float masked_below = -0.5f * inf;
   for (int it = 0; it < iters; ++it) {
     // u_i = log_mu_i - logsumexp_j(ps_ij + v_j) ; v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
+    if (FAST128) {
+      if (it == 0) sinkhorn_lse_pass128<true>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
+      else sinkhorn_lse_pass128<false>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
+      __syncthreads();
+      if (it == 0) sinkhorn_lse_pass128<true>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
+      else sinkhorn_lse_pass128<false>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
+      __syncthreads();
+      continue;
+    }
     if (it == 0) sinkhorn_lse_pass<true>(ps, K1, K1, 1, v, lmu, u, masked_below, warp, nwarp, lane);
     else sinkhorn_lse_pass<false>(ps, K1, K1, 1, v, lmu, u, masked_below, warp, nwarp, lane);
     __syncthreads();
@@ -290,8 +371,17 @@ extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const 
   if (!scores || !row_masks || !col_masks || !alpha || !out) return GR_ERR_BAD_ARG;
   const size_t smem = ((size_t)(K + 1) * (K + 1) + 4 * (size_t)(K + 1)) * sizeof(float);
   if (smem > 220 * 1024) return GR_ERR_CAPACITY;
-  if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sinkhorn_kernel<<<P, kSinkThreads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K, num_iterations, inf, out);
+  static int fast_knob = -1;
+  if (fast_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN128"); fast_knob = e ? atoi(e) : 1; }
+  if (K == 128 && fast_knob) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sinkhorn_kernel<true><<<P, kSink128Threads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
+                                                                                          num_iterations, inf, out);
+  } else {
+    if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sinkhorn_kernel<false><<<P, kSinkThreads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
+                                                                                         num_iterations, inf, out);
+  }
   GR_CHECK_LAUNCH("sinkhorn_kernel");
   return GR_OK;
 }

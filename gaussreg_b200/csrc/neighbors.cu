@@ -492,6 +492,7 @@ __constant__ unsigned int c_ladder[23] = {13u,      29u,      59u,      127u,   
                                           1447153u, 2938679u, 5967347u, 12117689u, 24607243u, 49969847u, 101473717u};
 constexpr int kLadderLen = 23;
 constexpr int kReplayThreads = 1024;
+constexpr int kReplayCluster = 8;  // CTAs per cloud for the global-memory phases
 constexpr int kReplaySmemElems = 5087;  // phases up to this bucket count run out of shared memory
 constexpr unsigned int kNoTouch = 0xffffffffu;
 
@@ -535,91 +536,140 @@ __device__ void block_suffix_scan(unsigned int* w, unsigned int n, unsigned int*
   }
 }
 
+// One phase of the replay over arrays that live either in the shared memory of the cluster's CTA 0 (CL_ACTIVE = 1:
+// only that CTA works, barriers are __syncthreads) or in global memory (all CL CTAs of the cluster work, barriers are
+// cluster barriers).  `bkc` caches each position's bucket so the 64-bit modulo runs once per phase.
+template <bool CLUSTER>
+__device__ __forceinline__ void replay_barrier() {
+  if (CLUSTER) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
+template <bool CLUSTER>
+__device__ __forceinline__ void replay_phase(const unsigned long long* __restrict__ key, unsigned int nb, unsigned int n,
+                                             unsigned int n_prev, const unsigned int* lin, unsigned int* lout, unsigned int* ft,
+                                             unsigned int* cn, unsigned int* fill, unsigned int* w, unsigned int* tmp,
+                                             unsigned int* bkc, unsigned int* sh_scan, unsigned int gtid, unsigned int GT,
+                                             bool scan_cta) {
+  for (unsigned int k = gtid; k < nb; k += GT) { ft[k] = kNoTouch; cn[k] = 0u; fill[k] = 0u; }
+  replay_barrier<CLUSTER>();
+  for (unsigned int s = gtid; s < n; s += GT) {
+    const unsigned int e = s < n_prev ? ld_cg(&lin[s]) : s;
+    const unsigned int bk = (unsigned int)(key[e] % nb);
+    bkc[s] = bk;
+    atomicMin(&ft[bk], s);
+    atomicAdd(&cn[bk], 1u);
+  }
+  replay_barrier<CLUSTER>();
+  for (unsigned int s = gtid; s < n; s += GT) {
+    const unsigned int bk = ld_cg(&bkc[s]);
+    w[s] = (ld_cg(&ft[bk]) == s) ? ld_cg(&cn[bk]) : 0u;
+  }
+  replay_barrier<CLUSTER>();
+  if (scan_cta) block_suffix_scan(w, n, sh_scan);
+  replay_barrier<CLUSTER>();
+  for (unsigned int s = gtid; s < n; s += GT) {
+    const unsigned int bk = ld_cg(&bkc[s]);
+    const unsigned int base = ld_cg(&w[ld_cg(&ft[bk])]);
+    const unsigned int slot = atomicAdd(&fill[bk], 1u);
+    tmp[base + slot] = s;
+  }
+  replay_barrier<CLUSTER>();
+  for (unsigned int s = gtid; s < n; s += GT) {
+    const unsigned int bk = ld_cg(&bkc[s]);
+    if (ld_cg(&ft[bk]) != s) continue;
+    const unsigned int base = ld_cg(&w[s]), c = ld_cg(&cn[bk]);
+    for (unsigned int a = 1; a < c; ++a) {  // descending insertion sort of the bucket's positions
+      const unsigned int x = ld_cg(&tmp[base + a]);
+      unsigned int j = a;
+      while (j > 0 && ld_cg(&tmp[base + j - 1]) < x) { tmp[base + j] = ld_cg(&tmp[base + j - 1]); --j; }
+      tmp[base + j] = x;
+    }
+    for (unsigned int a = 0; a < c; ++a) {
+      const unsigned int s2 = ld_cg(&tmp[base + a]);
+      lout[base + a] = s2 < n_prev ? ld_cg(&lin[s2]) : s2;
+    }
+  }
+  replay_barrier<CLUSTER>();
+}
+
+// CL CTAs (one thread-block cluster) per cloud.  Phases whose tables fit in shared memory run in the cluster's CTA 0
+// alone; the long tail (bucket counts 10273 ... ) runs over global memory with all CL x 1024 threads, which is what
+// hides the L2 latency of the dependent gathers.  CL = 1 is the single-CTA form for small clouds.
+template <int CL>
 __global__ void __launch_bounds__(kReplayThreads, 1) hash_order_replay_kernel(
     const int* __restrict__ off, int batch, const uint32_t* __restrict__ fscan, const unsigned long long* __restrict__ vkey,
     const float* __restrict__ bary, unsigned int* g_list0, unsigned int* g_list1, unsigned int* g_w, unsigned int* g_tmp,
-    unsigned int* g_ft, unsigned int* g_cn, unsigned int* g_fill, float* __restrict__ out_points) {
+    unsigned int* g_bkc, unsigned int* g_ft, unsigned int* g_cn, unsigned int* g_fill, float* __restrict__ out_points) {
   extern __shared__ unsigned int smem[];
   __shared__ unsigned int sh_scan[33];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / CL;
+  const unsigned int crank = blockIdx.x % CL;  // cluster dims (CL,1,1): rank inside the cluster
   const unsigned int vbase = fscan[off[b]];
   const unsigned int D = fscan[off[b + 1]] - vbase;
   if (D == 0) return;
+  const bool has_global = D > (unsigned int)kReplaySmemElems;
+  if (crank != 0 && !has_global) return;  // nobody in this cluster will touch a cluster barrier
   const unsigned long long* key = vkey + vbase;
   // global scratch of this cloud (element arrays start at the cloud's first point, tables at 3x)
   const size_t ebase = (size_t)off[b];
   const size_t tbase = 3 * (size_t)off[b] + 64 * (size_t)b;
-  unsigned int* lin = nullptr;
-  unsigned int* lout = nullptr;
-  unsigned int n_prev = 0;
   const unsigned int tid = threadIdx.x, T = blockDim.x;
+  unsigned int* lin = nullptr;
+  unsigned int n_prev = 0;
+  int p = 0;
 
-  for (int p = 0; p < kLadderLen; ++p) {
-    const unsigned int nb = c_ladder[p];
-    const unsigned int n = min(D, nb);
-    const bool in_smem = nb <= (unsigned int)kReplaySmemElems;
-    unsigned int *ft, *cn, *fill, *w, *tmp, *l0, *l1;
-    if (in_smem) {
-      l0 = smem; l1 = smem + kReplaySmemElems; w = smem + 2 * kReplaySmemElems; tmp = smem + 3 * kReplaySmemElems;
-      ft = smem + 4 * kReplaySmemElems; cn = smem + 5 * kReplaySmemElems; fill = smem + 6 * kReplaySmemElems;
-    } else {
-      l0 = g_list0 + ebase; l1 = g_list1 + ebase; w = g_w + ebase; tmp = g_tmp + ebase;
-      ft = g_ft + tbase; cn = g_cn + tbase; fill = g_fill + tbase;
+  // ---- shared-memory phases (CTA 0)
+  {
+    unsigned int* l0 = smem; unsigned int* l1 = smem + kReplaySmemElems;
+    unsigned int* w = smem + 2 * kReplaySmemElems; unsigned int* tmp = smem + 3 * kReplaySmemElems;
+    unsigned int* ft = smem + 4 * kReplaySmemElems; unsigned int* cn = smem + 5 * kReplaySmemElems;
+    unsigned int* fill = smem + 6 * kReplaySmemElems; unsigned int* bkc = smem + 7 * kReplaySmemElems;
+    for (; p < kLadderLen && c_ladder[p] <= (unsigned int)kReplaySmemElems; ++p) {
+      const unsigned int nb = c_ladder[p];
+      const unsigned int n = min(D, nb);
+      unsigned int* lout = (lin == l0) ? l1 : l0;  // must not alias the input list
+      if (crank == 0) replay_phase<false>(key, nb, n, n_prev, lin, lout, ft, cn, fill, w, tmp, bkc, sh_scan, tid, T, true);
+      lin = lout;
+      n_prev = n;
+      if (n == D) break;
     }
-    // output list of this phase must not alias the input list
-    lout = (lin == l0) ? l1 : l0;
-
-    for (unsigned int k = tid; k < nb; k += T) { ft[k] = kNoTouch; cn[k] = 0u; fill[k] = 0u; }
-    __syncthreads();
-    for (unsigned int s = tid; s < n; s += T) {
-      const unsigned int e = s < n_prev ? ld_cg(&lin[s]) : s;
-      const unsigned int bk = (unsigned int)(key[e] % nb);
-      atomicMin(&ft[bk], s);
-      atomicAdd(&cn[bk], 1u);
-    }
-    __syncthreads();
-    for (unsigned int s = tid; s < n; s += T) {
-      const unsigned int e = s < n_prev ? ld_cg(&lin[s]) : s;
-      const unsigned int bk = (unsigned int)(key[e] % nb);
-      w[s] = (ld_cg(&ft[bk]) == s) ? ld_cg(&cn[bk]) : 0u;
-    }
-    __syncthreads();
-    block_suffix_scan(w, n, sh_scan);
-    __syncthreads();
-    for (unsigned int s = tid; s < n; s += T) {
-      const unsigned int e = s < n_prev ? ld_cg(&lin[s]) : s;
-      const unsigned int bk = (unsigned int)(key[e] % nb);
-      const unsigned int base = ld_cg(&w[ld_cg(&ft[bk])]);
-      const unsigned int slot = atomicAdd(&fill[bk], 1u);
-      tmp[base + slot] = s;
-    }
-    __syncthreads();
-    for (unsigned int s = tid; s < n; s += T) {
-      const unsigned int e = s < n_prev ? ld_cg(&lin[s]) : s;
-      const unsigned int bk = (unsigned int)(key[e] % nb);
-      if (ld_cg(&ft[bk]) != s) continue;
-      const unsigned int base = ld_cg(&w[s]), c = ld_cg(&cn[bk]);
-      for (unsigned int a = 1; a < c; ++a) {  // descending insertion sort of the bucket's positions
-        const unsigned int x = ld_cg(&tmp[base + a]);
-        unsigned int j = a;
-        while (j > 0 && ld_cg(&tmp[base + j - 1]) < x) { tmp[base + j] = ld_cg(&tmp[base + j - 1]); --j; }
-        tmp[base + j] = x;
-      }
-      for (unsigned int a = 0; a < c; ++a) {
-        const unsigned int s2 = ld_cg(&tmp[base + a]);
-        lout[base + a] = s2 < n_prev ? ld_cg(&lin[s2]) : s2;
-      }
-    }
-    __syncthreads();
-    lin = lout;
-    n_prev = n;
-    if (n == D) break;
   }
-  // emission: position -> voxel
-  for (unsigned int pos = tid; pos < D; pos += T) {
-    const unsigned int e = ld_cg(&lin[pos]);
-    const size_t src = 3 * (size_t)(vbase + e), dst = 3 * (size_t)(vbase + pos);
-    out_points[dst] = bary[src]; out_points[dst + 1] = bary[src + 1]; out_points[dst + 2] = bary[src + 2];
+  if (has_global) {
+    // hand the list over to global memory, then continue with every CTA of the cluster
+    unsigned int* l0 = g_list0 + ebase; unsigned int* l1 = g_list1 + ebase;
+    if (crank == 0) {
+      for (unsigned int s = tid; s < n_prev; s += T) l0[s] = lin[s];
+    }
+    lin = l0;
+    replay_barrier<(CL > 1)>();
+    const unsigned int gtid = crank * T + tid, GT = CL * T;
+    for (; p < kLadderLen; ++p) {
+      const unsigned int nb = c_ladder[p];
+      const unsigned int n = min(D, nb);
+      unsigned int* lout = (lin == l0) ? l1 : l0;
+      replay_phase<(CL > 1)>(key, nb, n, n_prev, lin, lout, g_ft + tbase, g_cn + tbase, g_fill + tbase, g_w + ebase,
+                             g_tmp + ebase, g_bkc + ebase, sh_scan, gtid, GT, crank == 0);
+      lin = lout;
+      n_prev = n;
+      if (n == D) break;
+    }
+    // emission: position -> voxel
+    for (unsigned int pos = gtid; pos < D; pos += GT) {
+      const unsigned int e = ld_cg(&lin[pos]);
+      const size_t src = 3 * (size_t)(vbase + e), dst = 3 * (size_t)(vbase + pos);
+      out_points[dst] = bary[src]; out_points[dst + 1] = bary[src + 1]; out_points[dst + 2] = bary[src + 2];
+    }
+  } else {
+    for (unsigned int pos = tid; pos < D; pos += T) {
+      const unsigned int e = lin[pos];
+      const size_t src = 3 * (size_t)(vbase + e), dst = 3 * (size_t)(vbase + pos);
+      out_points[dst] = bary[src]; out_points[dst + 1] = bary[src + 1]; out_points[dst + 2] = bary[src + 2];
+    }
   }
 }
 
@@ -638,7 +688,7 @@ struct G1Workspace {
   uint32_t* vfill;   // n
   int* plist;        // n
   float* bary;       // 3n
-  unsigned int *list0, *list1, *w, *tmp;  // n each
+  unsigned int *list0, *list1, *w, *tmp, *bkc;  // n each
   unsigned int *ft, *cn, *fill;           // 3n + 64*batch each
   uint32_t* scan_ws;
   int* scalars;
@@ -670,6 +720,7 @@ static G1Workspace carve_g1(void* ws, size_t ws_bytes, int64_t n, int batch, boo
   w.list1 = c.take<unsigned int>(n + 1);
   w.w = c.take<unsigned int>(n + 1);
   w.tmp = c.take<unsigned int>(n + 1);
+  w.bkc = c.take<unsigned int>(n + 1);
   w.ft = c.take<unsigned int>(w.tbl_elems);
   w.cn = c.take<unsigned int>(w.tbl_elems);
   w.fill = c.take<unsigned int>(w.tbl_elems);
@@ -791,14 +842,35 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
   GR_CHECK_LAUNCH("voxel_scatter_kernel");
   voxel_barycenter_kernel<<<ceil_div(n, 128), 128, 0, st>>>(points, w.off, batch, w.fscan, w.vcnt, w.plist, w.bary);
   GR_CHECK_LAUNCH("voxel_barycenter_kernel");
-  static bool attr_set = false;
-  const size_t smem = 7 * (size_t)kReplaySmemElems * sizeof(unsigned int);
-  if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(hash_order_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  {
+    // clouds that may exceed the shared-memory phases get a cluster of kReplayCluster CTAs each
+    const size_t smem = 8 * (size_t)kReplaySmemElems * sizeof(unsigned int);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GR_CHECK_CUDA(cudaFuncSetAttribute(hash_order_replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GR_CHECK_CUDA(cudaFuncSetAttribute(hash_order_replay_kernel<kReplayCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    static int cl_knob = -1;
+    if (cl_knob < 0) { const char* e = getenv("GAUSSREG_REPLAY_CLUSTER"); cl_knob = e ? atoi(e) : kReplayCluster; }
+    if (n > kReplaySmemElems && cl_knob > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)batch * kReplayCluster);
+      cfg.blockDim = dim3(kReplayThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kReplayCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hash_order_replay_kernel<kReplayCluster>, (const int*)w.off, batch,
+                                       (const uint32_t*)w.fscan, (const unsigned long long*)w.vkey, (const float*)w.bary, w.list0,
+                                       w.list1, w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points));
+    } else {
+      hash_order_replay_kernel<1><<<batch, kReplayThreads, smem, st>>>(w.off, batch, w.fscan, w.vkey, w.bary, w.list0, w.list1,
+                                                                        w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points);
+    }
   }
-  hash_order_replay_kernel<<<batch, kReplayThreads, smem, st>>>(w.off, batch, w.fscan, w.vkey, w.bary, w.list0, w.list1,
-                                                                 w.w, w.tmp, w.ft, w.cn, w.fill, out_points);
   GR_CHECK_LAUNCH("hash_order_replay_kernel");
   return GR_OK;
 }

@@ -4,6 +4,11 @@
 // Host-side orchestration only: every tensor op below is one of this library's kernels.  Running the ~130 launches
 // of the six layers from C++ instead of from Python removes ~10 us of interpreter overhead per op, which is more
 // than most of these superpoint-sized kernels take on a B200.
+#include <stdlib.h>
+
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 extern "C" {
@@ -12,34 +17,33 @@ int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_
             const float* row_div, const float* residual, int64_t ldr, int64_t strideR, int act, void* stream);
 int gr_layer_norm_add(const float* a, const float* b, int64_t rows, int C, const float* gamma, const float* beta,
                       float eps, float* y, void* stream);
-int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,
-                           int num_heads, float* P, void* stream);
+int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* U, const float* qb,
+                              const float* emb, int N, int C, int num_heads, float* P, void* stream);
 int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
 }
 
 namespace gr {
 
 struct TfWs {
-  float *q, *k, *v, *U, *qb, *P, *hid, *att, *ffn, *y;
-  size_t bytes;
+  float *qkv, *U, *qb, *P, *hid, *att, *ffn, *y;
 };
 
-static TfWs carve_tf(void* ws, size_t ws_bytes, int N, int C, int H, bool* ok) {
+static size_t carve_tf(void* ws, size_t ws_bytes, int N, int C, int H, TfWs* sets, int n_sets, bool* ok) {
   Carver c(ws, ws_bytes);
-  TfWs w;
-  w.q = c.take<float>((size_t)N * C);
-  w.k = c.take<float>((size_t)N * C);
-  w.v = c.take<float>((size_t)N * C);
-  w.U = c.take<float>((size_t)H * N * C);
-  w.qb = c.take<float>((size_t)H * N);
-  w.P = c.take<float>((size_t)H * N * N);
-  w.hid = c.take<float>((size_t)N * C);
-  w.att = c.take<float>((size_t)N * C);
-  w.ffn = c.take<float>((size_t)N * 2 * C);
-  w.y = c.take<float>((size_t)N * C);
-  w.bytes = c.off;
+  for (int i = 0; i < n_sets; ++i) {
+    TfWs w;
+    w.qkv = c.take<float>((size_t)N * 3 * C);
+    w.U = c.take<float>((size_t)H * N * C);
+    w.qb = c.take<float>((size_t)H * N);
+    w.P = c.take<float>((size_t)H * N * N);
+    w.hid = c.take<float>((size_t)N * C);
+    w.att = c.take<float>((size_t)N * C);
+    w.ffn = c.take<float>((size_t)N * 2 * C);
+    w.y = c.take<float>((size_t)N * C);
+    if (sets) sets[i] = w;
+  }
   *ok = c.ok;
-  return w;
+  return c.off;
 }
 
 #define GR_TRY(expr)                 \
@@ -56,22 +60,40 @@ static int linear(const float* x, int rows, int in, const float* W, const float*
 static int layer(const gr_layer_weights& L, float* x, int N, const float* mem, int M, const float* emb, int C, int H, TfWs& w,
                  void* st) {
   const int dh = C / H;
-  GR_TRY(linear(x, N, C, L.wq, L.bq, C, w.q, 0, st));
-  GR_TRY(linear(mem, M, C, L.wk, L.bk, C, w.k, 0, st));
-  GR_TRY(linear(mem, M, C, L.wv, L.bv, C, w.v, 0, st));
+  const float *q, *k, *v;
+  int64_t ldq, ldk, ldv;
+  if (L.wqkv && L.bqkv && L.is_self) {  // x == mem: one product for q|k|v
+    GR_TRY(linear(x, N, C, L.wqkv, L.bqkv, 3 * C, w.qkv, 0, st));
+    q = w.qkv; k = w.qkv + C; v = w.qkv + 2 * C;
+    ldq = ldk = ldv = 3 * C;
+  } else if (L.wqkv && L.bqkv) {        // q from x, k|v from mem
+    float* kv = w.qkv + (size_t)N * C;
+    GR_TRY(linear(x, N, C, L.wqkv, L.bqkv, C, w.qkv, 0, st));
+    GR_TRY(linear(mem, M, C, L.wqkv + (size_t)C * C, L.bqkv + C, 2 * C, kv, 0, st));
+    q = w.qkv; ldq = C;
+    k = kv; v = kv + C; ldk = ldv = 2 * C;
+  } else {
+    float* kb = w.qkv + (size_t)N * C;
+    float* vb = kb + (size_t)M * C;
+    GR_TRY(linear(x, N, C, L.wq, L.bq, C, w.qkv, 0, st));
+    GR_TRY(linear(mem, M, C, L.wk, L.bk, C, kb, 0, st));
+    GR_TRY(linear(mem, M, C, L.wv, L.bv, C, vb, 0, st));
+    q = w.qkv; k = kb; v = vb;
+    ldq = ldk = ldv = C;
+  }
   if (L.is_self) {
     // U[h] = q_h (N,dh) @ W_p[h*dh:(h+1)*dh, :] ; qb[h] = q_h @ b_p[h*dh:(h+1)*dh]   (see attention.cu)
-    GR_TRY(gr_gemm(w.q, C, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0,
+    GR_TRY(gr_gemm(q, ldq, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0,
                    0, 0, st));
-    GR_TRY(gr_gemm(w.q, C, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
-    GR_TRY(gr_rpe_attention_probs(w.q, w.k, w.U, w.qb, emb, N, C, H, w.P, st));
+    GR_TRY(gr_gemm(q, ldq, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
+    GR_TRY(gr_rpe_attention_probs_ld(q, ldq, k, ldk, w.U, w.qb, emb, N, C, H, w.P, st));
   } else {
-    GR_TRY(gr_gemm(w.q, C, dh, w.k, C, dh, 1, w.P, M, (int64_t)N * M, N, M, dh, H, 1.0f / sqrtf((float)dh), nullptr, nullptr,
+    GR_TRY(gr_gemm(q, ldq, dh, k, ldk, dh, 1, w.P, M, (int64_t)N * M, N, M, dh, H, 1.0f / sqrtf((float)dh), nullptr, nullptr,
                    nullptr, 0, 0, 0, st));
     GR_TRY(gr_softmax_rows(w.P, (int64_t)H * N, M, st));
   }
   // hidden[:, h*dh:(h+1)*dh] = P[h] @ v[:, h*dh:(h+1)*dh]
-  GR_TRY(gr_gemm(w.P, M, (int64_t)N * M, w.v, C, dh, 0, w.hid, C, dh, N, dh, M, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
+  GR_TRY(gr_gemm(w.P, M, (int64_t)N * M, v, ldv, dh, 0, w.hid, C, dh, N, dh, M, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
   GR_TRY(linear(w.hid, N, C, L.wo, L.bo, C, w.att, 0, st));
   GR_TRY(gr_layer_norm_add(w.att, x, N, C, L.ln1_g, L.ln1_b, 1e-5f, w.y, st));
   GR_TRY(linear(w.y, N, C, L.w1, L.b1, 2 * C, w.ffn, 1, st));
@@ -80,34 +102,86 @@ static int layer(const gr_layer_weights& L, float* x, int N, const float* mem, i
   return GR_OK;
 }
 
+// A helper stream per (device, caller stream): the two clouds of a 'self' layer are independent, and one
+// superpoint-sized kernel (a few dozen CTAs) leaves most of the 148 SMs idle, so they run side by side.
+struct SideStream {
+  int dev;
+  cudaStream_t main, side;
+  cudaEvent_t fork, join;
+};
+
+static SideStream* side_stream(cudaStream_t main) {
+  static std::mutex mu;
+  static std::vector<SideStream*> all;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (SideStream* s : all)
+    if (s->dev == dev && s->main == main) return s;
+  SideStream* s = new SideStream{dev, main, nullptr, nullptr, nullptr};
+  if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+    set_last_error("transformer side stream", cudaGetLastError());
+    delete s;
+    return nullptr;
+  }
+  all.push_back(s);
+  return s;
+}
+
+static bool two_streams() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_TF_STREAMS"); v = e ? atoi(e) : 2; }
+  return v >= 2;
+}
+
 }  // namespace gr
 
 using namespace gr;
 
 extern "C" size_t gr_conditional_transformer_workspace_size(int N0, int N1, int C, int num_heads) {
   bool ok;
-  return carve_tf(nullptr, 0, N0 > N1 ? N0 : N1, C, num_heads, &ok).bytes;
+  return carve_tf(nullptr, 0, N0 > N1 ? N0 : N1, C, num_heads, nullptr, 2, &ok);
 }
 
 /* feats0 (N0,C) / feats1 (N1,C) are updated in place through all layers; "self" layers use emb0 (N0,N0,C) and
- * emb1 (N1,N1,C), "cross" layers run sequentially (feats0 attends feats1, then feats1 attends the UPDATED feats0). */
+ * emb1 (N1,N1,C), "cross" layers run sequentially (feats0 attends feats1, then feats1 attends the UPDATED feats0).
+ * The two clouds of a self layer are issued on two streams (joined again before the next cross layer and before
+ * returning: from the caller's point of view all work is ordered on `stream`). */
 extern "C" int gr_conditional_transformer(const gr_layer_weights* layers, int n_layers, float* feats0, float* feats1,
                                           const float* emb0, const float* emb1, int N0, int N1, int C, int num_heads,
                                           void* ws, size_t ws_bytes, void* stream) {
   if (!layers || n_layers <= 0 || !feats0 || !feats1 || N0 <= 0 || N1 <= 0 || C <= 0 || num_heads <= 0 || C % num_heads != 0)
     return GR_ERR_BAD_ARG;
   bool ok;
-  TfWs w = carve_tf(ws, ws_bytes, N0 > N1 ? N0 : N1, C, num_heads, &ok);
+  TfWs w[2];
+  carve_tf(ws, ws_bytes, N0 > N1 ? N0 : N1, C, num_heads, w, 2, &ok);
   if (!ws || !ok) return GR_ERR_WORKSPACE;
+  cudaStream_t main = static_cast<cudaStream_t>(stream);
+  SideStream* ss = two_streams() ? side_stream(main) : nullptr;
+  if (two_streams() && !ss) return GR_ERR_CUDA;
   for (int i = 0; i < n_layers; ++i) {
     const gr_layer_weights& L = layers[i];
     if (L.is_self) {
       if (!emb0 || !emb1 || !L.wp || !L.bp) return GR_ERR_BAD_ARG;
-      GR_TRY(layer(L, feats0, N0, feats0, N0, emb0, C, num_heads, w, stream));
-      GR_TRY(layer(L, feats1, N1, feats1, N1, emb1, C, num_heads, w, stream));
+      if (ss) {
+        GR_CHECK_CUDA(cudaEventRecord(ss->fork, main));
+        GR_CHECK_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+        const int rc0 = layer(L, feats0, N0, feats0, N0, emb0, C, num_heads, w[0], main);
+        const int rc1 = layer(L, feats1, N1, feats1, N1, emb1, C, num_heads, w[1], ss->side);
+        // always join, also on failure: the caller's stream must never run ahead of the helper
+        cudaEventRecord(ss->join, ss->side);
+        cudaStreamWaitEvent(main, ss->join, 0);
+        if (rc0 != GR_OK) return rc0;
+        if (rc1 != GR_OK) return rc1;
+      } else {
+        GR_TRY(layer(L, feats0, N0, feats0, N0, emb0, C, num_heads, w[0], stream));
+        GR_TRY(layer(L, feats1, N1, feats1, N1, emb1, C, num_heads, w[0], stream));
+      }
     } else {
-      GR_TRY(layer(L, feats0, N0, feats1, N1, nullptr, C, num_heads, w, stream));
-      GR_TRY(layer(L, feats1, N1, feats0, N0, nullptr, C, num_heads, w, stream));
+      GR_TRY(layer(L, feats0, N0, feats1, N1, nullptr, C, num_heads, w[0], stream));
+      GR_TRY(layer(L, feats1, N1, feats0, N0, nullptr, C, num_heads, w[0], stream));
     }
   }
   return GR_OK;

@@ -369,11 +369,29 @@ def apply_transform(points, transform):
     return gemm(p, R, True, bias=t).view(shape)
 
 
+def _fused_qkv(att):
+    """proj_q | proj_k | proj_v stacked row-wise -> ((3C,C) weight, (3C) bias); cached on proj_q.weight and rebuilt
+    when any of the six parameters changes version or device (load_state_dict copies in place -> version bump)."""
+    params = (att.proj_q.weight, att.proj_k.weight, att.proj_v.weight, att.proj_q.bias, att.proj_k.bias, att.proj_v.bias)
+    key = tuple((t._version, t.data_ptr()) for t in params)
+    cached = getattr(att.proj_q.weight, "_gr_qkv", None)
+    if cached is None or cached[0] != key:
+        w = torch.cat([t.detach() for t in params[:3]], dim=0).contiguous()
+        b = torch.cat([t.detach() for t in params[3:]], dim=0).contiguous()
+        cached = (key, w, b)
+        try:
+            att.proj_q.weight._gr_qkv = cached
+        except AttributeError:
+            pass
+    return cached[1], cached[2]
+
+
 def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, num_heads):
     """RPEConditionalTransformer.forward in one C-ABI call; feats are updated in place and returned."""
     import ctypes
     n = len(layer_modules)
     arr = (_lib.LayerWeights * n)()
+    keep = []
     for i, (m, block) in enumerate(zip(layer_modules, blocks)):
         a, o = m.attention, m.output
         att = a.attention
@@ -391,6 +409,9 @@ def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, n
         w.w2, w.b2 = o.squeeze.weight.data_ptr(), o.squeeze.bias.data_ptr()
         w.ln2_g, w.ln2_b = o.norm.weight.data_ptr(), o.norm.bias.data_ptr()
         w.is_self = 1 if block == "self" else 0
+        wqkv, bqkv = _fused_qkv(att)
+        keep.append((wqkv, bqkv))
+        w.wqkv, w.bqkv = wqkv.data_ptr(), bqkv.data_ptr()
     f0, f1 = _req(feats0).clone(), _req(feats1).clone()
     N0, C = f0.shape
     N1 = f1.shape[0]

@@ -153,6 +153,9 @@ int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t
  * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */
 int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,
                            int num_heads, float* P, void* stream);
+/* same, q and k being column slices of wider matrices (row pitches ldq / ldk, e.g. a fused q|k|v projection) */
+int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* U, const float* qb,
+                              const float* emb, int N, int C, int num_heads, float* P, void* stream);
 int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
 int gr_l2_normalize_rows(const float* x, int64_t rows, int C, float eps, float* y, void* stream);
 
@@ -167,6 +170,10 @@ typedef struct {
   const float *ln1_g, *ln1_b;                /* attention.norm */
   const float *w1, *b1, *w2, *b2;            /* output.expand (2C,C), output.squeeze (C,2C) */
   const float *ln2_g, *ln2_b;                /* output.norm */
+  /* optional: proj_q|proj_k|proj_v stacked row-wise, (3C,C) and (3C).  When set, q/k/v come out of one product
+   * (self layers) or of a q product and a fused k|v product (cross layers); results are identical, there are
+   * just fewer superpoint-sized launches.  NULL -> the separate matrices above are used. */
+  const float *wqkv, *bqkv;
   int is_self;
 } gr_layer_weights;
 size_t gr_conditional_transformer_workspace_size(int N0, int N1, int C, int num_heads);
