@@ -65,6 +65,13 @@ _SIGNATURES = {
     "gr_local_global_registration": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _f32, _i32, _i32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_weighted_procrustes": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
+    "gr_column_order_stats_workspace_size": (_sz, [_i32]),
+    "gr_column_order_stats": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "gr_gaussian_select_workspace_size": (_sz, [_i64]),
+    "gr_gaussian_select": (_i32, [_vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_gather_points_stats": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "gr_gaussian_features": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "gr_points_normalize": (_i32, [_vp, _i64, _vp, _f32, _i32, _vp]),
 }
 
 _STATUS = {-1: "bad argument", -2: "workspace too small", -3: "capacity overflow", -4: "CUDA error"}

@@ -17,7 +17,7 @@ template <int H>
 __global__ void __launch_bounds__(256) rpe_scores_softmax_kernel(const float* __restrict__ q, const float* __restrict__ kmat,
                                                                  const float* __restrict__ U, const float* __restrict__ qb,
                                                                  const float* __restrict__ emb, int N, int C, float scale,
-                                                                 float* __restrict__ P) {
+                                                                 float* __restrict__ P, long long ldq, long long ldk) {
   extern __shared__ float sm[];
   float* sU = sm;                 // [H][C]
   float* sq = sU + H * C;         // [C]
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) rpe_scores_softmax_kernel(const float* __
   const int DH = C / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < H * C; i += blockDim.x) sU[i] = U[((long long)(i / C) * N + n) * C + (i % C)];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sq[i] = q[(long long)n * C + i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sq[i] = q[(long long)n * ldq + i];
   __syncthreads();
   float qbh[H];
 #pragma unroll
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) rpe_scores_softmax_kernel(const float* __
   const int c4_per_head = DH >> 2;
   for (int m = threadIdx.x; m < N; m += blockDim.x) {
     const float4* e4 = reinterpret_cast<const float4*>(erow + (long long)m * C);
-    const float4* k4 = reinterpret_cast<const float4*>(kmat + (long long)m * C);
+    const float4* k4 = reinterpret_cast<const float4*>(kmat + (long long)m * ldk);
     float accp[H], acce[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) { accp[h] = 0.f; acce[h] = 0.f; }
@@ -279,12 +279,12 @@ extern "C" int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const floa
     GR_CHECK_LAUNCH("rpe_scores_softmax_v2_kernel");
     return GR_OK;
   }
-  if (ldq != C || ldk != C) return GR_ERR_BAD_ARG;  // the generic kernel reads dense q / k
+  if (ldk % 4 != 0) return GR_ERR_BAD_ARG;
   const size_t smem = ((size_t)num_heads * C + C + (size_t)num_heads * N) * sizeof(float);
   if (smem > 200 * 1024) return GR_ERR_CAPACITY;
   auto kern = rpe_scores_softmax_kernel<4>;
   if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, k, U, qb, emb, N, C, scale, P);
+  kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, k, U, qb, emb, N, C, scale, P, ldq, ldk);
   GR_CHECK_LAUNCH("rpe_scores_softmax_kernel");
   return GR_OK;
 }

@@ -203,6 +203,34 @@ int gr_local_global_registration(const float* matching_scores, int P, int K, int
 int gr_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int B, int n, float eps,
                            float* transforms, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * N1  Gaussian-splat cloud -> network input, the step in front of the path
+ *     (experiments/geotransformer.gaussian_splatting.indoor/demo.py:30-75 _read_ply_by_opacity and :81-124
+ *     load_data; geotransformer/utils/graphics_utils.py:34-89 eval_sh).
+ * cloud: (n, ld) f32 rows in 3DGS property order without normals (gs_fusion.py:172-184):
+ *     xyz 0..2 | f_dc 3..5 | f_rest 6..50 | opacity 51 | scale 52..54 | rot 55..58.
+ * Arguments documented as HOST are read before the call returns; everything else is device memory.
+ * --------------------------------------------------------------------------------------------- */
+/* out_values[j] (device) = ranks[j]-th smallest (0-based) entry of column cols[j]; cols/ranks HOST, n_queries <= 16.
+ * Exact order statistics for np.percentile (demo.py:40-42); the interpolation itself is host glue. */
+size_t gr_column_order_stats_workspace_size(int n_queries);
+int gr_column_order_stats(const float* cloud, int64_t n, int ld, const int32_t* cols, const int64_t* ranks, int n_queries,
+                          float* out_values, void* ws, size_t ws_bytes, void* stream);
+/* keep row i iff sigmoid(opacity) > opacity_min and lo[a] < xyz[a] < hi[a] (demo.py:34,40-43); lo/hi HOST double[3].
+ * out_index (capacity n) holds the kept rows in ascending order, out_count their number. */
+size_t gr_gaussian_select_workspace_size(int64_t n);
+int gr_gaussian_select(const float* cloud, int64_t n, int ld, int opacity_col, float opacity_min, const double* lo,
+                       const double* hi, int64_t* out_index, int64_t* out_count, void* ws, size_t ws_bytes, void* stream);
+/* out_points (m,3) = cloud[index, 0:3] (index NULL = all rows); out_stats float[9] = {float32 column sums in input
+ * order (numpy's axis-0 reduction order, demo.py:62), min xyz, max xyz}.  ws: >= 64 bytes. */
+int gr_gather_points_stats(const float* cloud, int ld, const int64_t* index, int64_t m, float* out_points,
+                           float* out_stats, void* ws, size_t ws_bytes, void* stream);
+/* out_feats (m,4) = [sigmoid(opacity), 255*clip(SH_deg3(view dir)+0.5,0,1) RGB] (demo.py:63-72); view_point HOST double[3]. */
+int gr_gaussian_features(const float* cloud, int ld, const int64_t* index, int64_t m, const double* view_point,
+                         float* out_feats, void* stream);
+/* points <- (points - center) [* scale] in float32 (demo.py:85-110); center3 HOST float[3]. */
+int gr_points_normalize(float* points, int64_t m, const float* center3, float scale, int apply_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
