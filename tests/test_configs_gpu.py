@@ -1,0 +1,123 @@
+"""GPU tests for the remaining BASELINE configurations:
+
+  config 3  many pairs through one process: per-pair results must not depend on what ran before (grow-only
+            workspaces, cached packed weights, helper streams) -> bit-identical transforms across orders and
+            repeats, and equal to the CPU oracle for a sampled pair;
+  config 5  one 200k-Gaussian pair with ~4096 superpoints per cloud: sizes at which the reference cannot run
+            (51 GB intermediate) and the CPU oracle only in pieces -> size-independent properties plus
+            teacher-forced tiles of the structure embedding against the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gaussreg_b200 import ext, ops, parallel
+from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+from gaussreg_b200.data import precompute_data_stack_mode, registration_collate_fn_stack_mode
+from gaussreg_b200.synthetic import make_pair_inputs
+from oracle import network as onet
+from tests.helpers import oracle_data, rel_l2, seeded_model
+
+pytestmark = pytest.mark.gpu
+KEYS = ("ref_points", "src_points", "ref_feats", "src_feats")
+
+
+def test_config3_many_pairs_order_independent():
+    model = seeded_model(0).cuda()
+    specs = [dict(seed=s, n_points=n) for s, n in [(0, 4000), (1, 2500), (2, 6000), (3, 4000), (4, 3000), (5, 5000)]]
+    pairs = [make_pair_inputs(**sp) for sp in specs]
+    T1 = parallel.register_pairs(model, pairs).cpu()
+    T2 = parallel.register_pairs(model, pairs[::-1]).cpu().flip(0)   # reverse order: different workspace history
+    T3 = parallel.register_pairs(model, pairs).cpu()
+    assert T1.shape == (len(pairs), 4, 4)
+    assert torch.equal(T1, T3), "repeat run differs: state leaks between pairs"
+    assert torch.equal(T1, T2), "order-dependent result: state leaks between pairs"
+    assert torch.isfinite(T1).all()
+    # a sampled pair against the CPU oracle (north_star tolerance 1e-4 Frobenius on the LGR transform)
+    with torch.no_grad():
+        want = onet.forward(seeded_model(0).state_dict(), oracle_data(specs[1]))
+    err = float(np.linalg.norm(T1[1].numpy() - want["estimated_transform"].numpy()))
+    assert err < 1e-4, err
+
+
+@pytest.fixture(scope="module")
+def large_pair():
+    """200k Gaussians per cloud on a 12 x 9 x 7.5 m room shell: ~4000 superpoints per cloud at the 0.4 m stage."""
+    d = make_pair_inputs(7, 200000, room=(12.0, 9.0, 7.5))
+    cfg = make_cfg()
+    data = registration_collate_fn_stack_mode([{k: d[k] for k in KEYS}], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                              cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    return d, data
+
+
+def test_config5_pyramid_properties(large_pair):
+    d, data = large_pair
+    lens = torch.stack(data["lengths"]).cpu()
+    assert lens[0].tolist() == [200000, 200000]
+    assert 3000 < int(lens[-1, 0]) < 6000 and 3000 < int(lens[-1, 1]) < 6000, lens[-1]
+    for i, (pts, nb) in enumerate(zip(data["points"], data["neighbors"])):
+        n = pts.shape[0]
+        assert nb.shape[0] == n and nb.shape[1] <= NEIGHBOR_LIMITS[i]
+        valid = nb < n
+        assert bool((nb[:, 0] == torch.arange(n, device=nb.device)).all()), "a point is its own nearest neighbour"
+        # rows are sorted by distance and every listed neighbour lies inside the radius (strict)
+        r = make_cfg().backbone.init_radius * 2 ** i
+        q = pts[:, None, :]
+        s = torch.cat([pts, torch.full((1, 3), 1e6, device=pts.device)])[nb.clamp_max(n)]
+        dist = ((q - s) ** 2).sum(-1)
+        dist = torch.where(valid, dist, torch.full_like(dist, float("inf")))
+        assert bool((dist[:, 1:] >= dist[:, :-1]).all()), f"stage {i}: neighbours not sorted"
+        assert bool((dist[valid] < r * r * (1 + 1e-6)).all())
+        # never crosses the ref / src boundary
+        n_ref = int(lens[i, 0])
+        side = torch.arange(n, device=nb.device)[:, None] < n_ref
+        assert bool(((nb < n_ref) == side)[valid].all())
+    # grid subsampling is idempotent at the same voxel size: every voxel already holds one barycentre
+    v1 = make_cfg().backbone.init_voxel_size * 2
+    again, again_len = ext.grid_subsampling(data["points"][1], data["lengths"][1], v1)
+    assert again_len.tolist() == data["lengths"][1].tolist()
+
+
+def test_config5_structure_embedding_tiles_vs_oracle(large_pair):
+    """emb[n, m] depends only on points n, m and the three nearest neighbours of n: rebuild a 64-point sub-problem
+    that contains those, run the CPU oracle on it, and compare with the same entries of the 4096-node GPU result."""
+    _, data = large_pair
+    model = seeded_model(0)
+    sd = model.state_dict()
+    nodes = data["points"][-1][: int(data["lengths"][-1][0])]
+    N = nodes.shape[0]
+    emb = model.transformer.embedding.cuda()(nodes)  # (N, N, 256), fused tcgen05 kernel
+    assert emb.shape == (N, N, 256)
+    g = torch.Generator().manual_seed(0)
+    anchors = torch.randperm(N, generator=g)[:4]
+    d2 = torch.cdist(nodes[anchors.cuda()], nodes)
+    knn = d2.topk(4, largest=False).indices[:, 1:].cpu()           # three nearest neighbours, self excluded
+    others = torch.randperm(N, generator=g)[:48]
+    subset = torch.unique(torch.cat([anchors, knn.flatten(), others]))
+    sub_pts = nodes[subset.cuda()].cpu()
+    want = onet.structure_embedding(sd, sub_pts, 0.2, 15, 3)        # (S, S, 256)
+    pos = {int(v): i for i, v in enumerate(subset.tolist())}
+    rows = torch.tensor([pos[int(a)] for a in anchors])
+    got = emb[anchors.cuda()][:, subset.cuda()].cpu()
+    assert rel_l2(got, want[rows]) < 1e-5
+    del emb
+
+
+def test_config5_full_forward(large_pair):
+    d, data = large_pair
+    model = seeded_model(0).cuda()
+    torch.cuda.synchronize()
+    out = model(data)
+    torch.cuda.synchronize()
+    T = out["estimated_transform"].double().cpu()
+    assert torch.isfinite(T).all() and torch.equal(T[3], torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64))
+    R = T[:3, :3]
+    assert float((R @ R.T - torch.eye(3, dtype=torch.float64)).norm()) < 1e-4 and abs(float(torch.det(R)) - 1.0) < 1e-4
+    assert out["ref_feats_c"].shape[0] > 3000
+    nrm = out["ref_feats_c"].norm(dim=1)
+    assert float((nrm - 1).abs().max()) < 1e-4
+    ms = out["matching_scores"]
+    assert ms.shape[1:] == (129, 129) and not torch.isnan(ms).any()
+    # determinism at full size
+    out2 = model(data)
+    assert torch.equal(out2["estimated_transform"], out["estimated_transform"])
