@@ -357,37 +357,58 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
-  {
-    // superpoint-sized products (M ~ 500) yield a handful of 128-row tiles: the FFMA kernel with 32x32 tiles
-    // fills the machine better than 4 tensor-core CTAs
-    const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
-    const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * batch;
-    const long long slices = (batch == 1 && K > 1152 && N % 4 == 0) ? (K + 767) / 768 : 1;  // (estimate with the default slice)
-    if (tiles * slices < 24) return 1;
+  static int kSlice = 0, kSched = 1;
+  if (kSlice == 0) {
+    const char* e = getenv("GAUSSREG_KSLICE");  // longest K chained into one TMEM accumulator (multiple of 32); default 768
+    kSlice = e ? atoi(e) : 768;
+    if (kSlice < 32 || kSlice % 32 != 0) kSlice = 768;
+    e = getenv("GAUSSREG_SPLITK_SCHED");        // 1: wave-aware slice count (default), 0: slice only for accuracy
+    kSched = e ? atoi(e) : 1;
   }
+  const int bn = (N > 128 && use_bn256()) ? 256 : (N > 64 ? 128 : 64);
+  const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn) * batch;
+  // ---- how many K slices?
+  // (a) accuracy: the tensor core's fp32 accumulation truncates, so the error grows with the number of MMA steps
+  //     chained into one accumulator; K beyond 1.5 x kSlice is cut into slices of at most kSlice, each accumulated
+  //     in its own TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.
+  // (b) occupancy: a 128-row tile grid rarely matches 148 SMs.  Among the slice counts allowed by (a), take the
+  //     one that minimises  waves x (slice length + fixed cost per CTA) + cost of the reduction pass
+  //     (calibrated on B200: ~0.06 us per unit of K per wave, ~6 us fixed, partial sums at ~3 TB/s).
+  int splits = 1, slice = K;
+  const bool may_split = batch == 1 && N % 4 == 0;
+  if (may_split && K > kSlice + kSlice / 2) { splits = (K + kSlice - 1) / kSlice; slice = kSlice; }
+  if (may_split && kSched && K >= 256) {
+    const long long slots = 148ll * (bn == 64 ? 2 : 1);
+    double best = 1e30;
+    int best_s = splits, best_slice = slice;
+    const int s_max = K / 128 < 64 ? K / 128 : 64;
+    for (int sc = 1; sc <= s_max; ++sc) {
+      int sl = ((K + sc - 1) / sc + 31) / 32 * 32;
+      if (sl > kSlice + kSlice / 2) continue;  // rule (a)
+      const int se = (K + sl - 1) / sl;
+      const long long waves = (tiles * se + slots - 1) / slots;
+      double cost = (double)waves * (0.06 * sl + 6.0);
+      if (se > 1) cost += 4.0 + 2.0 * se * (double)M * N * 4.0 / 3.0e6;
+      if (cost < best) { best = cost; best_s = se; best_slice = sl; }
+    }
+    splits = best_s; slice = best_slice;
+  }
+  // superpoint-sized products (M ~ 500) that still yield only a handful of CTAs: the FFMA kernel with 32x32 tiles
+  // fills the machine better
+  if (tiles * splits < 24) return 1;
   tc::Params p;
   p.A = A; p.B = B; p.C = C; p.bias = bias; p.row_div = row_div; p.residual = residual;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.sA = sA; p.sB = sB; p.sC = sC; p.sR = sR;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act; p.k_split = 0;
   p.B_packed = (batch == 1) ? B_packed : nullptr;
   p.packed_kblocks = (K + 31) / 32;
-  // The tensor core's fp32 accumulation truncates, so the error grows linearly with the number of MMA steps
-  // chained into one accumulator.  Long K is therefore cut into slices of kSlice, each accumulated in its own
-  // TMEM tile, and the slices are summed in fp32 (round-to-nearest) by splitk_reduce_kernel.
-  static int kSlice = 0;
-  if (kSlice == 0) {
-    const char* e = getenv("GAUSSREG_KSLICE");  // tuning knob (multiple of 32); default 768
-    kSlice = e ? atoi(e) : 768;
-    if (kSlice < 32 || kSlice % 32 != 0) kSlice = 768;
-  }
-  if (batch == 1 && K > kSlice + kSlice / 2 && N % 4 == 0) {
-    const int splits = (K + kSlice - 1) / kSlice;
+  if (splits > 1) {
     float* partial = splitk_scratch(st, (size_t)splits * M * N * sizeof(float));
     if (partial == nullptr) return GR_ERR_CUDA;
     tc::Params q = p;
     q.C = partial; q.ldc = N; q.sC = (long long)M * N; q.bias = nullptr; q.row_div = nullptr; q.residual = nullptr;
-    q.alpha = 1.f; q.act = 0; q.k_split = kSlice;
-    int rc = (N > 128 && use_bn256()) ? tc::launch<256>(q, splits, st) : (N > 64 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
+    q.alpha = 1.f; q.act = 0; q.k_split = slice;
+    int rc = bn == 256 ? tc::launch<256>(q, splits, st) : (bn == 128 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
     if (rc == GR_OK) {
       const long long total = (long long)M * (N / 4);
       tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);

@@ -26,19 +26,23 @@ __global__ void __launch_bounds__(256) row_positive_kernel(const float* __restri
 }
 
 // GROUP lanes cooperate on one query, each lane owns CPL consecutive channels per pass.
+// The gather is what bounds this kernel (one L2 round trip per neighbour row), so the neighbour loop is unrolled by
+// four with all four row loads issued before the FMAs; rows are padded to a multiple of four with zero-weight
+// entries (the shadow neighbour contributes exactly 0 in the reference as well), weights are read as float4.
 template <int GROUP, int CPL>
 __global__ void __launch_bounds__(128) kpconv_aggregate_kernel(
     const float* __restrict__ feats, int C, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
     const long long* __restrict__ idx, int H, long long ldi, int M, int Ns, const float* __restrict__ kp, float sigma,
     const unsigned char* __restrict__ pos_flag, float* __restrict__ A, float* __restrict__ row_div) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   constexpr int QPW = 32 / GROUP;  // queries per warp
+  const int Hp = (H + 3) & ~3;
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / GROUP, gl = lane % GROUP;
   const int slot = warp * QPW + sub;
-  float* w = smem + (size_t)slot * H * 16;                            // [H][15] weights
-  int* nidx = reinterpret_cast<int*>(w + (size_t)H * kKP);            // [H] neighbour index (or -1)
+  float* w = smem + (size_t)slot * Hp * 17;                           // [Hp][16] weights (k = 15 is padding)
+  int* nidx = reinterpret_cast<int*>(w + (size_t)Hp * 16);            // [Hp] neighbour index (or -1)
   const int m = (blockIdx.x * warps + warp) * QPW + sub;
   const bool active = m < M;
 
@@ -49,22 +53,28 @@ __global__ void __launch_bounds__(128) kpconv_aggregate_kernel(
   int cnt = 0;
   if (active) {
     const float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
-    for (int h = gl; h < H; h += GROUP) {
-      const long long j = idx[(long long)m * ldi + h];
+    for (int h = gl; h < Hp; h += GROUP) {
+      const long long j = h < H ? idx[(long long)m * ldi + h] : -1;
+      float4* w4 = reinterpret_cast<float4*>(w + h * 16);
       if (j >= Ns || j < 0) {
         nidx[h] = -1;
+        w4[0] = w4[1] = w4[2] = w4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
       }
       nidx[h] = (int)j;
       cnt += pos_flag[j];
       // (s - q) - kp, squared norm, each op rounded separately like the ATen elementwise chain
       const float dx = __fsub_rn(s_pts[3 * j], qx), dy = __fsub_rn(s_pts[3 * j + 1], qy), dz = __fsub_rn(s_pts[3 * j + 2], qz);
+      float wk[16];
 #pragma unroll
       for (int k = 0; k < kKP; ++k) {
         const float ex = __fsub_rn(dx, kx[k]), ey = __fsub_rn(dy, ky[k]), ez = __fsub_rn(dz, kz[k]);
         const float sq = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-        w[h * kKP + k] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(sqrtf(sq), sigma)), 0.0f);
+        wk[k] = fmaxf(__fsub_rn(1.0f, __fdiv_rn(sqrtf(sq), sigma)), 0.0f);
       }
+      wk[15] = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) w4[k4] = make_float4(wk[4 * k4], wk[4 * k4 + 1], wk[4 * k4 + 2], wk[4 * k4 + 3]);
     }
   }
   // neighbour count of the group
@@ -82,26 +92,36 @@ __global__ void __launch_bounds__(128) kpconv_aggregate_kernel(
     for (int k = 0; k < kKP; ++k)
 #pragma unroll
       for (int v = 0; v < CPL; ++v) acc[k][v] = 0.f;
-    for (int h = 0; h < H; ++h) {
-      const int j = nidx[h];
-      if (j < 0) continue;
-      float f[CPL];
-      if constexpr (CPL == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(&feats[(long long)j * C + c0]);
-        f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-      } else if constexpr (CPL == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(&feats[(long long)j * C + c0]);
-        f[0] = t.x; f[1] = t.y;
-      } else {
+    for (int h0 = 0; h0 < Hp; h0 += 4) {
+      float f[4][CPL];
 #pragma unroll
-        for (int v = 0; v < CPL; ++v) f[v] = feats[(long long)j * C + c0 + v];
+      for (int u = 0; u < 4; ++u) {
+        const int j = nidx[h0 + u];
+#pragma unroll
+        for (int v = 0; v < CPL; ++v) f[u][v] = 0.f;
+        if (j >= 0) {
+          const float* src = feats + (long long)j * C + c0;
+          if constexpr (CPL == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+            f[u][0] = t.x; f[u][1] = t.y; f[u][2] = t.z; f[u][3] = t.w;
+          } else if constexpr (CPL == 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(src));
+            f[u][0] = t.x; f[u][1] = t.y;
+          } else {
+#pragma unroll
+            for (int v = 0; v < CPL; ++v) f[u][v] = __ldg(src + v);
+          }
+        }
       }
-      const float* wh = w + h * kKP;
 #pragma unroll
-      for (int k = 0; k < kKP; ++k) {
-        const float wk = wh[k];
+      for (int u = 0; u < 4; ++u) {
+        const float4* w4 = reinterpret_cast<const float4*>(w + (h0 + u) * 16);
+        const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
+        const float wk[kKP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z};
 #pragma unroll
-        for (int v = 0; v < CPL; ++v) acc[k][v] = fmaf(wk, f[v], acc[k][v]);
+        for (int k = 0; k < kKP; ++k)
+#pragma unroll
+          for (int v = 0; v < CPL; ++v) acc[k][v] = fmaf(wk[k], f[u][v], acc[k][v]);
       }
     }
     float* out = A + (long long)m * kKP * C + c0;
@@ -124,7 +144,7 @@ static int launch_aggregate(const float* feats, int C, const float* q, const flo
                             long long ldi, int M, int Ns, const float* kp, float sigma, const unsigned char* flag, float* A,
                             float* row_div, cudaStream_t st) {
   constexpr int QPW = 32 / GROUP;
-  const size_t per_slot = (size_t)H * 16 * sizeof(float);
+  const size_t per_slot = (size_t)((H + 3) & ~3) * 17 * sizeof(float);
   int warps = 4;
   while (warps > 1 && per_slot * QPW * warps > 96 * 1024) warps >>= 1;
   const size_t smem = per_slot * QPW * warps;
