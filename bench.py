@@ -138,6 +138,15 @@ class OpProfiler:
                 key = "gr_linear_packed[tcgen05]" if self._lib.gr_last_gemm_path() == 1 else "gr_linear_packed[ffma]"
             elif name == "gr_structure_embedding_fused":  # (d_idx, a_idx, rows, angle_k, div, hidden, ...)
                 work = 2.0 * a[2] * (1 + a[3]) * a[5] * a[5]
+            # algorithmic HBM bytes of the HBM-class ops (SURVEY.md section 8(d) formulas)
+            elif name in ("gr_radius_neighbors", "gr_radius_neighbors_cached"):  # (q, s, ql, sl, batch, nq, ns, radius, out, ld, ...)
+                work = 12.0 * (a[5] + a[6]) + 8.0 * a[5] * a[9]
+                key = "gr_radius_neighbors"
+            elif name == "gr_kpconv_aggregate":  # (feats, C, q, s, idx, H, ld_idx, M, Ns, kp, nkp, sigma, A, ...)
+                C, H, M, Ns = a[1], a[5], a[7], a[8]
+                work = 8.0 * M * H + 12.0 * (M + Ns) + 4.0 * Ns * C + 4.0 * M * 15 * C
+            elif name == "gr_group_norm":  # (x, n_rows, C, ...)
+                work = 2.0 * 4.0 * a[1] * a[2]
             self.records.append((key, s, e, work, shape))
             return r
 
@@ -178,6 +187,43 @@ def clocks_sampler_stop(proc):
                 reasons.add(nm)
     return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
             "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rpe_microbench(dev, n=479, iters=20):
+    """The superpoint-attention stream kernel alone (rpe_scores_softmax_v2_kernel at the bench's superpoint count):
+    algorithmic bytes = the (N,N,256) embedding read once + the (4,N,N) scores read and written, CUDA events on the
+    launch stream, a 256 MB L2 flush before every launch."""
+    from gaussreg_b200 import _lib
+    from gaussreg_b200.ext import _stream
+    L = _lib.lib()
+    C, H = 256, 4
+    g = torch.Generator(device="cpu").manual_seed(0)
+    q = torch.randn(n, C, generator=g).to(dev)
+    k = torch.randn(n, C, generator=g).to(dev)
+    U = torch.randn(H, n, C, generator=g).to(dev)
+    qb = torch.randn(H, n, generator=g).to(dev)
+    emb = torch.randn(n, n, C, generator=g).to(dev)
+    P = torch.empty(H, n, n, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    evs = []
+    for i in range(iters + 2):
+        flush.fill_(i & 0xff)
+        # the q.k^T product first (separate kernel), then time only the streaming kernel: call the C entry, which
+        # issues both; the GEMM is ~4 us of the total and is included (conservative)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        st = L.gr_rpe_attention_probs(q.data_ptr(), k.data_ptr(), U.data_ptr(), qb.data_ptr(), emb.data_ptr(), n, C, H,
+                                      P.data_ptr(), _stream())
+        e.record()
+        if st != 0:
+            return None
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ms = sorted(s.elapsed_time(e) for s, e in evs[2:])
+    med = ms[len(ms) // 2]
+    nbytes = 4.0 * n * n * C + 2 * 4.0 * H * n * n + 4.0 * H * n * C
+    return {"achieved": nbytes / (med * 1e-3) / 1e9, "unit": "GB/s", "avg_launch_ms": med, "algorithmic_bytes": nbytes,
+            "note": "gr_rpe_attention_probs alone (q.k^T batched GEMM + streaming kernel), N=%d superpoints, L2 flushed" % n}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -300,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
         n_tc = sum(1 for r in lib.records if r[0] in tc_keys)
         achieved_tf = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         roofline = {
-            "kernel": "gemm_tf32x3_kernel + structure_embedding_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
+            "kernel": "gemm_tf32x3_kernel + structure_embedding_tc256_kernel (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
             "peak_source": peaks["source"] + " bf16 sustained (cuBLAS); kind::tf32 issues at half the bf16 rate and every fp32 "
@@ -314,12 +360,35 @@ def run_ours(args, rank, world, local_rank):
             n_t1 = sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused")
             t1_rows = int(t1_flop / max(n_t1, 1) / (2.0 * 4 * 256 * 256))  # pair-rows per launch (N^2)
             roofline["largest_single_kernel"] = {
-                "kernel": "structure_embedding_tc_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                "kernel": "structure_embedding_tc256_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                 "frac": t1_flop / (t1_ms * 1e-3) / 1e12 / peaks["tf_sustained"], "avg_launch_ms": t1_ms / max(n_t1, 1),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_full_structure_embedding_tc.csv
-                "traffic": 188.1e6, "traffic_source": "ncu --set full capture (N=479 superpoints), not re-measured live",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01f_launches_by_kernel.txt)
+                "traffic": 198.4e6, "traffic_source": "ncu capture of a bench step (N=479/488 superpoints), not re-measured live",
                 "algorithmic_bytes": 4.0 * t1_rows * (256 + 4),  # (N^2, 256) output + d/a indices
             }
+        # HBM-class kernels of the same profiled step: algorithmic bytes / event time against the measured copy peak
+        hbm = {}
+        n_calls = {}
+        for r in lib.records:
+            n_calls[r[0]] = n_calls.get(r[0], 0) + 1
+        for k in ("gr_radius_neighbors", "gr_kpconv_aggregate", "gr_group_norm"):
+            if per_op.get(k, 0.0) > 0:
+                gbs = work[k] / (per_op[k] * 1e-3) / 1e9
+                hbm[k] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                          "algorithmic_bytes_per_step": work[k], "calls_per_step": n_calls.get(k, 0), "ms_per_step": per_op[k]}
+        rpe = rpe_microbench(dev)
+        if rpe is not None:
+            rpe["peak"] = peaks["hbm_gbs"]
+            rpe["frac"] = rpe["achieved"] / peaks["hbm_gbs"]
+            hbm["rpe_scores_softmax_v2_kernel"] = rpe
+        roofline["hbm_class_kernels"] = hbm
+        traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(traffic_path):
+            tj = json.load(open(traffic_path))
+            roofline["traffic"] = tj["tensor_core_kernels"]["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tj["source"]
+            roofline["algorithmic_bytes_per_launch"] = sum(
+                4.0 * (sh[0] * sh[2] + sh[1] * sh[2] + sh[0] * sh[1]) * sh[3] * v[0] for sh, v in gemm_shapes.items()) / max(n_tc, 1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sd, impl, ccfg, limits = cpu_reference_setup()

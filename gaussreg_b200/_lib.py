@@ -31,6 +31,7 @@ _SIGNATURES = {
     "gr_grid_subsample": (_i32, [_vp, _vp, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_radius_neighbors_workspace_size": (_sz, [_i64, _i64, _i32]),
     "gr_radius_neighbors": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "gr_radius_neighbors_cached": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _i32, _vp]),
     "gr_gemm": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                        _vp, _i64, _i64, _i32, _vp]),
     "gr_linear_packed": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -181,9 +181,11 @@ extern "C" int gr_kpconv_aggregate(const float* s_feats, int C, const float* q_p
   }
   const long long* idx = reinterpret_cast<const long long*>(neighbor_idx);
 #define GR_AGG(G, V) return launch_aggregate<G, V>(s_feats, C, q_points, s_points, idx, H, ld_idx, M, Ns, kernel_points, sigma, flag, A, row_div, st)
+  // the kernel is bound by instruction issue, not bandwidth: four channels per lane where C allows it (two queries
+  // per warp for C = 64 / 32) keeps the FMA share of the instruction stream high
   if (C % 128 == 0) GR_AGG(32, 4);
-  if (C % 64 == 0) GR_AGG(32, 2);
-  if (C % 32 == 0) GR_AGG(32, 1);
+  if (C % 64 == 0) GR_AGG(16, 4);
+  if (C % 32 == 0) GR_AGG(16, 2);
   if (C == 16) GR_AGG(16, 1);
   if (C == 8) GR_AGG(8, 1);
   if (C == 4) GR_AGG(4, 1);

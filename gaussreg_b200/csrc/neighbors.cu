@@ -744,10 +744,13 @@ extern "C" size_t gr_radius_neighbors_workspace_size(int64_t nq, int64_t ns, int
   return carve_g2(nullptr, 0, ns, batch, &ok).bytes;
 }
 
-extern "C" int gr_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
-                                   const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
-                                   int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
-                                   void* stream) {
+/* Same search; `reuse_grid` != 0 promises that `ws` still holds the cell grid a previous call built for the SAME
+ * (s_points, s_lengths, radius): the support cloud is not binned again (of the 13 searches of one pyramid only 5 use
+ * a new support cloud / radius combination). */
+extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                                          const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
+                                          int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
+                                          int reuse_grid, void* stream) {
   if (batch <= 0 || nq < 0 || ns < 0 || !q_lengths || !s_lengths || !out_max_count || (out_idx && ld <= 0) ||
       nq >= (1ll << 31) || ns >= (1ll << 31) || (int64_t)batch * kCellsPerCloud >= (1ll << 31))
     return GR_ERR_BAD_ARG;
@@ -759,6 +762,19 @@ extern "C" int gr_radius_neighbors(const float* q_points, const float* s_points,
   const size_t ncell = (size_t)batch * kCellsPerCloud + 1;
 
   GR_CHECK_CUDA(cudaMemsetAsync(out_max_count, 0, sizeof(int32_t), st));
+  if (reuse_grid) {
+    // only the query offsets change (the bounding boxes this kernel resets are not needed once the grid exists)
+    prep_offsets_kernel<<<1, 256, 0, st>>>(q_lengths, w.q_off, nullptr, nullptr, batch, w.bbox, w.scalars, 8);
+    GR_CHECK_LAUNCH("prep_offsets_kernel");
+    if (nq > 0) {
+      const float r2 = radius * radius;
+      radius_search_kernel<<<ceil_div(nq, kSearchWarps), kSearchWarps * 32, 0, st>>>(
+          q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
+          (long long)ld, out_max_count);
+      GR_CHECK_LAUNCH("radius_search_kernel");
+    }
+    return GR_OK;
+  }
   GR_CHECK_CUDA(cudaMemsetAsync(w.cell_cnt, 0, ncell * sizeof(uint32_t), st));
   prep_offsets_kernel<<<1, 256, 0, st>>>(q_lengths, w.q_off, s_lengths, w.s_off, batch, w.bbox, w.scalars, 8);
   GR_CHECK_LAUNCH("prep_offsets_kernel");
@@ -788,6 +804,14 @@ extern "C" int gr_radius_neighbors(const float* q_points, const float* s_points,
     GR_CHECK_LAUNCH("radius_search_kernel");
   }
   return GR_OK;
+}
+
+extern "C" int gr_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                                   const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
+                                   int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  return gr_radius_neighbors_cached(q_points, s_points, q_lengths, s_lengths, batch, nq, ns, radius, out_idx, ld, out_max_count,
+                                    ws, ws_bytes, 0, stream);
 }
 
 extern "C" size_t gr_grid_subsample_workspace_size(int64_t n_points, int batch) {

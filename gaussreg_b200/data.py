@@ -35,17 +35,24 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     lengths_list = len_dev
 
     # --- radius searches into limit-wide tables, then one sync for the widths
+    # Stage i's support cloud is searched with radius r_i by "neighbors" and "subsampling" of stage i and (r_i = 2 r_{i-1})
+    # by "upsampling" of stage i-1: one cell grid per stage serves all three (5 grids for 13 searches).
     tables, counts, meta = [], [], []
+    grids = [ext.radius_grid_workspace(points_list[i], lengths_list[i]) for i in range(num_stages)]
+    built = [False] * num_stages
     r = radius
     for i in range(num_stages):
         cur_p, cur_l = points_list[i], lengths_list[i]
-        t, c = ext.radius_neighbors_device(cur_p, cur_p, cur_l, cur_l, r, neighbor_limits[i])
+        t, c = ext.radius_neighbors_device(cur_p, cur_p, cur_l, cur_l, r, neighbor_limits[i], grid_ws=grids[i], reuse_grid=built[i])
+        built[i] = True
         tables.append(t); counts.append(c); meta.append(("neighbors", neighbor_limits[i]))
         if i < num_stages - 1:
             sub_p, sub_l = points_list[i + 1], lengths_list[i + 1]
-            t, c = ext.radius_neighbors_device(sub_p, cur_p, sub_l, cur_l, r, neighbor_limits[i])
+            t, c = ext.radius_neighbors_device(sub_p, cur_p, sub_l, cur_l, r, neighbor_limits[i], grid_ws=grids[i], reuse_grid=True)
             tables.append(t); counts.append(c); meta.append(("subsampling", neighbor_limits[i]))
-            t, c = ext.radius_neighbors_device(cur_p, sub_p, cur_l, sub_l, r * 2, neighbor_limits[i + 1])
+            t, c = ext.radius_neighbors_device(cur_p, sub_p, cur_l, sub_l, r * 2, neighbor_limits[i + 1], grid_ws=grids[i + 1],
+                                               reuse_grid=built[i + 1])
+            built[i + 1] = True
             tables.append(t); counts.append(c); meta.append(("upsampling", neighbor_limits[i + 1]))
         r *= 2
     widths = torch.cat(counts).cpu().tolist()  # sync 2

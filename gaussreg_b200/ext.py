@@ -88,20 +88,30 @@ def grid_subsampling(points, lengths, voxel_size):
     return [s_points.contiguous() if m != out.shape[0] else s_points, out_len]
 
 
-def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None):
+def radius_grid_workspace(s_points, s_lengths):
+    """A dedicated workspace for one support cloud, so that its cell grid can be reused by later searches."""
+    nbytes = _lib.lib().gr_radius_neighbors_workspace_size(0, s_points.shape[0], s_lengths.shape[0])
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=s_points.device)
+
+
+def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None, grid_ws=None, reuse_grid=False):
     """Sync-free core: fills a (Nq, ld) int64 table (first min(count, ld) sorted neighbours per row,
-    padded with Ns) and returns (table, max_count device scalar)."""
+    padded with Ns) and returns (table, max_count device scalar).  `grid_ws` (radius_grid_workspace) keeps the
+    support cloud's cell grid; pass reuse_grid=True on later searches of the same (support, radius)."""
     L = _lib.lib()
     dev = q_points.device
     nq, ns, batch = q_points.shape[0], s_points.shape[0], q_lengths.shape[0]
     max_count = torch.empty((1,), dtype=torch.int32, device=dev)
     if out is None and ld > 0:
         out = torch.empty((nq, ld), dtype=torch.int64, device=dev)
-    nbytes = L.gr_radius_neighbors_workspace_size(nq, ns, batch)
-    ws = _workspace(nbytes, dev)
-    st = L.gr_radius_neighbors(q_points.data_ptr(), s_points.data_ptr(), q_lengths.data_ptr(), s_lengths.data_ptr(),
-                               batch, nq, ns, float(radius), out.data_ptr() if out is not None else None,
-                               int(ld), max_count.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    if grid_ws is None:
+        if reuse_grid:
+            raise RuntimeError("reuse_grid needs the grid_ws of the call that built the grid")
+        grid_ws = _workspace(L.gr_radius_neighbors_workspace_size(nq, ns, batch), dev)
+    st = L.gr_radius_neighbors_cached(q_points.data_ptr(), s_points.data_ptr(), q_lengths.data_ptr(), s_lengths.data_ptr(),
+                                      batch, nq, ns, float(radius), out.data_ptr() if out is not None else None,
+                                      int(ld), max_count.data_ptr(), grid_ws.data_ptr(), grid_ws.numel(), int(reuse_grid),
+                                      _stream())
     _lib.check(st, "radius_neighbors")
     return out, max_count
 

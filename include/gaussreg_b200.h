@@ -78,6 +78,12 @@ size_t gr_radius_neighbors_workspace_size(int64_t nq, int64_t ns, int batch);
 int gr_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
                         const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius, int64_t* out_idx,
                         int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes, void* stream);
+/* Same, with reuse_grid != 0 promising that `ws` still holds the cell grid built by an earlier call for the same
+ * (s_points, s_lengths, radius): the support cloud is not binned again. */
+int gr_radius_neighbors_cached(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                               const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
+                               int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
+                               int reuse_grid, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense fp32 product with fused epilogue (used by K1 contraction, K2 Linear, T1-T3 projections,
