@@ -226,6 +226,27 @@ def rpe_microbench(dev, n=479, iters=20):
             "note": "gr_rpe_attention_probs alone (q.k^T batched GEMM + streaming kernel), N=%d superpoints, L2 flushed" % n}
 
 
+def throughput_mode(model, pairs, dev, n_pairs=16, streams=2):
+    """BASELINE configs 3/4 style: a list of pairs through parallel.register_pairs, sequentially and software-
+    pipelined over `streams` CUDA streams (pyramid of pair i+1 under the network of pair i).  Host buffers in, one
+    D2H of all transforms out; not the headline `value` (that is one pair per step, strictly serial)."""
+    from gaussreg_b200 import parallel
+    jobs = [pairs[i % len(pairs)] for i in range(n_pairs)]
+    out = {}
+    for name, ns in (("sequential", 1), (f"pipelined_{streams}_streams", streams)):
+        parallel.register_pairs(model, jobs[:3], streams=ns)  # warm the per-stream workspaces
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        T = parallel.register_pairs(model, jobs, streams=ns).cpu()
+        e.record()
+        torch.cuda.synchronize()
+        out[name] = {"pairs": n_pairs, "ms": s.elapsed_time(e), "pairs_per_s": n_pairs / (s.elapsed_time(e) * 1e-3)}
+        out.setdefault("checksum", float(T.double().sum()))
+        out["same_result"] = bool(abs(out["checksum"] - float(T.double().sum())) == 0.0)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -390,6 +411,9 @@ def run_ours(args, rank, world, local_rank):
             roofline["algorithmic_bytes_per_launch"] = sum(
                 4.0 * (sh[0] * sh[2] + sh[1] * sh[2] + sh[0] * sh[1]) * sh[3] * v[0] for sh, v in gemm_shapes.items()) / max(n_tc, 1)
         cpu = None
+        throughput = None
+        if world == 1 and not args.no_throughput:
+            throughput = throughput_mode(model, [make_pair_inputs(100 + i, N_POINTS) for i in range(4)], dev)
         if world == 1 and not args.no_cpu_baseline:
             sd, impl, ccfg, limits = cpu_reference_setup()
             sec = cpu_reference_step(sd, impl, ccfg, limits, pairs[0])
@@ -409,6 +433,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "throughput_mode": throughput,
             "per_op_ms": {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
             "profiled_step_ms": prof_step_ms, "top_op": top,
             "gemm_shapes_MNKbatchT_count_ms": [[list(k), v[0], round(v[1], 4)] for k, v in
@@ -426,6 +451,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-throughput", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -34,13 +34,18 @@ def gather_transforms(local_transforms, n_pairs, rank=None, world=None):
     return out.view(world, per, 4, 4).transpose(0, 1).reshape(world * per, 4, 4)[:n_pairs].contiguous()
 
 
-def register_pairs(model, pairs, cfg=None, neighbor_limits=None):
+def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1):
     """Coarse-register a list of scene pairs (BASELINE configs 3 / 4): every rank runs the pairs it owns through
     the single-pair forward (the reference model is batch-1 only, model.py:77-89; pairs never interact), one
     all-gather returns all transforms in pair order to every rank.
 
     `pairs`: sequence of dicts with ref_points / src_points / ref_feats / src_feats (numpy or tensors), indexed
-    globally; each rank touches only `pairs[rank::world]`.  Returns a (len(pairs), 4, 4) float32 CUDA tensor."""
+    globally; each rank touches only `pairs[rank::world]`.  Returns a (len(pairs), 4, 4) float32 CUDA tensor.
+
+    `streams` > 1 software-pipelines consecutive pairs over that many CUDA streams: the neighbour pyramid of pair
+    i+1 (a few CTAs per kernel, two host syncs for its data-dependent sizes) then overlaps the network of pair i.
+    Every per-call scratch buffer of the library is keyed by stream, so the results are bit-identical to the
+    sequential order; the first pair always runs alone (it packs the static weights other streams then read)."""
     from .config import make_cfg, NEIGHBOR_LIMITS
     from .data import registration_collate_fn_stack_mode
     cfg = cfg or make_cfg()
@@ -51,8 +56,36 @@ def register_pairs(model, pairs, cfg=None, neighbor_limits=None):
     mine = shard_pairs(len(pairs), rank, world)
     local = torch.empty((len(mine), 4, 4), dtype=torch.float32, device=dev)
     keys = ("ref_points", "src_points", "ref_feats", "src_feats")
-    for j, i in enumerate(mine):
+
+    def one(j, i):
         data = registration_collate_fn_stack_mode([{k: pairs[i][k] for k in keys}], cfg.backbone.num_stages,
                                                   cfg.backbone.init_voxel_size, cfg.backbone.init_radius, limits)
         local[j] = model(data)["estimated_transform"]
+
+    if streams <= 1 or len(mine) <= 1:
+        for j, i in enumerate(mine):
+            one(j, i)
+    else:
+        cur = torch.cuda.current_stream()
+        one(0, mine[0])
+        cur.synchronize()
+        pool = _stream_pool(dev, streams)
+        for s in pool:
+            s.wait_stream(cur)
+        for j, i in enumerate(mine[1:], start=1):
+            with torch.cuda.stream(pool[j % streams]):
+                one(j, i)
+        for s in pool:
+            cur.wait_stream(s)
     return gather_transforms(local, len(pairs), rank, world)
+
+
+_STREAM_POOLS = {}
+
+
+def _stream_pool(dev, n):
+    """Streams are kept for the life of the process: the library's per-stream workspaces are keyed by them."""
+    pool = _STREAM_POOLS.setdefault(dev.index, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]

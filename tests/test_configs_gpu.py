@@ -33,6 +33,10 @@ def test_config3_many_pairs_order_independent():
     assert torch.equal(T1, T3), "repeat run differs: state leaks between pairs"
     assert torch.equal(T1, T2), "order-dependent result: state leaks between pairs"
     assert torch.isfinite(T1).all()
+    # software-pipelined over two / three streams: same bits
+    T4 = parallel.register_pairs(model, pairs, streams=2).cpu()
+    T5 = parallel.register_pairs(model, pairs, streams=3).cpu()
+    assert torch.equal(T1, T4) and torch.equal(T1, T5), "stream-pipelined result differs from the sequential one"
     # a sampled pair against the CPU oracle (north_star tolerance 1e-4 Frobenius on the LGR transform)
     with torch.no_grad():
         want = onet.forward(seeded_model(0).state_dict(), oracle_data(specs[1]))

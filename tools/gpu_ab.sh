@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
   i=$((i+1))
-  env $cfg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
+  env $cfg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-throughput > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
   python - "$cfg" gpurun_out/ab_$i.json <<'PY'
 import json, sys
 try:

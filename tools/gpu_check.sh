@@ -17,8 +17,8 @@ PY
 if [ "$1" = "ncu" ]; then
   timeout 400 ncu --set full --clock-control none --import-source on \
     -k regex:'structure_embedding_tc_kernel|rpe_scores_softmax_v2_kernel|sinkhorn_kernel|hash_order_replay_kernel' -c 5 \
-    -f -o gpurun_out/ncu_full_misc python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_misc.log 2>&1
+    -f -o gpurun_out/ncu_full_misc python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-throughput > gpurun_out/ncu_misc.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:'gemm_tf32x3_kernel' -s 8 -c 4 \
-    -f -o gpurun_out/ncu_full_gemm python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
+    -f -o gpurun_out/ncu_full_gemm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-throughput > gpurun_out/ncu_gemm.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi
