@@ -373,6 +373,8 @@ def run_ours(args, rank, world, local_rank):
             "peak_source": peaks["source"] + " bf16 sustained (cuBLAS); kind::tf32 issues at half the bf16 rate and every fp32 "
                                              "product costs 3 MMAs, so tensor-pipe occupancy ~= 6 x frac",
             "tensor_pipe_equiv_frac": 6.0 * achieved_tf / peaks["tf_sustained"],
+            # the MMA rate actually issued (3 tf32 MMAs per fp32 product) against the tf32 peak (= bf16 peak / 2)
+            "tf32_mma_tflops": 3.0 * achieved_tf, "tf32_peak_tflops": peaks["tf_sustained"] / 2.0,
             "launches_per_step": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
             "flop_per_step_fp32_equiv": tc_flop, "share_of_step": tc_ms / max(sum(per_op.values()), 1e-9),
         }
@@ -383,6 +385,8 @@ def run_ours(args, rank, world, local_rank):
             roofline["largest_single_kernel"] = {
                 "kernel": "structure_embedding_tc256_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                 "frac": t1_flop / (t1_ms * 1e-3) / 1e12 / peaks["tf_sustained"], "avg_launch_ms": t1_ms / max(n_t1, 1),
+                "tf32_mma_tflops": 3.0 * t1_flop / (t1_ms * 1e-3) / 1e12,
+                "frac_of_tf32_peak": 3.0 * t1_flop / (t1_ms * 1e-3) / 1e12 / (peaks["tf_sustained"] / 2.0),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01f_launches_by_kernel.txt)
                 "traffic": 198.4e6, "traffic_source": "ncu capture of a bench step (N=479/488 superpoints), not re-measured live",
                 "algorithmic_bytes": 4.0 * t1_rows * (256 + 4),  # (N^2, 256) output + d/a indices

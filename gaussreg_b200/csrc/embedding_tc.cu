@@ -72,6 +72,20 @@ __device__ __forceinline__ void sincos_fp32(float a, float* s, float* c) {
   }
 }
 
+// |a| < 0.5: Taylor kernels (truncation < 2e-11), no range reduction
+__device__ __forceinline__ void sincos_small(float a, float* s, float* c) {
+  const float a2 = a * a;
+  float ps = fmaf(a2, 2.7557319e-6f, -1.9841270e-4f);
+  ps = fmaf(ps, a2, 8.3333333e-3f);
+  ps = fmaf(ps, a2, -1.6666667e-1f);
+  *s = fmaf(a * a2, ps, a);
+  float pc = fmaf(a2, -2.7557319e-7f, 2.4801587e-5f);
+  pc = fmaf(pc, a2, -1.3888889e-3f);
+  pc = fmaf(pc, a2, 4.1666667e-2f);
+  pc = fmaf(pc, a2, -0.5f);
+  *c = fmaf(pc, a2, 1.0f);
+}
+
 // Branch-free sin / cos for the arguments this model produces (|a| < ~100): three-term Cody-Waite reduction by
 // pi/2 (the products are exact inside the FMAs), degree-9 / degree-10 minimax-free Taylor kernels on
 // [-pi/4, pi/4], quadrant fix-up by selects.  Measured against float64 over 2e6 arguments in [-64, 64]:
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
 
   if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
   if (tid == 0) {
-    for (int s = 0; s < kEmbStages; ++s) { mbar_init(full_bar(s), kEmbProducers); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kEmbStages; ++s) { mbar_init(full_bar(s), kEmbProducers / 32); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,8 +191,11 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + kEmbTile + off) = lo;
       }
+      // every lane fences its own stores towards the async proxy; ONE arrival per warp (512 single arrivals on one
+      // mbarrier word serialise for the better part of a microsecond per k-block)
       fence_proxy_async();
-      mbar_arrive(full_bar(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
     }
     // ---------------------------------------------------------------- epilogue
     mbar_wait(accum_bar, 0);
@@ -269,6 +286,12 @@ constexpr int kE2BTile = kE2BN * kEmbBK * 4;         // 32 KB
 constexpr int kE2StageBytes = 2 * kE2ATile + 2 * kE2BTile;  // 96 KB
 constexpr int kE2Smem = kE2Stages * kE2StageBytes + 1024 + 256;
 
+// CL = 2: thread-block clusters of two CTAs (two row tiles).  Both CTAs need the same weight tile at the same step,
+// and the weight stream out of L2 (64 KB per k-block per SM, hi + lo) is what bounds this kernel once the operand is
+// generated only once: CTA 0 fetches the hi half, CTA 1 the lo half, each multicast into both CTAs' stage (every
+// CTA's full barrier sees all 64 KB).  A stage may be overwritten in BOTH CTAs only when both tensor cores have
+// consumed it, so every MMA commit is multicast to both CTAs' empty barriers (arrival count 2).
+template <int CL>
 __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kernel(
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
@@ -283,6 +306,7 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
   auto slot_free = [&](int s) { return bar_base + 8u * (2 * kE2Stages + 1 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kE2Stages + 3);
   __shared__ float s_div[kEmbC / 2];
+  __shared__ float s_xmax[4][kEmbProducers / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long r0 = (long long)blockIdx.x * kEmbBM;
@@ -291,10 +315,10 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
 
   if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
   if (tid == 0) {
-    for (int s = 0; s < kE2Stages; ++s) { mbar_init(full_bar(s), kEmbProducers); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kE2Stages; ++s) { mbar_init(full_bar(s), kEmbProducers / 32); mbar_init(empty_bar(s), CL); }
     mbar_init(accum_bar, 1);
-    mbar_init(slot_free(0), kEmbProducers);
-    mbar_init(slot_free(1), kEmbProducers);
+    mbar_init(slot_free(0), kEmbProducers / 32);
+    mbar_init(slot_free(1), kEmbProducers / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr int kMmaWarp = kEmbProducers / 32;
@@ -305,6 +329,8 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp < kMmaWarp) {
@@ -315,6 +341,24 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
     if (valid) {
       for (int k = 0; k < angle_k; ++k) xg[k] = a_idx[r * angle_k + k];
       xg[angle_k] = d_idx[r];
+    }
+    // largest |index| of this row tile per product: a k-block whose largest argument stays below 0.5 rad for EVERY
+    // row takes the short Taylor kernels without range reduction (a CTA-uniform branch, no divergence)
+    {
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const float mg = warp_max(fabsf(xg[g4]));
+        if (lane == 0) s_xmax[g4][warp] = mg;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEmbProducers) : "memory");  // producer warps only
+    }
+    float xmax[4];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      float mg = 0.f;
+#pragma unroll
+      for (int w = 0; w < kEmbProducers / 32; ++w) mg = fmaxf(mg, s_xmax[g4][w]);
+      xmax[g4] = mg;
     }
     const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter / 64-column group read by this warp
     const uint32_t my_tmem = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
@@ -340,7 +384,8 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
           for (int j = 0; j < 16; ++j) mx[c16 * 16 + j] = fmaxf(mx[c16 * 16 + j], __uint_as_float(t[j]));
         }
         tc_fence_before();
-        mbar_arrive(slot_free((g - 1) & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(slot_free((g - 1) & 1));
       }
       unsigned char* st = smem + s * kE2StageBytes;
       if (tid == 0) {
@@ -350,19 +395,32 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {  // packed tile (nt, kb) = [hi 16 KB][lo 16 KB]
           const float* src = wsrc + ((size_t)(nt * kEmbKB + kb)) * (2 * kEmbTile / 4);
-          bulk_copy_g2s(b_hi + nt * kEmbTile, src, kEmbTile, full_bar(s));
-          bulk_copy_g2s(b_lo + nt * kEmbTile, src + kEmbTile / 4, kEmbTile, full_bar(s));
+          if (CL == 1) {
+            bulk_copy_g2s(b_hi + nt * kEmbTile, src, kEmbTile, full_bar(s));
+            bulk_copy_g2s(b_lo + nt * kEmbTile, src + kEmbTile / 4, kEmbTile, full_bar(s));
+          } else if (crank == 0) {
+            bulk_copy_g2s_multicast(b_hi + nt * kEmbTile, src, kEmbTile, full_bar(s), (uint16_t)0x3);
+          } else {
+            bulk_copy_g2s_multicast(b_lo + nt * kEmbTile, src + kEmbTile / 4, kEmbTile, full_bar(s), (uint16_t)0x3);
+          }
         }
       }
       const float x = g == 0 ? xg[0] : (g == 1 ? xg[1] : (g == 2 ? xg[2] : xg[3]));
+      const float xm = g == 0 ? xmax[0] : (g == 1 ? xmax[1] : (g == 2 ? xmax[2] : xmax[3]));
+      const bool small_args = xm * s_div[kb * 16] < 0.5f;  // div_term decreases with the frequency index
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int c = h8 * 2 + jj;
         const int i0 = kb * 16 + c * 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-          sincos_cw(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
-          sincos_cw(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          if (small_args) {
+            sincos_small(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+            sincos_small(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          } else {
+            sincos_cw(__fmul_rn(x, s_div[i0]), &v.x, &v.y);
+            sincos_cw(__fmul_rn(x, s_div[i0 + 1]), &v.z, &v.w);
+          }
         }
         float4 hi, lo;
         hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
@@ -371,8 +429,11 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + kE2ATile + off) = lo;
       }
+      // every lane fences its own stores towards the async proxy; ONE arrival per warp (512 single arrivals on one
+      // mbarrier word serialise for the better part of a microsecond per k-block)
       fence_proxy_async();
-      mbar_arrive(full_bar(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
     }
     // ---------------------------------------------------------------- epilogue
     // Read-outs happen at kb == 2 of the FOLLOWING product, so every angle product has been folded into mx by now;
@@ -429,13 +490,15 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
           umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
           umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
         }
-        umma_commit(empty_bar(s));
+        if (CL == 1) umma_commit(empty_bar(s));
+        else umma_commit_multicast(empty_bar(s), (uint16_t)0x3);
       }
       umma_commit(accum_bar);
     }
     __syncwarp();
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer may still multicast into this CTA's stages / barriers until it is done too
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(512));
@@ -467,21 +530,40 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
   if (rows == 0) return GR_OK;
   if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
   static bool attr_set = false;
-  static int cw = 1, width = 256;
+  static int cw = 1, width = 256, cluster = 1;
   if (!attr_set) {
     GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
     GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
-    const char* e = getenv("GAUSSREG_T1_SINCOS");  // 0: libm sincosf + small-argument polynomial, 1: branch-free Cody-Waite
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
+    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
+    // 2: CTA pairs share the weight stream by multicast.  Correct, but measured SLOWER on B200 (1.24 vs 1.18 ms per
+    // pair): the kernel is paced by its producers' instruction issue, not by L2, and the pair adds hand-over stalls.
+    const char* e = getenv("GAUSSREG_T1_CLUSTER");
+    cluster = e ? atoi(e) : 1;
+    e = getenv("GAUSSREG_T1_SINCOS");  // 0: libm sincosf + small-argument polynomial, 1: branch-free Cody-Waite
     cw = e ? atoi(e) : 1;
     e = getenv("GAUSSREG_T1_WIDTH");               // 256: full-width CTA with ping-pong TMEM slots, 128: two column halves
     width = e ? atoi(e) : 256;
     attr_set = true;
   }
   if (width == 256) {
-    tc::structure_embedding_tc256_kernel<<<(unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM), tc::kEmbThreads, tc::kE2Smem,
-                                           static_cast<cudaStream_t>(stream)>>>(d_idx, a_idx, rows, angle_k, div_term, wd_packed,
-                                                                                wa_packed, bias_d, bias_a, out);
+    const unsigned tiles = (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM);
+    if (cluster == 2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((tiles + 1) / 2 * 2);  // whole pairs; a padding CTA runs the protocol on rows >= `rows` and stores nothing
+      cfg.blockDim = dim3(tc::kEmbThreads);
+      cfg.dynamicSmemBytes = tc::kE2Smem;
+      cfg.stream = static_cast<cudaStream_t>(stream);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::structure_embedding_tc256_kernel<2>, d_idx, a_idx, (long long)rows, angle_k, div_term,
+                                       wd_packed, wa_packed, bias_d, bias_a, out));
+    } else {
+      tc::structure_embedding_tc256_kernel<1><<<tiles, tc::kEmbThreads, tc::kE2Smem, static_cast<cudaStream_t>(stream)>>>(
+          d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+    }
     GR_CHECK_LAUNCH("structure_embedding_tc256_kernel");
     return GR_OK;
   }

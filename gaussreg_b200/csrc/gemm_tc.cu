@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
   const int nkb = (kend - kbeg + BK - 1) / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), kProducerThreads / 32); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
       tile_store<BM>(ra, st, st + C::kABytes, tid);
       if (!packed) tile_store<BN>(rb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, tid);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(full_bar(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));  // one arrival per warp: 256 single arrivals on one word serialise
       if (kb + 1 < nkb) {
         ra = ra_next;
         if (!packed) rb = rb_next;

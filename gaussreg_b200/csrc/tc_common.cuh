@@ -93,5 +93,31 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
                : "memory");
 }
 
+// ---- thread-block clusters: multicast bulk copy / multicast commit / cluster barrier ---------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> the SAME shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes that landed in it
+__device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                        uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// arrive (once) on the mbarrier at this offset in every CTA of cta_mask when all prior tcgen05 ops of this thread finish
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+
 }  // namespace tc
 }  // namespace gr
