@@ -89,3 +89,29 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
         collated["lengths"] = lengths.to(dev)
     collated["batch_size"] = batch_size
     return collated
+
+
+def calibrate_neighbors_stack_mode(dataset, collate_fn, num_stages, voxel_size, search_radius, keep_ratio=0.8,
+                                   sample_threshold=2000):
+    """utils/data.py:192-217: neighbour limits such that `keep_ratio` of the points keep all their neighbours.
+
+    Same signature and integer-exact result; the pyramids come from the CUDA kernels (through `collate_fn`, normally
+    `registration_collate_fn_stack_mode`), the neighbourhood-size histograms are accumulated on the device and only
+    the (num_stages, hist_n) table crosses to the host."""
+    hist_n = int(np.ceil(4 / 3 * np.pi * (search_radius / voxel_size + 1) ** 3))
+    max_neighbor_limits = [hist_n] * num_stages
+    neighbor_hists = None
+    for i in range(len(dataset)):
+        data_dict = collate_fn([dataset[i]], num_stages, voxel_size, search_radius, max_neighbor_limits, precompute_data=True)
+        hists = []
+        for neighbors in data_dict["neighbors"]:
+            counts = (neighbors < neighbors.shape[0]).sum(dim=1)
+            hists.append(torch.bincount(counts, minlength=hist_n)[:hist_n])
+        h = torch.stack(hists)
+        neighbor_hists = h if neighbor_hists is None else neighbor_hists + h
+        if int(neighbor_hists.sum(dim=1).min()) > sample_threshold:
+            break
+    neighbor_hists = neighbor_hists.cpu().numpy().astype(np.int32)
+    cum_sum = np.cumsum(neighbor_hists.T, axis=0)
+    neighbor_limits = np.sum(cum_sum < (keep_ratio * cum_sum[hist_n - 1, :]), axis=0)
+    return neighbor_limits

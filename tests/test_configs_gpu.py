@@ -125,3 +125,18 @@ def test_config5_full_forward(large_pair):
     # determinism at full size
     out2 = model(data)
     assert torch.equal(out2["estimated_transform"], out["estimated_transform"])
+
+
+def test_calibrate_neighbors_matches_reference_golden():
+    """utils/data.py:192-217 on the CUDA pyramid: integer-exact against the limits the unmodified reference computed."""
+    import os
+    import sys
+    from gaussreg_b200.data import calibrate_neighbors_stack_mode
+    from tests.helpers import GOLDEN_DIR
+    sys.path.insert(0, GOLDEN_DIR)
+    from make_calibration_golden import SPEC, dataset
+    gold = np.load(os.path.join(GOLDEN_DIR, "calibration_golden.npz"))
+    s = SPEC
+    limits = calibrate_neighbors_stack_mode(dataset(), registration_collate_fn_stack_mode, s["num_stages"], s["voxel_size"],
+                                            s["search_radius"], s["keep_ratio"], s["sample_threshold"])
+    assert np.array_equal(np.asarray(limits), gold["neighbor_limits"]), (limits, gold["neighbor_limits"])
