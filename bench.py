@@ -247,6 +247,40 @@ def throughput_mode(model, pairs, dev, n_pairs=16, streams=2):
     return out
 
 
+def pyramid_batched(pairs, dev, n_pairs=32, reps=3):
+    """BASELINE config 3 shape for the neighbour pyramid alone: `n_pairs` pairs stacked [ref_1..ref_P, src_1..src_P]
+    (utils/data.py:139-189 with batch_size = P) through ONE precompute_data_stack_mode call.  At batch 1 these kernels
+    are latency-bound; this shows what they reach when every launch has P times the work.  Algorithmic bytes:
+    G1 12 N_in + 12 M_out per call, G2 12 (Nq + Ns) + 8 Nq W per call."""
+    from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+    from gaussreg_b200.data import precompute_data_stack_mode
+    cfg = make_cfg()
+    refs = [torch.from_numpy(pairs[i % len(pairs)]["ref_points"]) for i in range(n_pairs)]
+    srcs = [torch.from_numpy(pairs[i % len(pairs)]["src_points"]) for i in range(n_pairs)]
+    pts = torch.cat(refs + srcs).to(dev)
+    lens = torch.tensor([p.shape[0] for p in refs + srcs], dtype=torch.int64, device=dev)
+    best, data = None, None
+    for _ in range(reps + 1):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                          cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        best = ms if best is None else min(best, ms)
+    n = [p.shape[0] for p in data["points"]]
+    nbytes = 0.0
+    for i in range(len(n)):
+        nbytes += 24.0 * n[i] + 8.0 * n[i] * data["neighbors"][i].shape[1]
+        if i + 1 < len(n):
+            nbytes += 12.0 * n[i] + 12.0 * n[i + 1]                                           # G1
+            nbytes += 12.0 * (n[i + 1] + n[i]) + 8.0 * n[i + 1] * data["subsampling"][i].shape[1]
+            nbytes += 12.0 * (n[i] + n[i + 1]) + 8.0 * n[i] * data["upsampling"][i].shape[1]
+    return {"pairs": n_pairs, "stage_points": n, "ms": best, "ms_per_pair": best / n_pairs, "pairs_per_s": n_pairs / (best * 1e-3),
+            "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / (best * 1e-3) / 1e9}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -417,7 +451,10 @@ def run_ours(args, rank, world, local_rank):
         cpu = None
         throughput = None
         if world == 1 and not args.no_throughput:
-            throughput = throughput_mode(model, [make_pair_inputs(100 + i, N_POINTS) for i in range(4)], dev)
+            extra_pairs = [make_pair_inputs(100 + i, N_POINTS) for i in range(4)]
+            throughput = throughput_mode(model, extra_pairs, dev)
+            throughput["pyramid_batched"] = pyramid_batched(extra_pairs, dev)
+            throughput["pyramid_batched"]["frac_of_hbm_peak"] = throughput["pyramid_batched"]["achieved_GBps"] / read_peaks()["hbm_gbs"]
         if world == 1 and not args.no_cpu_baseline:
             sd, impl, ccfg, limits = cpu_reference_setup()
             sec = cpu_reference_step(sd, impl, ccfg, limits, pairs[0])

@@ -17,6 +17,7 @@ constexpr int kMaxQueries = 16;
 
 struct SelectQueries {
   int col[kMaxQueries];
+  unsigned int rank[kMaxQueries];
   int n;
 };
 
@@ -72,10 +73,9 @@ __global__ void select_pick_kernel(unsigned int* __restrict__ hist, SelState* __
   }
 }
 
-__global__ void select_init_kernel(SelState* __restrict__ state, const unsigned int* __restrict__ ranks, int nq,
-                                   unsigned int* __restrict__ hist) {
+__global__ void select_init_kernel(SelState* __restrict__ state, SelectQueries qs, unsigned int* __restrict__ hist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nq) { state[i].prefix = 0u; state[i].rank = ranks[i]; }
+  if (i < qs.n) { state[i].prefix = 0u; state[i].rank = qs.rank[i]; }
   if (i < kMaxQueries * 256) hist[i] = 0u;
 }
 
@@ -265,18 +265,15 @@ extern "C" int gr_column_order_stats(const float* cloud, int64_t n, int ld, cons
   Carver c(ws, ws_bytes);
   unsigned int* hist = c.take<unsigned int>((size_t)kMaxQueries * 256);
   SelState* state = c.take<SelState>(kMaxQueries);
-  unsigned int* d_ranks = c.take<unsigned int>(kMaxQueries);
-  SelectQueries qs;
-  unsigned int h_ranks[kMaxQueries];
+  SelectQueries qs;  // travels as a kernel argument: no host buffer outlives the call, no hidden synchronisation
   qs.n = n_queries;
   for (int q = 0; q < n_queries; ++q) {
     if (cols[q] < 0 || cols[q] >= ld || ranks[q] < 0 || ranks[q] >= n) return GR_ERR_BAD_ARG;
     qs.col[q] = cols[q];
-    h_ranks[q] = (unsigned int)ranks[q];
+    qs.rank[q] = (unsigned int)ranks[q];
   }
-  GR_CHECK_CUDA(cudaMemcpyAsync(d_ranks, h_ranks, n_queries * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
-  GR_CHECK_CUDA(cudaStreamSynchronize(st));  // h_ranks lives on this stack frame
-  select_init_kernel<<<ceil_div(kMaxQueries * 256, 256), 256, 0, st>>>(state, d_ranks, n_queries, hist);
+  for (int q = n_queries; q < kMaxQueries; ++q) { qs.col[q] = 0; qs.rank[q] = 0u; }
+  select_init_kernel<<<ceil_div(kMaxQueries * 256, 256), 256, 0, st>>>(state, qs, hist);
   GR_CHECK_LAUNCH("select_init_kernel");
   const int blocks = (int)min((long long)148 * 8, (long long)ceil_div(n, 256));
   for (int pass = 0; pass < 4; ++pass) {
