@@ -233,12 +233,12 @@ def throughput_mode(model, pairs, dev, n_pairs=16, streams=2):
     from gaussreg_b200 import parallel
     jobs = [pairs[i % len(pairs)] for i in range(n_pairs)]
     out = {}
-    for name, ns in (("sequential", 1), (f"pipelined_{streams}_streams", streams)):
-        parallel.register_pairs(model, jobs[:3], streams=ns)  # warm the per-stream workspaces
+    for name, ns, pb in (("sequential", 1, 1), (f"pipelined_{streams}_streams", streams, 1), ("batched_pyramid_8", 1, 8)):
+        parallel.register_pairs(model, jobs[:8 if pb > 1 else 3], streams=ns, pyramid_batch=pb)  # warm the workspaces
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        T = parallel.register_pairs(model, jobs, streams=ns).cpu()
+        T = parallel.register_pairs(model, jobs, streams=ns, pyramid_batch=pb).cpu()
         e.record()
         torch.cuda.synchronize()
         out[name] = {"pairs": n_pairs, "ms": s.elapsed_time(e), "pairs_per_s": n_pairs / (s.elapsed_time(e) * 1e-3)}

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "gr_gather_points_stats": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "gr_gaussian_features": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     "gr_points_normalize": (_i32, [_vp, _i64, _vp, _f32, _i32, _vp]),
+    "gr_pair_major_rows": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "gr_pair_major_table": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 
 _STATUS = {-1: "bad argument", -2: "workspace too small", -3: "capacity overflow", -4: "CUDA error"}

@@ -115,3 +115,76 @@ def calibrate_neighbors_stack_mode(dataset, collate_fn, num_stages, voxel_size, 
     cum_sum = np.cumsum(neighbor_hists.T, axis=0)
     neighbor_limits = np.sum(cum_sum < (keep_ratio * cum_sum[hist_n - 1, :]), axis=0)
     return neighbor_limits
+
+
+def precompute_pairs_stack_mode(ref_points_list, src_points_list, num_stages, voxel_size, radius, neighbor_limits):
+    """ONE neighbour pyramid for P pairs (BASELINE configs 3 / 4), returned as P single-pair pyramids.
+
+    The clouds are stacked [ref_1..ref_P, src_1..src_P] as `registration_collate_fn_stack_mode` stacks a batch
+    (utils/data.py:139-189) and go through precompute_data_stack_mode once: every grid subsample / radius search
+    kernel then carries P pairs' work per launch.  csrc/pairs.cu re-orders each stage to pair-major order and
+    re-bases the neighbour indices, so that pair i's `points / neighbors / subsampling / upsampling` are row
+    slices (views) -- bit-identical to what the single-pair call returns, including the table widths
+    `min(max_count_of_that_pair, limit)`.  Host syncs: three per batch instead of two per pair.
+
+    Returns a list of dicts with the keys of precompute_data_stack_mode plus `lengths_host` (python ints, lets the
+    model skip its own device->host read of the stage lengths)."""
+    from . import _lib
+    L = _lib.lib()
+    P = len(ref_points_list)
+    assert P == len(src_points_list) and P > 0
+    dev = ext._device()
+    clouds = [torch.as_tensor(p) for p in list(ref_points_list) + list(src_points_list)]
+    points = torch.cat([c.to(dev, torch.float32, non_blocking=True) for c in clouds], dim=0)
+    lengths = torch.tensor([c.shape[0] for c in clouds], dtype=torch.int64, device=dev)
+    g = precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits)
+    st = ext._stream()
+    zero = torch.zeros((1,), dtype=torch.int64, device=dev)
+    ref_off = [torch.cat([zero, torch.cumsum(l[:P], 0)]) for l in g["lengths"]]   # (P+1,) per stage
+    src_off = [torch.cat([zero, torch.cumsum(l[P:], 0)]) for l in g["lengths"]]
+    pm_points = []
+    for i in range(num_stages):
+        src, out = g["points"][i].contiguous(), torch.empty_like(g["points"][i])
+        _lib.check(L.gr_pair_major_rows(src.data_ptr(), 3, src.shape[0], ref_off[i].data_ptr(), src_off[i].data_ptr(), P,
+                                        out.data_ptr(), st), "pair_major_rows")
+        pm_points.append(out)
+    tables, widths = {}, []
+    for key, q_stage, s_stage in ([("neighbors", i, i) for i in range(num_stages)] +
+                                  [("subsampling", i + 1, i) for i in range(num_stages - 1)] +
+                                  [("upsampling", i, i + 1) for i in range(num_stages - 1)]):
+        idx = q_stage if key != "subsampling" else s_stage
+        t = g[key][idx]
+        ld = t.stride(0)
+        out = torch.empty((t.shape[0], ld), dtype=torch.int64, device=dev)
+        w = torch.empty((P,), dtype=torch.int32, device=dev)
+        _lib.check(L.gr_pair_major_table(t.data_ptr(), ld, t.shape[1], t.shape[0], ref_off[q_stage].data_ptr(),
+                                         src_off[q_stage].data_ptr(), ref_off[s_stage].data_ptr(), src_off[s_stage].data_ptr(),
+                                         P, out.data_ptr(), w.data_ptr(), st), "pair_major_table")
+        tables.setdefault(key, []).append(out)
+        widths.append(w)
+    host_len = torch.stack(g["lengths"]).cpu().tolist()                 # (stages, 2P)     -- sync 3
+    host_w = torch.stack(widths).cpu().tolist()                         # (13, P)
+    order = ([("neighbors", i) for i in range(num_stages)] + [("subsampling", i) for i in range(num_stages - 1)] +
+             [("upsampling", i) for i in range(num_stages - 1)])
+    limits = {"neighbors": lambda i: neighbor_limits[i], "subsampling": lambda i: neighbor_limits[i],
+              "upsampling": lambda i: neighbor_limits[i + 1]}
+    q_stage_of = {"neighbors": lambda i: i, "subsampling": lambda i: i + 1, "upsampling": lambda i: i}
+    pm_start = [[0] * (P + 1) for _ in range(num_stages)]
+    for s_ in range(num_stages):
+        for i in range(P):
+            pm_start[s_][i + 1] = pm_start[s_][i] + host_len[s_][i] + host_len[s_][P + i]
+    out_list = []
+    for i in range(P):
+        d = {"points": [], "lengths": [], "lengths_host": [], "neighbors": [], "subsampling": [], "upsampling": []}
+        for s_ in range(num_stages):
+            a, b = pm_start[s_][i], pm_start[s_][i + 1]
+            d["points"].append(pm_points[s_][a:b])
+            d["lengths_host"].append((host_len[s_][i], host_len[s_][P + i]))
+            d["lengths"].append(torch.stack([g["lengths"][s_][i], g["lengths"][s_][P + i]]))
+        for row, (key, k) in enumerate(order):
+            qs = q_stage_of[key](k)
+            a, b = pm_start[qs][i], pm_start[qs][i + 1]
+            w = min(int(host_w[row][i]), limits[key](k))
+            d[key].append(tables[key][k][a:b, :w])
+        out_list.append(d)
+    return out_list

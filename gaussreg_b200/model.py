@@ -45,8 +45,12 @@ class GeoTransformer(nn.Module):
         feats = data_dict["features"]
         lengths = data_dict["lengths"]
         # stage lengths are needed on the host to slice ref / src (model.py:77-79 does three .item() syncs)
-        lens = torch.stack([lengths[-1], lengths[1], lengths[0]]).cpu()
-        ref_length_c, ref_length_f, ref_length = int(lens[0, 0]), int(lens[1, 0]), int(lens[2, 0])
+        host = data_dict.get("lengths_host")  # extension: stage lengths already known on the host (batched pyramid)
+        if host is not None:
+            ref_length_c, ref_length_f, ref_length = int(host[-1][0]), int(host[1][0]), int(host[0][0])
+        else:
+            lens = torch.stack([lengths[-1], lengths[1], lengths[0]]).cpu()
+            ref_length_c, ref_length_f, ref_length = int(lens[0, 0]), int(lens[1, 0]), int(lens[2, 0])
         points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
         ref_points_c, src_points_c = points_c[:ref_length_c], points_c[ref_length_c:]
         ref_points_f, src_points_f = points_f[:ref_length_f], points_f[ref_length_f:]

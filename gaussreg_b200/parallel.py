@@ -34,13 +34,17 @@ def gather_transforms(local_transforms, n_pairs, rank=None, world=None):
     return out.view(world, per, 4, 4).transpose(0, 1).reshape(world * per, 4, 4)[:n_pairs].contiguous()
 
 
-def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1):
+def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1, pyramid_batch=1):
     """Coarse-register a list of scene pairs (BASELINE configs 3 / 4): every rank runs the pairs it owns through
     the single-pair forward (the reference model is batch-1 only, model.py:77-89; pairs never interact), one
     all-gather returns all transforms in pair order to every rank.
 
     `pairs`: sequence of dicts with ref_points / src_points / ref_feats / src_feats (numpy or tensors), indexed
     globally; each rank touches only `pairs[rank::world]`.  Returns a (len(pairs), 4, 4) float32 CUDA tensor.
+
+    `pyramid_batch` > 1 builds ONE neighbour pyramid per that many pairs (data.precompute_pairs_stack_mode): the
+    ~170 latency-bound launches and the host syncs of the pyramid are shared by the whole group, the network still
+    runs pair by pair; results are bit-identical.
 
     `streams` > 1 software-pipelines consecutive pairs over that many CUDA streams: the neighbour pyramid of pair
     i+1 (a few CTAs per kernel, two host syncs for its data-dependent sizes) then overlaps the network of pair i.
@@ -62,7 +66,18 @@ def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1):
                                                   cfg.backbone.init_voxel_size, cfg.backbone.init_radius, limits)
         local[j] = model(data)["estimated_transform"]
 
-    if streams <= 1 or len(mine) <= 1:
+    if pyramid_batch > 1:
+        from .data import precompute_pairs_stack_mode
+        for g0 in range(0, len(mine), pyramid_batch):
+            group = mine[g0:g0 + pyramid_batch]
+            pyr = precompute_pairs_stack_mode([pairs[i]["ref_points"] for i in group], [pairs[i]["src_points"] for i in group],
+                                              cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, limits)
+            for j, (i, data) in enumerate(zip(group, pyr)):
+                data["features"] = torch.cat([torch.as_tensor(pairs[i]["ref_feats"]), torch.as_tensor(pairs[i]["src_feats"])],
+                                             dim=0).to(dev, torch.float32, non_blocking=True)
+                data["batch_size"] = 1
+                local[g0 + j] = model(data)["estimated_transform"]
+    elif streams <= 1 or len(mine) <= 1:
         for j, i in enumerate(mine):
             one(j, i)
     else:

@@ -237,6 +237,17 @@ int gr_gaussian_features(const float* cloud, int ld, const int64_t* index, int64
 /* points <- (points - center) [* scale] in float32 (demo.py:85-110); center3 HOST float[3]. */
 int gr_points_normalize(float* points, int64_t m, const float* center3, float scale, int apply_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Config 3 / 4: one neighbour pyramid for P pairs (utils/data.py:139-189 stacks [ref_1..ref_P, src_1..src_P]; the
+ * reference model is batch-1, model.py:77-89), then pair-major re-ordering so that every pair is a row slice.
+ * ref_off / src_off: device int64 [P+1] prefix sums of the per-cloud lengths of one pyramid stage.
+ * --------------------------------------------------------------------------------------------- */
+int gr_pair_major_rows(const float* in, int C, int64_t n_rows, const int64_t* ref_off, const int64_t* src_off, int P,
+                       float* out, void* stream);
+int gr_pair_major_table(const int64_t* in, int64_t ld, int W, int64_t n_rows, const int64_t* q_ref_off,
+                        const int64_t* q_src_off, const int64_t* s_ref_off, const int64_t* s_src_off, int P, int64_t* out,
+                        int32_t* widths, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

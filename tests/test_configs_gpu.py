@@ -37,6 +37,21 @@ def test_config3_many_pairs_order_independent():
     T4 = parallel.register_pairs(model, pairs, streams=2).cpu()
     T5 = parallel.register_pairs(model, pairs, streams=3).cpu()
     assert torch.equal(T1, T4) and torch.equal(T1, T5), "stream-pipelined result differs from the sequential one"
+    # one batched pyramid for groups of pairs (csrc/pairs.cu): same bits again, and the per-pair views equal the
+    # single-pair pyramid tensor for tensor
+    T6 = parallel.register_pairs(model, pairs, pyramid_batch=4).cpu()
+    T7 = parallel.register_pairs(model, pairs, pyramid_batch=6).cpu()
+    assert torch.equal(T1, T6) and torch.equal(T1, T7), "batched-pyramid result differs from the sequential one"
+    from gaussreg_b200.data import precompute_pairs_stack_mode
+    cfg = make_cfg()
+    args = (cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    batched = precompute_pairs_stack_mode([p["ref_points"] for p in pairs], [p["src_points"] for p in pairs], *args)
+    for p, b in zip(pairs, batched):
+        single = registration_collate_fn_stack_mode([{k: p[k] for k in KEYS}], *args)
+        for key in ("points", "neighbors", "subsampling", "upsampling"):
+            for x, y in zip(single[key], b[key]):
+                assert x.shape == y.shape and torch.equal(x, y), key
+        assert [tuple(l.tolist()) for l in single["lengths"]] == [tuple(l) for l in b["lengths_host"]]
     # a sampled pair against the CPU oracle (north_star tolerance 1e-4 Frobenius on the LGR transform)
     with torch.no_grad():
         want = onet.forward(seeded_model(0).state_dict(), oracle_data(specs[1]))
