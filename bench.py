@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 METRIC = "scene-pairs/sec coarse-reg fwd, 30k-Gaussian clouds"
 UNIT = "pairs/s"
-N_POINTS = 30000
+N_POINTS = int(os.environ.get("GAUSSREG_BENCH_POINTS", "30000"))  # BASELINE config 2; the override exists for the CPU contract test only
 WORKLOAD = "configs[1]: single 30k-Gaussian pair, full pyramid+KPConvFPN+GeometricTransformer+LGR fwd"
 
 

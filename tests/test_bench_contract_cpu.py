@@ -1,0 +1,33 @@
+"""CPU test of bench.py's reference arm (`--impl reference`): it must run without a GPU, print exactly one JSON
+line with the contract's keys, and rank != 0 must exit silently (the driver launches it under torchrun for N > 1).
+Runs on a 2k-point pair (env override) so that the whole CPU suite stays within minutes."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env):
+    env = dict(os.environ, GAUSSREG_BENCH_POINTS="2000", **extra_env)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "0"], env=env, capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = _run({"RANK": "0", "WORLD_SIZE": "1"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_reference_arm_other_ranks_are_silent():
+    p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert p.returncode == 0 and p.stdout.strip() == ""
