@@ -20,7 +20,7 @@ _sz = ctypes.c_size_t
 class LayerWeights(ctypes.Structure):
     """gr_layer_weights (include/gaussreg_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("wq", "bq", "wk", "bk", "wv", "bv", "wp", "bp", "wo", "bo", "ln1_g", "ln1_b",
-                                               "w1", "b1", "w2", "b2", "ln2_g", "ln2_b", "wqkv", "bqkv")] + [("is_self", ctypes.c_int)]
+                                               "w1", "b1", "w2", "b2", "ln2_g", "ln2_b", "wqkv", "bqkv", "w1t", "w2t")] + [("is_self", ctypes.c_int)]
 
 
 _SIGNATURES = {

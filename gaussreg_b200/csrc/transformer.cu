@@ -24,6 +24,106 @@ int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
 
 namespace gr {
 
+// ---- fused AttentionOutput (output_layer.py:14-21): y = LayerNorm(x + squeeze(relu(expand(x)))) -----------------
+// Three superpoint-sized launches (two GEMMs of ~0.1 GFLOP and a LayerNorm) are pure latency; here a CTA owns 8 rows,
+// keeps x, the 512 hidden units and the result in shared memory, streams the two K-major (pre-transposed) weight
+// matrices out of L2 with coalesced loads, and finishes with the LayerNorm of layernorm_add_kernel (same lane
+// mapping and reduction order).  C = 256 only.
+constexpr int kMlpRows = 8;
+constexpr int kMlpC = 256;
+
+__global__ void __launch_bounds__(kMlpC) transformer_mlp_kernel(const float* __restrict__ x, int N, const float* __restrict__ w1t,
+                                                               const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                               const float* __restrict__ b2, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  __shared__ __align__(16) float xs[kMlpRows][kMlpC];
+  __shared__ __align__(16) float hs[kMlpRows][2 * kMlpC];
+  __shared__ __align__(16) float ys[kMlpRows][kMlpC];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * kMlpRows;
+#pragma unroll
+  for (int r = 0; r < kMlpRows; ++r) xs[r][tid] = (row0 + r < N) ? x[(long long)(row0 + r) * kMlpC + tid] : 0.f;
+  __syncthreads();
+  {  // expand + ReLU: hidden units tid and tid + 256
+    float a0[kMlpRows], a1[kMlpRows];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+#pragma unroll 2
+    for (int k = 0; k < kMlpC; k += 4) {
+      float w0[4], w1[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        w0[kk] = __ldg(w1t + (long long)(k + kk) * (2 * kMlpC) + tid);
+        w1[kk] = __ldg(w1t + (long long)(k + kk) * (2 * kMlpC) + kMlpC + tid);
+      }
+#pragma unroll
+      for (int r = 0; r < kMlpRows; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k]);
+        a0[r] = fmaf(xv.x, w0[0], a0[r]); a1[r] = fmaf(xv.x, w1[0], a1[r]);
+        a0[r] = fmaf(xv.y, w0[1], a0[r]); a1[r] = fmaf(xv.y, w1[1], a1[r]);
+        a0[r] = fmaf(xv.z, w0[2], a0[r]); a1[r] = fmaf(xv.z, w1[2], a1[r]);
+        a0[r] = fmaf(xv.w, w0[3], a0[r]); a1[r] = fmaf(xv.w, w1[3], a1[r]);
+      }
+    }
+    const float bb0 = b1[tid], bb1 = b1[kMlpC + tid];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) {
+      hs[r][tid] = fmaxf(a0[r] + bb0, 0.f);
+      hs[r][kMlpC + tid] = fmaxf(a1[r] + bb1, 0.f);
+    }
+  }
+  __syncthreads();
+  {  // squeeze: output channel tid
+    float a[kMlpRows];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) a[r] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < 2 * kMlpC; k += 4) {
+      float w[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(w2t + (long long)(k + kk) * kMlpC + tid);
+#pragma unroll
+      for (int r = 0; r < kMlpRows; ++r) {
+        const float4 hv = *reinterpret_cast<const float4*>(&hs[r][k]);
+        a[r] = fmaf(hv.x, w[0], a[r]);
+        a[r] = fmaf(hv.y, w[1], a[r]);
+        a[r] = fmaf(hv.z, w[2], a[r]);
+        a[r] = fmaf(hv.w, w[3], a[r]);
+      }
+    }
+    const float bb = b2[tid];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) ys[r][tid] = a[r] + bb;
+  }
+  __syncthreads();
+  // LayerNorm(x + h): warp w owns row w, lane mapping and reduction order of layernorm_add_kernel
+  const int row = row0 + warp;
+  if (row >= N) return;
+  float v[kMlpC / 32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMlpC / 32; ++i) {
+    v[i] = xs[warp][lane + 32 * i] + ys[warp][lane + 32 * i];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)kMlpC;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMlpC / 32; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)kMlpC + eps);
+#pragma unroll
+  for (int i = 0; i < kMlpC / 32; ++i) {
+    const int c = lane + 32 * i;
+    y[(long long)row * kMlpC + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+static bool mlp_fused() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_TF_MLP"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
+
 struct TfWs {
   float *qkv, *U, *qb, *P, *hid, *att, *ffn, *y;
 };
@@ -96,6 +196,12 @@ static int layer(const gr_layer_weights& L, float* x, int N, const float* mem, i
   GR_TRY(gr_gemm(w.P, M, (int64_t)N * M, v, ldv, dh, 0, w.hid, C, dh, N, dh, M, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
   GR_TRY(linear(w.hid, N, C, L.wo, L.bo, C, w.att, 0, st));
   GR_TRY(gr_layer_norm_add(w.att, x, N, C, L.ln1_g, L.ln1_b, 1e-5f, w.y, st));
+  if (L.w1t && L.w2t && C == kMlpC && mlp_fused()) {
+    transformer_mlp_kernel<<<(N + kMlpRows - 1) / kMlpRows, kMlpC, 0, static_cast<cudaStream_t>(st)>>>(
+        w.y, N, L.w1t, L.b1, L.w2t, L.b2, L.ln2_g, L.ln2_b, 1e-5f, x);
+    GR_CHECK_LAUNCH("transformer_mlp_kernel");
+    return GR_OK;
+  }
   GR_TRY(linear(w.y, N, C, L.w1, L.b1, 2 * C, w.ffn, 1, st));
   GR_TRY(linear(w.ffn, N, 2 * C, L.w2, L.b2, C, w.att, 0, st));
   GR_TRY(gr_layer_norm_add(w.y, w.att, N, C, L.ln2_g, L.ln2_b, 1e-5f, x, st));

@@ -386,6 +386,19 @@ def _fused_qkv(att):
     return cached[1], cached[2]
 
 
+def _transposed(weight):
+    """(out, in) Linear weight -> contiguous (in, out) copy, cached on the parameter per version / device."""
+    cached = getattr(weight, "_gr_t", None)
+    key = (weight._version, weight.data_ptr())
+    if cached is None or cached[0] != key:
+        cached = (key, weight.detach().t().contiguous())
+        try:
+            weight._gr_t = cached
+        except AttributeError:
+            pass
+    return cached[1]
+
+
 def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, num_heads):
     """RPEConditionalTransformer.forward in one C-ABI call; feats are updated in place and returned."""
     import ctypes
@@ -412,6 +425,9 @@ def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, n
         wqkv, bqkv = _fused_qkv(att)
         keep.append((wqkv, bqkv))
         w.wqkv, w.bqkv = wqkv.data_ptr(), bqkv.data_ptr()
+        w1t, w2t = _transposed(o.expand.weight), _transposed(o.squeeze.weight)
+        keep.append((w1t, w2t))
+        w.w1t, w.w2t = w1t.data_ptr(), w2t.data_ptr()
     f0, f1 = _req(feats0).clone(), _req(feats1).clone()
     N0, C = f0.shape
     N1 = f1.shape[0]

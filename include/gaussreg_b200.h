@@ -180,6 +180,9 @@ typedef struct {
    * (self layers) or of a q product and a fused k|v product (cross layers); results are identical, there are
    * just fewer superpoint-sized launches.  NULL -> the separate matrices above are used. */
   const float *wqkv, *bqkv;
+  /* optional: output.expand / output.squeeze weights transposed to K-major, (C,2C) and (2C,C), for the fused
+   * AttentionOutput kernel (GAUSSREG_TF_MLP=1); NULL -> the two GEMMs + LayerNorm path. */
+  const float *w1t, *w2t;
   int is_self;
 } gr_layer_weights;
 size_t gr_conditional_transformer_workspace_size(int N0, int N1, int C, int num_heads);

@@ -77,7 +77,7 @@ def test_kpconv_vs_oracle(C, Co, H):
     assert rel_l2(got, want) < 1e-5
 
 
-@pytest.mark.parametrize("N,C", [(1000, 32), (5003, 64), (777, 2048), (300, 1024)])
+@pytest.mark.parametrize("N,C", [(1000, 32), (5003, 64), (777, 2048), (300, 1024), (3001, 256), (15000, 256)])
 def test_group_norm_and_fusions(N, C):
     x, add = _rand(N, C, seed=1) * 3 + 0.5, _rand(N, C, seed=2)
     gamma, beta = _rand(C, seed=3), _rand(C, seed=4)
