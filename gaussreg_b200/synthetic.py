@@ -53,7 +53,10 @@ def sh_basis_deg3(dirs):
 
 
 def gaussian_features(cloud):
-    """(N,59) Gaussian attributes -> (N,4) float32 network features [opacity, R, G, B] (demo.py:30-75)."""
+    """(N,59) Gaussian attributes -> (N,4) float32 network features [opacity, R, G, B] (demo.py:63-72, no filtering).
+
+    Part of the SYNTHETIC INPUT GENERATOR only (bench / tests build their host-side pairs with it).  The product's
+    implementation of this step is gaussians.read_cloud_by_opacity (csrc/gaussians.cu)."""
     cloud = np.asarray(cloud)
     pts = cloud[:, 0:3].astype(np.float64)
     f_dc = cloud[:, 3:6].astype(np.float64)  # (N,3)
