@@ -60,3 +60,20 @@ def test_oracle_forward_matches_reference_golden(case):
         assert rel_l2(out["corr_scores"], gold["corr_scores"]) < 1e-3
     # north_star tolerance on the transform: 1e-4 Frobenius
     assert float(np.linalg.norm(out["estimated_transform"].numpy() - gold["estimated_transform"])) < 1e-4
+
+
+def test_config_matches_reference_config():
+    """gaussreg_b200.config.make_cfg() carries exactly the model-related values of the reference's config.py
+    (golden produced by importing the unmodified reference, tests/golden/make_config_golden.py)."""
+    import json
+    from gaussreg_b200.config import make_cfg
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "config_golden.json")))
+    cfg = make_cfg()
+    for section, values in gold.items():
+        for key, want in values.items():
+            assert key in cfg[section], (section, key)
+            got = cfg[section][key]
+            if isinstance(want, float):
+                assert float(got) == want, (section, key, got, want)
+            else:
+                assert got == want, (section, key, got, want)
