@@ -25,52 +25,55 @@ COL_XYZ, COL_FDC, COL_FREST, COL_OPACITY = 0, 3, 6, 51
 ATTR_DIM = 59
 
 
-def eval_sh_deg3(sh, dirs):
-    """graphics_utils.py:34-89 with deg = 3.  sh (..., C, 16), dirs (..., 3) -> (..., C).  The expression trees are
-    kept exactly as the reference writes them (numpy rounds every binary operation separately)."""
-    result = C0 * sh[..., 0]
+def _sh_basis_terms(dirs):
+    """The 15 direction-only factors of the degree-1..3 real SH basis, each parenthesised the way Python evaluates
+    the reference's products (graphics_utils.py:60-88 multiply left to right: constant x monomial [x polynomial]),
+    paired with the sign with which the reference adds the term.  dirs (..., 3) -> list of (sign, (..., 1) array)."""
     x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
-    result = (result - C1 * y * sh[..., 1] + C1 * z * sh[..., 2] - C1 * x * sh[..., 3])
     xx, yy, zz = x * x, y * y, z * z
     xy, yz, xz = x * y, y * z, x * z
-    result = (result + C2[0] * xy * sh[..., 4] + C2[1] * yz * sh[..., 5] + C2[2] * (2.0 * zz - xx - yy) * sh[..., 6] +
-              C2[3] * xz * sh[..., 7] + C2[4] * (xx - yy) * sh[..., 8])
-    result = (result + C3[0] * y * (3 * xx - yy) * sh[..., 9] + C3[1] * xy * z * sh[..., 10] +
-              C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12] +
-              C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + C3[5] * z * (xx - yy) * sh[..., 14] +
-              C3[6] * x * (xx - 3 * yy) * sh[..., 15])
-    return result
+    band1 = [(-1, C1 * y), (+1, C1 * z), (-1, C1 * x)]
+    band2 = [(+1, C2[0] * xy), (+1, C2[1] * yz), (+1, C2[2] * (2.0 * zz - xx - yy)), (+1, C2[3] * xz), (+1, C2[4] * (xx - yy))]
+    band3 = [(+1, C3[0] * y * (3 * xx - yy)), (+1, C3[1] * xy * z), (+1, C3[2] * y * (4 * zz - xx - yy)),
+             (+1, C3[3] * z * (2 * zz - 3 * xx - 3 * yy)), (+1, C3[4] * x * (4 * zz - xx - yy)), (+1, C3[5] * z * (xx - yy)),
+             (+1, C3[6] * x * (xx - 3 * yy))]
+    return band1 + band2 + band3
+
+
+def eval_sh_deg3(sh, dirs):
+    """graphics_utils.py:34-89 with deg = 3.  sh (..., C, 16), dirs (..., 3) -> (..., C).  One running sum, term k
+    added (or subtracted) as `basis_k * sh[..., k]` in coefficient order: the same sequence of individually rounded
+    numpy operations as the reference's three chained expressions."""
+    acc = C0 * sh[..., 0]
+    for k, (sign, basis) in enumerate(_sh_basis_terms(dirs), start=1):
+        term = basis * sh[..., k]
+        acc = acc + term if sign > 0 else acc - term
+    return acc
 
 
 def read_cloud_by_opacity(cloud, point_limit=None):
     """demo.py:30-75 on an (N,59) float32 cloud.  Returns (points (M,3) f32, point_features (M,4) f32, index (M,))."""
     cloud = np.asarray(cloud, dtype=np.float32)
-    opacity = cloud[:, COL_OPACITY].copy()
-    opacity = 1 / (1 + np.exp(-opacity))                                       # :34 (float32)
-    x, y, z = cloud[:, 0].copy(), cloud[:, 1].copy(), cloud[:, 2].copy()
-    index_x = (x < np.percentile(x, 95)) * (x > np.percentile(x, 5))           # :40
-    index_y = (y < np.percentile(y, 95)) * (y > np.percentile(y, 5))
-    index_z = (z < np.percentile(z, 95)) * (z > np.percentile(z, 5))
-    index = np.where((opacity > 0.7) * index_x * index_y * index_z)[0]         # :43
-    points = np.stack([x, y, z], axis=1)
-    if point_limit is not None and index.shape[0] > point_limit:
+    alpha = cloud[:, COL_OPACITY].copy()
+    alpha = 1 / (1 + np.exp(-alpha))                                            # :34, float32 throughout
+    axes = [cloud[:, a].copy() for a in range(3)]
+    inside = [(c < np.percentile(c, 95)) * (c > np.percentile(c, 5)) for c in axes]   # :40-42
+    keep = np.where((alpha > 0.7) * inside[0] * inside[1] * inside[2])[0]       # :43
+    if point_limit is not None and keep.shape[0] > point_limit:
         raise NotImplementedError("farthest-point sampling (fpsample==0.3.2, demo.py:45-48) is third-party: parity unpinned")
-    features_dc = np.zeros((points.shape[0], 3, 1))                            # float64, :49-52
-    features_dc[:, :, 0] = cloud[:, COL_FDC:COL_FDC + 3]
-    features_extra = np.zeros((points.shape[0], 45))
-    features_extra[:, :] = cloud[:, COL_FREST:COL_FREST + 45]
-    features_extra = features_extra.reshape((features_extra.shape[0], 3, 15))   # :60
-    features = np.concatenate([features_dc, features_extra], axis=2)[index]     # (M,3,16)
-    points = points[index]
-    center_point = points.mean(0)                                               # float32, :63
-    max_length = np.linalg.norm(points.max(axis=0) - points.min(axis=0))
-    center_point = center_point + np.array([0, 2 * max_length, 0])              # float64 from here
-    dir_pp = points - center_point[None, :].repeat(points.shape[0], 0)
-    dir_pp_normalized = dir_pp / (np.linalg.norm(dir_pp, axis=1, keepdims=True) + 1e-6)
-    sh2rgb = eval_sh_deg3(features, dir_pp_normalized)
-    colors = np.clip(sh2rgb + 0.5, 0.0, 1.0) * 255
-    point_features = np.concatenate([opacity[index].reshape(points.shape[0], -1), colors.astype(np.float32)], axis=1)
-    return points, point_features, index
+    xyz = np.stack(axes, axis=1)[keep]                                           # float32 (M,3)
+    # float64 SH table (M, 3 channels, 16 coefficients): DC first, then the 15 higher-order ones per channel (:49-61)
+    coeffs = np.zeros((keep.shape[0], 3, 16))
+    coeffs[:, :, 0] = cloud[keep, COL_FDC:COL_FDC + 3]
+    coeffs[:, :, 1:] = cloud[keep, COL_FREST:COL_FREST + 45].astype(np.float64).reshape(-1, 3, 15)
+    eye = xyz.mean(0)                                                            # float32 mean, :63
+    diagonal = np.linalg.norm(xyz.max(axis=0) - xyz.min(axis=0))
+    eye = eye + np.array([0, 2 * diagonal, 0])                                   # float64 from here, :64
+    view = xyz - eye[None, :].repeat(xyz.shape[0], 0)
+    view = view / (np.linalg.norm(view, axis=1, keepdims=True) + 1e-6)
+    rgb = np.clip(eval_sh_deg3(coeffs, view) + 0.5, 0.0, 1.0) * 255
+    point_features = np.concatenate([alpha[keep].reshape(xyz.shape[0], -1), rgb.astype(np.float32)], axis=1)
+    return xyz, point_features, keep
 
 
 def _center_and_scale(points):
