@@ -9,7 +9,7 @@ A step = one pass of the hot path (neighbour pyramid G1/G2/G3 -> KPConvFPN -> Ge
 SuperPointMatching -> Sinkhorn -> LocalGlobalRegistration) over one synthetic 30k+30k Gaussian pair
 (BASELINE.json configs[1]).  `value` times it with the pair resident in HBM, `e2e` through the public
 API with pinned host buffers (H2D of points/features, D2H of the 4x4 transform inside the timed region).
-Multi-GPU: pairs are sharded rank-wise (weak scaling), one NCCL all-gather of the transforms per step.
+Multi-GPU: pairs are sharded rank-wise (weak scaling), ONE NCCL all-gather of all transforms after the last step.
 """
 import argparse
 import json
@@ -29,6 +29,13 @@ METRIC = "scene-pairs/sec coarse-reg fwd, 30k-Gaussian clouds"
 UNIT = "pairs/s"
 N_POINTS = int(os.environ.get("GAUSSREG_BENCH_POINTS", "30000"))  # BASELINE config 2; the override exists for the CPU contract test only
 WORKLOAD = "configs[1]: single 30k-Gaussian pair, full pyramid+KPConvFPN+GeometricTransformer+LGR fwd"
+
+
+def bench_config(world):
+    """The `config` object of the JSON line: identical in both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "n_points_per_cloud": N_POINTS, "pairs_per_step_per_gpu": 1,
+            "l2_flush_between_steps": True, "weights": "seeded random init (no checkpoint offline)",
+            "parallelism": f"pairs sharded over {world} rank(s), one all-gather of the transforms at the end"}
 
 
 def read_peaks():
@@ -76,14 +83,16 @@ def cpu_reference_step(sd, impl, cfg, limits, pair):
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores.  Exactly
+    `--steps` timed steps after `--warmup` untimed ones; a step = one full 30k+30k pair (about 2.5 s of CPU work on
+    a 16-core box, so the driver's 20 + 3 steps take about a minute)."""
     if rank != 0:
         return
     from gaussreg_b200.synthetic import make_pair_inputs
 
     sd, impl, cfg, limits = cpu_reference_setup()
     pair = make_pair_inputs(0, N_POINTS)
-    # bounded: each step is one full pair (about 10 s of CPU work); cap the count so the run ends in minutes
-    steps, warmup = max(1, min(args.steps, 6)), min(args.warmup, 1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     for _ in range(warmup):
         cpu_reference_step(sd, impl, cfg, limits, pair)
     times = [cpu_reference_step(sd, impl, cfg, limits, pair) for _ in range(steps)]
@@ -92,15 +101,60 @@ def run_reference(args, rank, world):
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "requested_steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_points_per_cloud": N_POINTS, "pairs_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": impl.kind,
-                         "sample": f"{steps} x one 30k+30k pair: neighbour pyramid through the reference's own C++ "
-                                   f"(oracle/_ref, 1 thread) + network through the torch-CPU restatement ({cores} threads)"},
+        "config": bench_config(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(impl),
+                         "sample": f"{steps} x one {N_POINTS}+{N_POINTS} pair: neighbour pyramid through the reference's own C++ "
+                                   f"(oracle/_ref, 1 thread, as the reference runs it) + network through the torch-CPU "
+                                   f"restatement oracle/network.py ({cores} threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def cpu_kind(impl):
+    """cpu_baseline.kind: the pyramid half is the reference's own C++ when oracle/_ref was built, the network half is
+    always the port (oracle/network.py, pinned to goldens of the unmodified Python reference)."""
+    return "reference-ext+port-network" if impl.kind == "reference" else "port"
+
+
+def gpu_torch_baseline(pair, dev, steps=3):
+    """The reference's real deployment (demo.py:139-149): neighbour pyramid on ONE host core through its C++
+    extension, `to_cuda`, then the network as stock PyTorch fp32 ops on the GPU.  The network half is the port
+    (oracle/network.py: the same ATen op sequence as the reference modules, allow_tf32 off) run under a CUDA default
+    device; a reported baseline, not the target."""
+    from oracle import network as onet
+    from oracle import neighbors as on
+    sd, impl, cfg, limits = cpu_reference_setup()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    pts = np.concatenate([pair["ref_points"], pair["src_points"]]).astype(np.float32)
+    lens = np.array([pair["ref_points"].shape[0], pair["src_points"].shape[0]], np.int64)
+    feats = np.concatenate([pair["ref_feats"], pair["src_feats"]]).astype(np.float32)
+    t_pyr, t_net, T = [], [], None
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        pyr = on.precompute_data_stack_mode(impl, pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                            cfg.backbone.init_radius, limits)
+        t1 = time.perf_counter()
+        data = {k: [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in v] for k, v in pyr.items()}
+        data["features"] = torch.from_numpy(feats).to(dev)
+        with torch.no_grad(), torch.device(dev):
+            out = onet.forward(sd, data)
+        T = out["estimated_transform"].cpu()
+        t2 = time.perf_counter()
+        if it > 0:  # first pass warms cuBLAS / cuSOLVER handles
+            t_pyr.append(t1 - t0)
+            t_net.append(t2 - t1)
+    del data, out
+    torch.cuda.empty_cache()
+    pyr_s, net_s = sum(t_pyr) / len(t_pyr), sum(t_net) / len(t_net)
+    return {"value": 1.0 / (pyr_s + net_s), "unit": UNIT, "pyramid_cpu_s": pyr_s, "network_gpu_s": net_s,
+            "kind": cpu_kind(impl) + " on cuda", "steps": steps, "checksum": float(T.double().abs().sum()),
+            "sample": f"{steps} x the same {N_POINTS}+{N_POINTS} pair: pyramid via the reference C++ (1 host thread, "
+                      f"as demo.py runs it) + H2D + stock-PyTorch fp32 network on this GPU + D2H of the transform"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,6 +335,118 @@ def pyramid_batched(pairs, dev, n_pairs=32, reps=3):
             "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / (best * 1e-3) / 1e9}
 
 
+def config3_batch(model, dev, n_pairs=128, distinct=32):
+    """BASELINE configs[2]: 128 synthetic ScanNet-GSReg-shape pairs through ONE process on one GPU, host buffers in,
+    one D2H of the (128,4,4) transforms out (parallel.register_pairs; per-pair semantics, no cross-pair state).
+    The 128 jobs cycle over `distinct` different seeded pairs (generating 128 distinct ones costs 26 s of host time)."""
+    from gaussreg_b200 import parallel
+    from gaussreg_b200.synthetic import make_pair_inputs
+    pool = [make_pair_inputs(1000 + i, N_POINTS) for i in range(distinct)]
+    jobs = [pool[i % distinct] for i in range(n_pairs)]
+    out = {"pairs": n_pairs, "distinct_pairs": distinct, "n_points_per_cloud": N_POINTS}
+    ref = None
+    for name, kw in (("sequential", dict(streams=1)), ("concurrent", dict(workers=parallel.default_workers()))):
+        parallel.register_pairs(model, jobs[:8], **kw)  # warm workspaces / streams
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T = parallel.register_pairs(model, jobs, **kw).cpu()
+        sec = time.perf_counter() - t0
+        out[name] = {"ms": 1e3 * sec, "pairs_per_s": n_pairs / sec, **{k: v for k, v in kw.items()}}
+        if ref is None:
+            ref = T
+        else:
+            out["bit_identical_to_sequential"] = bool(torch.equal(ref, T))
+    out["speedup_vs_sequential"] = out["concurrent"]["pairs_per_s"] / out["sequential"]["pairs_per_s"]
+    return out
+
+
+def config5_large_pair(model, dev, steps=2):
+    """BASELINE configs[4]: one 200k+200k pair whose coarsest stage holds ~4000 superpoints per cloud (dense
+    4096-class attention stress).  Reports the pair latency and the structure-embedding kernel's tensor roofline at
+    that size (FLOPs as executed: 2 N^2 (1+k) 256^2 per cloud, fp32-equivalent)."""
+    from gaussreg_b200 import _lib
+    from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+    from gaussreg_b200.data import registration_collate_fn_stack_mode
+    from gaussreg_b200.synthetic import make_pair_inputs
+    cfg = make_cfg()
+    d = make_pair_inputs(7, 200000, room=(12.0, 9.0, 7.5))
+    dd = {k: d[k] for k in ("ref_points", "src_points", "ref_feats", "src_feats")}
+    lib = _lib._lib
+    times, t1_ms, t1_flop, n_super = [], 0.0, 0.0, None
+    for it in range(steps + 1):
+        prof = it == steps and isinstance(lib, OpProfiler)
+        if prof:
+            lib.records, lib.enabled = [], True
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        data = registration_collate_fn_stack_mode([dict(dd)], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                                  cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+        out = model(data)
+        T = out["estimated_transform"].cpu()
+        e.record()
+        torch.cuda.synchronize()
+        if prof:
+            lib.enabled = False
+            for name, s1, e1, w, _ in lib.records:
+                if name == "gr_structure_embedding_fused":
+                    t1_ms += s1.elapsed_time(e1)
+                    t1_flop += w
+        if it > 0:
+            times.append(s.elapsed_time(e))
+        n_super = [int(x) for x in data["lengths"][-1].tolist()]
+        del data, out
+    torch.cuda.empty_cache()
+    peaks = read_peaks()
+    res = {"n_points_per_cloud": 200000, "superpoints": n_super, "ms_per_pair": sum(times) / len(times),
+           "pairs_per_s": 1e3 * len(times) / sum(times), "finite": bool(torch.isfinite(T).all())}
+    if t1_ms > 0:
+        tf = t1_flop / (t1_ms * 1e-3) / 1e12
+        res["structure_embedding"] = {"ms": t1_ms, "achieved": tf, "unit": "TFLOP/s fp32-equivalent", "frac_of_bf16_sustained": tf / peaks["tf_sustained"],
+                                      "tf32_mma_tflops": 3.0 * tf, "frac_of_tf32_peak": 3.0 * tf / (peaks["tf_sustained"] / 2.0)}
+    return res
+
+
+def config4_sharded(model, rank, world, dev, pairs_per_rank=128, distinct=8):
+    """BASELINE configs[3]: pairs sharded over the ranks (pair i -> rank i mod W), every rank runs its share, ONE
+    all-gather of the transforms at the very end.  128 pairs per rank (1024 over 8 GPUs), cycling over `distinct`
+    seeded pairs per rank.  Device-timed with a barrier on both sides, max over ranks."""
+    import torch.distributed as dist
+    from gaussreg_b200 import parallel
+    from gaussreg_b200.synthetic import make_pair_inputs
+    n = pairs_per_rank * world
+    pool = {}
+    jobs = []
+    for i in range(n):  # global pair list; this rank only materialises the pairs it owns
+        if i % world == rank:
+            key = (i // world) % distinct
+            if key not in pool:
+                pool[key] = make_pair_inputs(2000 + rank * distinct + key, N_POINTS)
+            jobs.append(pool[key])
+        else:
+            jobs.append(None)
+    parallel.register_pairs(model, [j for j in jobs if j is not None][:4], workers=parallel.default_workers(), distributed=False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    T = parallel.register_pairs(model, jobs, workers=parallel.default_workers())
+    e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"pairs": n, "pairs_per_rank": pairs_per_rank, "ms": ms, "pairs_per_s": n / (ms * 1e-3), "collectives": 1 if world > 1 else 0,
+            "finite": bool(torch.isfinite(T).all()), "shape": list(T.shape)}
+
+
+def warm_steps(args):
+    return max(args.warmup, 3)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -295,9 +461,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        os.environ.pop("NCCL_DEBUG", None)
-        os.environ["NCCL_DEBUG_FILE"] = "/tmp/nccl_debug_%h_%p.log"
+        # NCCL_DEBUG / NCCL_DEBUG_FILE are left exactly as the launcher set them (the driver reads the communicator
+        # banner to check the rank count); rank 0 prints its JSON line last, after every rank has torn NCCL down
         dist.init_process_group("nccl", device_id=dev)
     lib = OpProfiler(_lib.lib())
     _lib._lib = lib  # route every call through the (disabled) profiler
@@ -320,25 +485,30 @@ def run_ours(args, rank, world, local_rank):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values()) + 16
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # every rank keeps the transforms of its own pairs; ONE all-gather collects them after the last step
+    # (SURVEY.md section 8(e) / BASELINE configs[3]: the path has no per-pair exchange)
+    local_T = torch.zeros((max(args.steps, warm_steps(args)), 4, 4), dtype=torch.float32, device=dev)
+
     def step_resident(i):
         pts, feats, lens = resident[i % pool]
         data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
                                           cfg.backbone.init_radius, NEIGHBOR_LIMITS)
         data["features"] = feats
-        T = model(data)["estimated_transform"]
-        return parallel.gather_transforms(T.unsqueeze(0), world, rank, world)  # (world,4,4): one pair per rank per step
+        local_T[i] = model(data)["estimated_transform"]
 
     def step_e2e(i):
         h = host[i % pool]
         data = registration_collate_fn_stack_mode([dict(h)], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
                                                   cfg.backbone.init_radius, NEIGHBOR_LIMITS)
         T = model(data)["estimated_transform"]
-        return parallel.gather_transforms(T.unsqueeze(0), world, rank, world).cpu()
+        local_T[i] = T
+        return T.cpu()  # the step's result is read back on the host every step (64 bytes)
 
     def timed(step_fn, steps, warmup):
         for i in range(warmup):
             step_fn(i)
         if world > 1:
+            parallel.gather_transforms(local_T[:steps], steps * world, rank, world)  # warm the communicator
             dist.barrier()
         torch.cuda.synchronize()
         evs = []
@@ -350,9 +520,16 @@ def run_ours(args, rank, world, local_rank):
             step_fn(i)
             e.record()
             evs.append((s, e))
+        # the single collective of the run: (steps,4,4) per rank -> (steps*world,4,4) on every rank, timed
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        allT = parallel.gather_transforms(local_T[:steps], steps * world, rank, world)
+        e.record()
+        evs.append((s, e))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        assert allT.shape[0] == steps * world and bool(torch.isfinite(allT).all())
         launches = _lib.launch_count() - launches0
         total_ms = sum(s.elapsed_time(e) for s, e in evs)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -360,7 +537,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches
 
-    warm = max(args.warmup, 3)
+    warm = warm_steps(args)
     sampler = clocks_sampler_start(local_rank) if rank == 0 else None
     total_ms, launches = timed(step_resident, args.steps, warm)
     clocks = clocks_sampler_stop(sampler) if rank == 0 else None
@@ -388,6 +565,17 @@ def run_ours(args, rank, world, local_rank):
             g[0] += 1
             g[1] += ms
     prof_step_ms = s0.elapsed_time(e0)
+
+    # BASELINE configs[2..4] (throughput / stress configurations; not the headline `value`)
+    cfg3 = cfg4 = cfg5 = None
+    if not args.no_throughput:
+        if world > 1:
+            cfg4 = config4_sharded(model, rank, world, dev)  # every rank takes part (one all-gather at the end)
+        else:
+            cfg3 = config3_batch(model, dev)
+            cfg4 = {"note": "n_gpus = 1: identical to config3_128_pairs_1gpu (no collective)", "pairs": cfg3["pairs"],
+                    "pairs_per_s": cfg3["concurrent"]["pairs_per_s"], "collectives": 0}
+            cfg5 = config5_large_pair(model, dev)
 
     if rank == 0:
         peaks = read_peaks()
@@ -450,6 +638,12 @@ def run_ours(args, rank, world, local_rank):
                 4.0 * (sh[0] * sh[2] + sh[1] * sh[2] + sh[0] * sh[1]) * sh[3] * v[0] for sh, v in gemm_shapes.items()) / max(n_tc, 1)
         cpu = None
         throughput = None
+        gpu_torch = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                gpu_torch = gpu_torch_baseline(pairs[0], dev)
+            except Exception as ex:  # a baseline leg must never take the bench line down
+                gpu_torch = {"unavailable": repr(ex)[:200]}
         if world == 1 and not args.no_throughput:
             extra_pairs = [make_pair_inputs(100 + i, N_POINTS) for i in range(4)]
             throughput = throughput_mode(model, extra_pairs, dev)
@@ -458,31 +652,39 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             sd, impl, ccfg, limits = cpu_reference_setup()
             sec = cpu_reference_step(sd, impl, ccfg, limits, pairs[0])
-            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": impl.kind,
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind(impl),
                    "sample": "1 x the same 30k+30k pair: pyramid via the reference C++ (oracle/_ref, 1 thread) + "
                              "network via the torch-CPU restatement (all threads); %.1f s" % sec}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_points_per_cloud": N_POINTS, "pairs_per_step_per_gpu": 1,
-                       "l2_flush_between_steps": True, "weights": "seeded random init (no checkpoint offline)",
-                       "parallelism": f"pairs sharded over {world} rank(s), all-gather of transforms"},
+            "config": bench_config(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64 * world,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_torch_baseline": gpu_torch,
+            "config3_128_pairs_1gpu": cfg3,
+            "config4_sharded_pairs": cfg4,
+            "config5_200k_pair": cfg5,
             "throughput_mode": throughput,
             "per_op_ms": {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
             "profiled_step_ms": prof_step_ms, "top_op": top,
             "gemm_shapes_MNKbatchT_count_ms": [[list(k), v[0], round(v[1], 4)] for k, v in
                                                sorted(gemm_shapes.items(), key=lambda kv: -kv[1][1])[:24]],
         }
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(1.0)  # let the other ranks' NCCL teardown lines drain: the JSON line is the last thing printed
+    if rank == 0:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        print(json.dumps(line), flush=True)
 
 
 def main():

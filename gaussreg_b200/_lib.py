@@ -23,6 +23,42 @@ class LayerWeights(ctypes.Structure):
                                                "w1", "b1", "w2", "b2", "ln2_g", "ln2_b", "wqkv", "bqkv", "w1t", "w2t")] + [("is_self", ctypes.c_int)]
 
 
+class UnaryWeights(ctypes.Structure):
+    """gr_unary_weights (include/gaussreg_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("weight", "weight_packed", "bias", "gn_weight", "gn_bias")] + \
+               [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "leaky_relu")]
+
+
+class KPConvWeights(ctypes.Structure):
+    """gr_kpconv_weights."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("weights", "weights_kmajor", "weights_kmajor_packed", "bias", "kernel_points")] + \
+               [("sigma", ctypes.c_float), ("in_channels", ctypes.c_int), ("out_channels", ctypes.c_int)]
+
+
+class BlockWeights(ctypes.Structure):
+    """gr_block_weights."""
+    _fields_ = [("kind", ctypes.c_int), ("strided", ctypes.c_int), ("unary1", UnaryWeights), ("conv", KPConvWeights),
+                ("gn_conv_weight", ctypes.c_void_p), ("gn_conv_bias", ctypes.c_void_p), ("unary2", UnaryWeights),
+                ("shortcut", UnaryWeights)]
+
+
+FPN_STAGES, FPN_BLOCKS = 5, 14
+
+
+class FpnWeights(ctypes.Structure):
+    """gr_fpn_weights."""
+    _fields_ = [("blocks", BlockWeights * FPN_BLOCKS), ("decoder4", UnaryWeights), ("decoder3", UnaryWeights),
+                ("decoder2", UnaryWeights), ("group_norm", ctypes.c_int), ("eps", ctypes.c_float)]
+
+
+class Pyramid(ctypes.Structure):
+    """gr_pyramid."""
+    _fields_ = [("points", ctypes.c_void_p * FPN_STAGES), ("n_points", ctypes.c_int * FPN_STAGES)]
+    for _k in ("neighbors", "subsampling", "upsampling"):
+        _fields_ += [(_k, ctypes.c_void_p * FPN_STAGES), (_k + "_w", ctypes.c_int * FPN_STAGES), (_k + "_ld", ctypes.c_int64 * FPN_STAGES)]
+    del _k
+
+
 _SIGNATURES = {
     "gr_version": (ctypes.c_char_p, []),
     "gr_last_error": (ctypes.c_char_p, []),
@@ -40,6 +76,12 @@ _SIGNATURES = {
     "gr_last_gemm_path": (_i32, []),
     "gr_kpconv_aggregate_workspace_size": (_sz, [_i64]),
     "gr_kpconv_aggregate": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "gr_unary_block_workspace_size": (_sz, [_i64, _i32, _i32]),
+    "gr_unary_block": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "gr_kpconv_block_workspace_size": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "gr_kpconv_block": (_i32, [_vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "gr_kpconv_fpn_workspace_size": (_sz, [_vp, _vp]),
+    "gr_kpconv_fpn": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_group_norm_workspace_size": (_sz, [_i64, _i32]),
     "gr_group_norm": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gr_layer_norm_add": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),

@@ -274,7 +274,7 @@ extern "C" int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const floa
     if (rc != GR_OK) return rc;
     const size_t smem = (size_t)num_heads * N * sizeof(float);
     auto kern = rpe_scores_softmax_v2_kernel;
-    if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem));
     kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(U, qb, emb, N, scale, P);
     GR_CHECK_LAUNCH("rpe_scores_softmax_v2_kernel");
     return GR_OK;
@@ -283,7 +283,7 @@ extern "C" int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const floa
   const size_t smem = ((size_t)num_heads * C + C + (size_t)num_heads * N) * sizeof(float);
   if (smem > 200 * 1024) return GR_ERR_CAPACITY;
   auto kern = rpe_scores_softmax_kernel<4>;
-  if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem));
   kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, k, U, qb, emb, N, C, scale, P, ldq, ldk);
   GR_CHECK_LAUNCH("rpe_scores_softmax_kernel");
   return GR_OK;

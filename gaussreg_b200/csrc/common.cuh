@@ -35,6 +35,29 @@ void count_launch(int n = 1);
     }                                                         \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember it per (kernel, device) so that a
+// process driving several GPUs opts in on each of them (runtime.cu)
+cudaError_t ensure_smem_attr(const void* kernel, int bytes);
+
+// optional request to the tensor-core GEMM: also produce GroupNorm partial statistics of the output.  On return
+// nblk > 0 is the number of row blocks written to partial[nblk][groups]; nblk == 0: the product ran without them.
+struct GnStatsOut {
+  double2* partial;
+  size_t capacity_blocks;
+  int groups;
+  int nblk;
+};
+// gemm.cu: C = act(alpha A op(B) / row_div + bias + residual) with optional packed weights / GroupNorm statistics
+int gemm_ex(const float* A, long long lda, const float* B, long long ldb, int trans_b, float* C, long long ldc, int M, int N, int K,
+            float alpha, const float* bias, const float* row_div, const float* residual, long long ldr, int act, void* stream,
+            const float* B_packed, GnStatsOut* gn);
+// norm.cu: y = act(GroupNorm(x) [+ add]) from partial statistics (finalize + apply); ws holds `groups` float2
+int group_norm_from_partial(const float* x, long long n_rows, int C, int groups, const double2* partial, int nblk,
+                            const float* gamma, const float* beta, float eps, const float* add, int act, float* y,
+                            float2* stats, void* stream);
+// rows covered by one partial block of the split-K reduction (gemm_tc.cu)
+constexpr int kGnReduceRows = 32;
+
 // ---- workspace carving ----------------------------------------------------------------------
 struct Carver {
   char* base;

@@ -118,7 +118,7 @@ extern "C" int gr_embedding_indices(const float* points, int N, float sigma_d, f
   if ((size_t)N * sizeof(float) > 160 * 1024) return GR_ERR_CAPACITY;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)N * sizeof(float);
-  if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(pairdist_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(pairdist_knn_kernel), (int)smem));
   pairdist_knn_kernel<<<N, 128, smem, st>>>(points, N, sigma_d, angle_k, d_idx, knn);
   GR_CHECK_LAUNCH("pairdist_knn_kernel");
   const float factor_a = (float)(180.0 / ((double)sigma_a * 3.141592653589793));  // geotransformer.py:14

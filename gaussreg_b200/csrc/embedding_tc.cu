@@ -529,13 +529,14 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
   if (rows < 0 || angle_k < 1 || angle_k > 3 || hidden_dim != tc::kEmbC) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
-  static bool attr_set = false;
+  static bool knobs_read = false;
   static int cw = 1, width = 256, cluster = 1;
-  if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kEmbSmem));
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
-    GR_CHECK_CUDA(cudaFuncSetAttribute(tc::structure_embedding_tc256_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kE2Smem));
+  // the shared-memory opt-in is a per-device attribute (ensure_smem_attr remembers it per kernel and device)
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_tc_kernel<true>), tc::kEmbSmem));
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_tc_kernel<false>), tc::kEmbSmem));
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_tc256_kernel<1>), tc::kE2Smem));
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_tc256_kernel<2>), tc::kE2Smem));
+  if (!knobs_read) {
     // 2: CTA pairs share the weight stream by multicast.  Correct, but measured SLOWER on B200 (1.24 vs 1.18 ms per
     // pair): the kernel is paced by its producers' instruction issue, not by L2, and the pair adds hand-over stalls.
     const char* e = getenv("GAUSSREG_T1_CLUSTER");
@@ -544,7 +545,7 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
     cw = e ? atoi(e) : 1;
     e = getenv("GAUSSREG_T1_WIDTH");               // 256: full-width CTA with ping-pong TMEM slots, 128: two column halves
     width = e ? atoi(e) : 256;
-    attr_set = true;
+    knobs_read = true;
   }
   if (width == 256) {
     const unsigned tiles = (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM);

@@ -22,6 +22,7 @@ namespace gr {
 
 struct GemmParams;  // gemm.cu
 
+
 namespace tc {
 
 constexpr int BM = 128;
@@ -41,6 +42,10 @@ struct Params {
   // 128 rows x 32 k): the B tiles then arrive by bulk async copies instead of being converted by the producers
   const float* B_packed;
   int packed_kblocks;  // ceil(K / 32) of the packed matrix
+  // optional GroupNorm statistics of the OUTPUT (K2 fused into its producer): per 128-row tile and group the
+  // (sum, sum of squares) of the final values, folded in a fixed order -> gn_partial[blockIdx.y * gn_groups + g]
+  double2* gn_partial;
+  int gn_groups;
 };
 
 template <int BN>
@@ -83,7 +88,9 @@ __device__ __forceinline__ void tile_store(const TileRegs<ROWS>& t, unsigned cha
     const float4 v = t.v[i];
     float4 hi, lo;
     hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+    // lo = x - hi is exact in fp32; the tensor core drops its 13 low mantissa bits itself (error 2^-22 |x|), so the
+    // second cvt.rna (four instructions on sm_100a) is not spent on it
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
     *reinterpret_cast<float4*>(s_hi + off) = hi;
     *reinterpret_cast<float4*>(s_lo + off) = lo;
   }
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
         if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
         else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
       }
+      float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int rr = 0; rr < 32; rr += 4) {
         const int row = rr + rsub;
@@ -232,6 +240,45 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
         float* dst = Cp + (long long)m * p.ldc + n;
         if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
         else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
+        if (p.gn_partial) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < p.N) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
+        }
+      }
+      if (p.gn_partial) {  // column sums over this warp's 32 rows (fp32, at most 8 terms per lane, then 4 lanes)
+        float2* gn_col = reinterpret_cast<float2*>(smem + 40 * 1024);  // [4 row quarters][BN]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+        }
+        if (rsub == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) gn_col[q * BN + c0 + c4 + e] = make_float2(cs[e], cq[e]);
+        }
+      }
+    }
+    if (p.gn_partial) {
+      // fold the four row quarters per column (double, fixed order), then the columns of each group
+      const float2* gn_col = reinterpret_cast<const float2*>(smem + 40 * 1024);
+      double2* gn_cold = reinterpret_cast<double2*>(smem + 48 * 1024);  // [BN]
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < BN) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) { const float2 v = gn_col[qq * BN + tid]; a += (double)v.x; b += (double)v.y; }
+        gn_cold[tid] = make_double2(a, b);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int cg = p.N / p.gn_groups;  // host guarantees cg | BN and N % BN-aligned groups
+      if (tid < BN / cg) {
+        const int gidx = n0 / cg + tid;
+        if (gidx < p.gn_groups) {
+          double a = 0.0, b = 0.0;
+          for (int c = tid * cg; c < (tid + 1) * cg; ++c) { a += gn_cold[c].x; b += gn_cold[c].y; }
+          p.gn_partial[(long long)blockIdx.y * p.gn_groups + gidx] = make_double2(a, b);
+        }
       }
     }
     tc_fence_before();
@@ -300,14 +347,78 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// Split-K reduction that also carries the GroupNorm statistics of its output: a block owns kRedRows rows and all N
+// columns (thread = 4 consecutive columns, remaining thread bits walk rows); per-thread fp32 sums over at most 32
+// rows, folded in double in a fixed order -> gn_partial[blockIdx.x * G + g].
+constexpr int kRedRows = kGnReduceRows;
+__global__ void __launch_bounds__(256) splitk_reduce_gn_kernel(const float* __restrict__ partial, int splits, Params p) {
+  extern __shared__ double2 red_sh[];  // chs[N], then stage[R * N] when several row lanes share a column
+  double2* chs = red_sh;
+  double2* stage = red_sh + p.N;
+  const int r0 = blockIdx.x * kRedRows, r1 = min(p.M, r0 + kRedRows);
+  const int tid = threadIdx.x;
+  const int c4n = p.N >> 2;
+  const int lanes = c4n < 256 ? c4n : 256;
+  const int R = 256 / lanes;
+  const int rs = tid / lanes;
+  const long long plane = (long long)p.M * p.N;
+  if (rs < R) {
+    for (int cc = tid % lanes; cc < c4n; cc += lanes) {
+      const int n = cc * 4;
+      float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bv = make_float4(p.bias[n], p.bias[n + 1], p.bias[n + 2], p.bias[n + 3]);
+      for (int r = r0 + rs; r < r1; r += R) {
+        const long long i = (long long)r * c4n + cc;
+        float4 acc = reinterpret_cast<const float4*>(partial)[i];
+        for (int z = 1; z < splits; ++z) {
+          const float4 v = reinterpret_cast<const float4*>(partial + z * plane)[i];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+        const float rd = p.row_div ? p.row_div[r] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = v[j] * p.alpha;
+          if (p.row_div) x = x / rd;
+          if (p.bias) x += b4[j];
+          if (p.residual) x += p.residual[(long long)r * p.ldr + n + j];
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          else if (p.act == 2) x = x > 0.f ? x : 0.1f * x;
+          v[j] = x;
+          fs[j] += x; fq[j] = fmaf(x, x, fq[j]);
+        }
+        float* dst = p.C + (long long)r * p.ldc + n;
+        if ((p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
+      }
+      double2* dst = (R == 1) ? chs + n : stage + (size_t)rs * p.N + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = make_double2((double)fs[k], (double)fq[k]);
+    }
+  }
+  __syncthreads();
+  if (R > 1) {
+    for (int c = tid; c < p.N; c += 256) {
+      double2 a = stage[c];
+      for (int k = 1; k < R; ++k) { const double2 b = stage[(size_t)k * p.N + c]; a.x += b.x; a.y += b.y; }
+      chs[c] = a;
+    }
+    __syncthreads();
+  }
+  const int cg = p.N / p.gn_groups;
+  for (int g = tid; g < p.gn_groups; g += 256) {
+    double a = 0.0, b = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += chs[c].x; b += chs[c].y; }
+    p.gn_partial[(long long)blockIdx.x * p.gn_groups + g] = make_double2(a, b);
+  }
+}
+
 template <int BN>
 static int launch(const Params& p, int batch, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
-  }
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_kernel<BN>), C::kSmemBytes));
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
   gemm_tf32x3_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(p);
   GR_CHECK_LAUNCH("gemm_tf32x3_kernel");
@@ -354,7 +465,9 @@ static bool use_bn256() {
 // Returns GR_OK when the tensor-core path ran, 1 when the problem does not qualify (caller falls back to SIMT).
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
-                const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed) {
+                const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed,
+                GnStatsOut* gn) {
+  if (gn) gn->nblk = 0;
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
@@ -403,6 +516,10 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act; p.k_split = 0;
   p.B_packed = (batch == 1) ? B_packed : nullptr;
   p.packed_kblocks = (K + 31) / 32;
+  p.gn_partial = nullptr; p.gn_groups = 0;
+  // GroupNorm statistics ride in the epilogue when every group lies inside one column tile
+  const bool gn_ok = gn && gn->partial && batch == 1 && gn->groups > 0 && N % gn->groups == 0 && N % 4 == 0 &&
+                     bn % (N / gn->groups) == 0 && (N / gn->groups) <= bn;
   if (splits > 1) {
     float* partial = splitk_scratch(st, (size_t)splits * M * N * sizeof(float));
     if (partial == nullptr) return GR_ERR_CUDA;
@@ -411,12 +528,28 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     q.alpha = 1.f; q.act = 0; q.k_split = slice;
     int rc = bn == 256 ? tc::launch<256>(q, splits, st) : (bn == 128 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
     if (rc == GR_OK) {
-      const long long total = (long long)M * (N / 4);
-      tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);
+      const int nblk = (M + tc::kRedRows - 1) / tc::kRedRows;
+      if (gn_ok && (size_t)nblk <= gn->capacity_blocks) {
+        p.gn_partial = gn->partial; p.gn_groups = gn->groups;
+        const int c4n = N / 4, lanes = c4n < 256 ? c4n : 256, R = 256 / lanes;
+        const size_t smem = ((size_t)N + (R > 1 ? (size_t)R * N : 0)) * sizeof(double2);
+        if (smem > 48 * 1024) {
+          if (ensure_smem_attr(reinterpret_cast<const void*>(tc::splitk_reduce_gn_kernel), (int)smem) != cudaSuccess) return GR_ERR_CUDA;
+        }
+        tc::splitk_reduce_gn_kernel<<<nblk, 256, smem, st>>>(partial, splits, p);
+        gn->nblk = nblk;
+      } else {
+        const long long total = (long long)M * (N / 4);
+        tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);
+      }
       count_launch();
       if (cudaGetLastError() != cudaSuccess) rc = GR_ERR_CUDA;
     }
     return rc;
+  }
+  if (gn_ok && (size_t)((M + 127) / 128) <= gn->capacity_blocks) {
+    p.gn_partial = gn->partial; p.gn_groups = gn->groups;
+    gn->nblk = (M + 127) / 128;
   }
   if (N > 128 && use_bn256()) return tc::launch<256>(p, batch, st);
   if (N > 64) return tc::launch<128>(p, batch, st);

@@ -388,7 +388,7 @@ extern "C" int gr_local_global_registration(const float* matching_scores, int P,
   if (!ws || !c.ok) return GR_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)K * (K + 1) * sizeof(float);
-  if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(lgr_correspondence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(lgr_correspondence_kernel), (int)smem));
   lgr_correspondence_kernel<<<P, kLgrThreads, smem, st>>>(matching_scores, K, ld, ref_knn_masks, src_knn_masks, topk,
                                                            confidence_threshold, mutual, counts, cand_rc, cand_score);
   GR_CHECK_LAUNCH("lgr_correspondence_kernel");

@@ -400,15 +400,15 @@ extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const 
   static int exp2_knob = -1;
   if (exp2_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN_EXP2"); exp2_knob = e ? atoi(e) : 1; }  // measured: 0.63 -> 0.52 ms
   if (K == 128 && fast_knob && exp2_knob) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<true, true>), (int)smem));
     sinkhorn_kernel<true, true><<<P, kSink128Threads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha,
                                                                                                 K, num_iterations, inf, out);
   } else if (K == 128 && fast_knob) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<true>), (int)smem));
     sinkhorn_kernel<true><<<P, kSink128Threads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
                                                                                           num_iterations, inf, out);
   } else {
-    if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<false>), (int)smem));
     sinkhorn_kernel<false><<<P, kSinkThreads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
                                                                                          num_iterations, inf, out);
   }

@@ -869,12 +869,8 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
   {
     // clouds that may exceed the shared-memory phases get a cluster of kReplayCluster CTAs each
     const size_t smem = 8 * (size_t)kReplaySmemElems * sizeof(unsigned int);
-    static bool attr_set = false;
-    if (!attr_set) {
-      GR_CHECK_CUDA(cudaFuncSetAttribute(hash_order_replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      GR_CHECK_CUDA(cudaFuncSetAttribute(hash_order_replay_kernel<kReplayCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(hash_order_replay_kernel<1>), (int)smem));
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(hash_order_replay_kernel<kReplayCluster>), (int)smem));
     static int cl_knob = -1;
     if (cl_knob < 0) { const char* e = getenv("GAUSSREG_REPLAY_CLUSTER"); cl_knob = e ? atoi(e) : kReplayCluster; }
     if (n > kReplaySmemElems && cl_knob > 1) {

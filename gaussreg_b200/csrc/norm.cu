@@ -312,18 +312,14 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
   if (variant < 0) { const char* e = getenv("GAUSSREG_GN"); variant = e ? atoi(e) : 1; }
   if (variant == 0) {
     const size_t smem = (size_t)(C > 256 ? C : 256) * sizeof(double2);
-    if (smem > 48 * 1024) GR_CHECK_CUDA(cudaFuncSetAttribute(groupnorm_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(groupnorm_partial_kernel), (int)smem));
     groupnorm_partial_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
     GR_CHECK_LAUNCH("groupnorm_partial_kernel");
   } else {
     const int lanes = (C / 4) < 256 ? (C / 4) : 256;
     const int R = 256 / lanes;
     const size_t smem = ((size_t)C + (R > 1 ? (size_t)R * C : 0)) * sizeof(double2);
-    static bool attr_set = false;
-    if (!attr_set) {
-      GR_CHECK_CUDA(cudaFuncSetAttribute(groupnorm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
-    }
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(groupnorm_stats_kernel), 96 * 1024));
     groupnorm_stats_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
     GR_CHECK_LAUNCH("groupnorm_stats_kernel");
   }
@@ -335,6 +331,22 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
   GR_CHECK_LAUNCH("groupnorm_apply_kernel");
   return GR_OK;
 }
+
+namespace gr {
+int group_norm_from_partial(const float* x, long long n_rows, int C, int groups, const double2* partial, int nblk,
+                            const float* gamma, const float* beta, float eps, const float* add, int act, float* y,
+                            float2* stats, void* stream) {
+  if (n_rows <= 0) return GR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  groupnorm_finalize_kernel<<<groups, 256, 0, st>>>(partial, nblk, groups, n_rows * (long long)(C / groups), eps, stats);
+  GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
+  const long long total4 = n_rows * (long long)(C / 4);
+  const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
+  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y);
+  GR_CHECK_LAUNCH("groupnorm_apply_kernel");
+  return GR_OK;
+}
+}  // namespace gr
 
 /* T2/T3: y = LayerNorm(a + b) (b may be NULL). */
 extern "C" int gr_layer_norm_add(const float* a, const float* b, int64_t rows, int C, const float* gamma, const float* beta,

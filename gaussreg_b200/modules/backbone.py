@@ -1,4 +1,6 @@
 """KPConvFPN (reference: experiments/geotransformer.gaussian_splatting.indoor/backbone.py:95-212)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -30,6 +32,14 @@ class KPConvFPN(nn.Module):
 
     @torch.no_grad()
     def forward(self, feats, data_dict):
+        """One C-ABI call (csrc/backbone.cu issues every kernel of the 14 blocks and 3 decoders); the per-module
+        Python path below is kept for teacher-forced tests (GAUSSREG_FPN_NATIVE=0)."""
+        if os.environ.get("GAUSSREG_FPN_NATIVE", "1") != "0":
+            return ops.kpconv_fpn(self, feats, data_dict)
+        return self.forward_modules(feats, data_dict)
+
+    @torch.no_grad()
+    def forward_modules(self, feats, data_dict):
         P, NB = data_dict["points"], data_dict["neighbors"]
         SUB, UP = data_dict["subsampling"], data_dict["upsampling"]
         f1 = self.encoder1_1(feats, P[0], P[0], NB[0])

@@ -104,9 +104,8 @@ class UnaryBlock(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, add=None, act_after_add=None):
-        x = ops.linear(x, self.mlp.weight, self.mlp.bias)
-        act = "leaky_relu" if self.leaky_relu is not None else act_after_add
-        return self.norm(x, add=add, act=act)
+        # Linear -> GroupNorm (+ add) -> activation in one C-ABI call; the norm's statistics ride in the product's epilogue
+        return ops.unary_block(self, x, add=add, act_after_add=act_after_add)
 
 
 class LastUnaryBlock(nn.Module):
@@ -137,8 +136,7 @@ class ConvBlock(nn.Module):
 
     @torch.no_grad()
     def forward(self, s_feats, q_points, s_points, neighbor_indices):
-        x = self.KPConv(s_feats, q_points, s_points, neighbor_indices)
-        return self.norm(x, act="leaky_relu")
+        return ops.kpconv_block(self.KPConv, self.norm, s_feats, q_points, s_points, neighbor_indices)
 
 
 class ResidualBlock(nn.Module):
@@ -164,8 +162,7 @@ class ResidualBlock(nn.Module):
     @torch.no_grad()
     def forward(self, s_feats, q_points, s_points, neighbor_indices):
         x = self.unary1(s_feats)
-        x = self.KPConv(x, q_points, s_points, neighbor_indices)
-        x = self.norm_conv(x, act="leaky_relu")
+        x = ops.kpconv_block(self.KPConv, self.norm_conv, x, q_points, s_points, neighbor_indices)
         shortcut = maxpool(s_feats, neighbor_indices) if self.strided else s_feats
         if not isinstance(self.unary_shortcut, nn.Identity):
             shortcut = self.unary_shortcut(shortcut)

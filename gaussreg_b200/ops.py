@@ -121,6 +121,195 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_
     return gemm(A, weights.view(K * C, Co), False, bias=bias, row_div=row_div)
 
 
+# ------------------------------------------------------------------------------------------------
+# native KPConv blocks / FPN: parameter structs for the C ABI (include/gaussreg_b200.h, csrc/backbone.cu)
+# ------------------------------------------------------------------------------------------------
+def _fill_unary(dst, mlp, norm, leaky, keep):
+    """gr_unary_weights from an nn.Linear (+ optional GroupNorm wrapper)."""
+    w = mlp.weight
+    dst.weight = w.data_ptr()
+    if w.is_contiguous() and w.shape[1] % 4 == 0:
+        pk = packed_weight_tf32x3(w)
+        keep.append(pk)
+        dst.weight_packed = pk.data_ptr()
+    else:
+        dst.weight_packed = None
+    dst.bias = mlp.bias.data_ptr() if mlp.bias is not None else None
+    if norm is not None:
+        dst.gn_weight, dst.gn_bias = norm.norm.weight.data_ptr(), norm.norm.bias.data_ptr()
+    else:
+        dst.gn_weight, dst.gn_bias = None, None
+    dst.in_channels, dst.out_channels, dst.leaky_relu = w.shape[1], w.shape[0], int(bool(leaky))
+
+
+def _fill_kpconv(dst, conv, keep):
+    K, C, Co = conv.weights.shape
+    dst.weights = conv.weights.data_ptr()
+    if (K * C) % 4 == 0:
+        wk = _kmajor_weights(conv.weights)
+        pk = packed_weight_tf32x3(wk)
+        keep += [wk, pk]
+        dst.weights_kmajor, dst.weights_kmajor_packed = wk.data_ptr(), pk.data_ptr()
+    else:
+        dst.weights_kmajor, dst.weights_kmajor_packed = None, None
+    dst.bias = conv.bias.data_ptr() if conv.bias is not None else None
+    dst.kernel_points = conv.kernel_points.data_ptr()
+    dst.sigma, dst.in_channels, dst.out_channels = float(conv.sigma), C, Co
+
+
+def _module_key(module):
+    return tuple((t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _cached_struct(module, build):
+    """C parameter struct of `module`, rebuilt when any parameter / buffer changes version or storage."""
+    key = _module_key(module)
+    cached = module.__dict__.get("_gr_native")
+    if cached is None or cached[0] != key:
+        keep = []
+        cached = (key, build(keep), keep)
+        module.__dict__["_gr_native"] = cached
+    return cached[1]
+
+
+def invalidate_weight_caches(module):
+    """Drop every derived weight image (packed / transposed / fused copies and native parameter structs) under
+    `module`.  Needed only after IN-PLACE edits through `param.data`, which do not bump the version counter the
+    caches are keyed on; load_state_dict / optimizer steps are detected automatically."""
+    for m in module.modules():
+        m.__dict__.pop("_gr_native", None)
+    for p in list(module.parameters()) + list(module.buffers()):
+        for attr in ("_gr_packed", "_gr_kmajor", "_gr_qkv", "_gr_t"):
+            if hasattr(p, attr):
+                try:
+                    delattr(p, attr)
+                except AttributeError:
+                    pass
+
+
+def unary_block(block, x, add=None, act_after_add=None):
+    """UnaryBlock / LastUnaryBlock forward (modules.py:53-101) in one C-ABI call: the GroupNorm statistics come out
+    of the Linear's epilogue."""
+    import ctypes
+    x = _req(x)
+    norm = getattr(block, "norm", None)
+    leaky = getattr(block, "leaky_relu", None) is not None
+
+    def build(keep):
+        w = _lib.UnaryWeights()
+        _fill_unary(w, block.mlp, norm, leaky, keep)
+        return w
+
+    w = _cached_struct(block, build)
+    rows = x.shape[0]
+    out = torch.empty((rows, w.out_channels), dtype=_F32, device=x.device)
+    groups = norm.num_groups if norm is not None else 1
+    eps = norm.norm.eps if norm is not None else 1e-5
+    if add is not None:
+        add = _req(add)
+    L = _lib.lib()
+    ws = _workspace(L.gr_unary_block_workspace_size(rows, w.out_channels, groups), x.device)
+    st = L.gr_unary_block(ctypes.byref(w), x.data_ptr(), rows, groups, float(eps), _ptr(add), ACT[act_after_add], out.data_ptr(),
+                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "unary_block")
+    return out
+
+
+def kpconv_block(conv, norm, s_feats, q_points, s_points, neighbor_indices):
+    """KPConv [+ GroupNorm + LeakyReLU] (kpconv.py:79-122, modules.py:104-146) in one C-ABI call."""
+    import ctypes
+    s_feats, q_points, s_points = _req(s_feats), _req(q_points), _req(s_points)
+    assert neighbor_indices.dtype == torch.int64 and neighbor_indices.stride(1) == 1
+
+    def build(keep):
+        w = _lib.KPConvWeights()
+        _fill_kpconv(w, conv, keep)
+        return w
+
+    w = _cached_struct(conv, build)
+    M, H = neighbor_indices.shape
+    Ns = s_feats.shape[0]
+    out = torch.empty((M, w.out_channels), dtype=_F32, device=s_feats.device)
+    groups = norm.num_groups if norm is not None else 1
+    L = _lib.lib()
+    ws = _workspace(L.gr_kpconv_block_workspace_size(M, Ns, w.in_channels, w.out_channels, groups), s_feats.device)
+    st = L.gr_kpconv_block(ctypes.byref(w), norm.norm.weight.data_ptr() if norm is not None else None,
+                           norm.norm.bias.data_ptr() if norm is not None else None, groups,
+                           float(norm.norm.eps) if norm is not None else 1e-5, s_feats.data_ptr(), q_points.data_ptr(),
+                           s_points.data_ptr(), neighbor_indices.data_ptr(), H, neighbor_indices.stride(0), M, Ns, out.data_ptr(),
+                           ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "kpconv_block")
+    return out
+
+
+_FPN_BLOCK_NAMES = ("encoder1_1", "encoder1_2", "encoder2_1", "encoder2_2", "encoder2_3", "encoder3_1", "encoder3_2", "encoder3_3",
+                    "encoder4_1", "encoder4_2", "encoder4_3", "encoder5_1", "encoder5_2", "encoder5_3")
+
+
+def kpconv_fpn(backbone, feats, data_dict):
+    """KPConvFPN.forward (backbone.py:164-212) as ONE C-ABI call -> [l2, l3, l4, f5]."""
+    import ctypes
+    import torch.nn as nn
+    feats = _req(feats)
+
+    def build(keep):
+        W = _lib.FpnWeights()
+        groups, eps = None, 1e-5
+        for i, name in enumerate(_FPN_BLOCK_NAMES):
+            m, b = getattr(backbone, name), W.blocks[i]
+            conv = m.KPConv
+            _fill_kpconv(b.conv, conv, keep)
+            if hasattr(m, "unary2"):  # ResidualBlock
+                b.kind, b.strided = 1, int(m.strided)
+                if isinstance(m.unary1, nn.Identity):
+                    b.unary1.in_channels = 0
+                else:
+                    _fill_unary(b.unary1, m.unary1.mlp, m.unary1.norm, True, keep)
+                b.gn_conv_weight, b.gn_conv_bias = m.norm_conv.norm.weight.data_ptr(), m.norm_conv.norm.bias.data_ptr()
+                _fill_unary(b.unary2, m.unary2.mlp, m.unary2.norm, False, keep)
+                if isinstance(m.unary_shortcut, nn.Identity):
+                    b.shortcut.in_channels = 0
+                else:
+                    _fill_unary(b.shortcut, m.unary_shortcut.mlp, m.unary_shortcut.norm, False, keep)
+                groups, eps = m.norm_conv.num_groups, m.norm_conv.norm.eps
+            else:                     # ConvBlock
+                b.kind, b.strided = 0, 0
+                b.gn_conv_weight, b.gn_conv_bias = m.norm.norm.weight.data_ptr(), m.norm.norm.bias.data_ptr()
+        _fill_unary(W.decoder4, backbone.decoder4.mlp, backbone.decoder4.norm, True, keep)
+        _fill_unary(W.decoder3, backbone.decoder3.mlp, backbone.decoder3.norm, True, keep)
+        _fill_unary(W.decoder2, backbone.decoder2.mlp, None, False, keep)
+        W.group_norm, W.eps = int(groups), float(eps)
+        return W
+
+    W = _cached_struct(backbone, build)
+    P = _lib.Pyramid()
+    pts, nb, sub, up = data_dict["points"], data_dict["neighbors"], data_dict["subsampling"], data_dict["upsampling"]
+    keep = []
+    for s in range(_lib.FPN_STAGES):
+        pt = _req(pts[s])
+        keep.append(pt)
+        P.points[s], P.n_points[s] = pt.data_ptr(), pt.shape[0]
+        for key, tabs in (("neighbors", nb), ("subsampling", sub), ("upsampling", up)):
+            if s < len(tabs):
+                t = tabs[s]
+                assert t.dtype == torch.int64 and t.stride(1) == 1
+                getattr(P, key)[s] = t.data_ptr()
+                getattr(P, key + "_w")[s] = t.shape[1]
+                getattr(P, key + "_ld")[s] = t.stride(0)
+    dev = feats.device
+    n = [p.shape[0] for p in pts]
+    outs = [torch.empty((n[1], W.decoder2.out_channels), dtype=_F32, device=dev),
+            torch.empty((n[2], W.decoder3.out_channels), dtype=_F32, device=dev),
+            torch.empty((n[3], W.decoder4.out_channels), dtype=_F32, device=dev),
+            torch.empty((n[4], W.blocks[13].unary2.out_channels), dtype=_F32, device=dev)]
+    L = _lib.lib()
+    ws = _workspace(L.gr_kpconv_fpn_workspace_size(ctypes.byref(W), ctypes.byref(P)), dev)
+    st = L.gr_kpconv_fpn(ctypes.byref(W), ctypes.byref(P), feats.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                         outs[2].data_ptr(), outs[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "kpconv_fpn")
+    return outs
+
+
 def group_norm(x, groups, gamma, beta, eps=1e-5, add=None, act=None, out=None):
     x = _req(x)
     n, C = x.shape

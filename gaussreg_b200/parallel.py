@@ -34,7 +34,13 @@ def gather_transforms(local_transforms, n_pairs, rank=None, world=None):
     return out.view(world, per, 4, 4).transpose(0, 1).reshape(world * per, 4, 4)[:n_pairs].contiguous()
 
 
-def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1, pyramid_batch=1):
+def default_workers():
+    """Worker threads `register_pairs(workers=...)` uses when asked for "as many as pay off" (env GAUSSREG_WORKERS)."""
+    import os
+    return max(1, int(os.environ.get("GAUSSREG_WORKERS", "4")))
+
+
+def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1, pyramid_batch=1, workers=1, distributed=True):
     """Coarse-register a list of scene pairs (BASELINE configs 3 / 4): every rank runs the pairs it owns through
     the single-pair forward (the reference model is batch-1 only, model.py:77-89; pairs never interact), one
     all-gather returns all transforms in pair order to every rank.
@@ -49,13 +55,22 @@ def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1, pyra
     `streams` > 1 software-pipelines consecutive pairs over that many CUDA streams: the neighbour pyramid of pair
     i+1 (a few CTAs per kernel, two host syncs for its data-dependent sizes) then overlaps the network of pair i.
     Every per-call scratch buffer of the library is keyed by stream, so the results are bit-identical to the
-    sequential order; the first pair always runs alone (it packs the static weights other streams then read)."""
+    sequential order; the first pair always runs alone (it packs the static weights other streams then read).
+
+    `workers` > 1 is the throughput mode of BASELINE configs 3 / 4: that many host threads, each with its own CUDA
+    stream, take pairs round-robin.  A single pair's forward is a chain of several hundred mostly small kernels
+    that leave most of the 148 SMs idle; pairs on different streams fill them.  The C-ABI calls release the GIL, so
+    the threads issue concurrently; the per-stream workspaces keep the pairs independent and every transform is
+    bit-identical to the sequential result.
+
+    `pairs` may hold None at the positions other ranks own.  `distributed=False` skips the all-gather (warm-up)."""
     from .config import make_cfg, NEIGHBOR_LIMITS
     from .data import registration_collate_fn_stack_mode
     cfg = cfg or make_cfg()
     limits = neighbor_limits or NEIGHBOR_LIMITS
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    use_dist = distributed and dist.is_initialized()
+    world = dist.get_world_size() if use_dist else 1
+    rank = dist.get_rank() if use_dist else 0
     dev = torch.device("cuda", torch.cuda.current_device())
     mine = shard_pairs(len(pairs), rank, world)
     local = torch.empty((len(mine), 4, 4), dtype=torch.float32, device=dev)
@@ -77,6 +92,31 @@ def register_pairs(model, pairs, cfg=None, neighbor_limits=None, streams=1, pyra
                                              dim=0).to(dev, torch.float32, non_blocking=True)
                 data["batch_size"] = 1
                 local[g0 + j] = model(data)["estimated_transform"]
+    elif workers > 1 and len(mine) > 1:
+        import threading
+        cur = torch.cuda.current_stream()
+        one(0, mine[0])  # alone: packs the static weights every stream then reads
+        cur.synchronize()
+        pool = _stream_pool(dev, workers)
+        errors = []
+
+        def work(w):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(pool[w]):
+                    for j in range(1 + w, len(mine), workers):
+                        one(j, mine[j])
+                    pool[w].synchronize()
+            except BaseException as ex:  # surfaced on the caller's thread below
+                errors.append(ex)
+
+        threads = [threading.Thread(target=work, args=(w,), daemon=True) for w in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
     elif streams <= 1 or len(mine) <= 1:
         for j, i in enumerate(mine):
             one(j, i)

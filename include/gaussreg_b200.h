@@ -135,6 +135,82 @@ int gr_upsample_concat(const float* coarse, int Nc, int C1, const int64_t* idx, 
                        int C2, int M, float* out, void* stream);
 int gr_gather_rows(const float* x, int n, int C, const int64_t* idx, int64_t rows, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K2/K4  KPConv blocks and the whole KPConvFPN as single entry points
+ * (geotransformer/modules/kpconv/modules.py:53-225, experiments/.../backbone.py:164-212).
+ *
+ * The host structs below hold DEVICE pointers to the module parameters (state_dict tensors) plus derived
+ * operand images the caller prepares once per parameter version:
+ *   weight_packed          gr_pack_weight_tf32x3 image of `weight`            (may be NULL: converted on the fly)
+ *   weights_kmajor         (out, 15*in) K-major copy of KPConv.weights        (may be NULL: NN product on `weights`)
+ *   weights_kmajor_packed  gr_pack_weight_tf32x3 image of weights_kmajor      (may be NULL)
+ * GroupNorm statistics of every Linear / KPConv output are produced by the product's own epilogue (per-tile
+ * partial sums folded in a fixed order), so a block costs no separate statistics pass over its activations.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* weight;        /* nn.Linear weight (out, in) */
+  const float* weight_packed;
+  const float* bias;          /* (out) or NULL */
+  const float* gn_weight;     /* GroupNorm affine (out); NULL = no norm (LastUnaryBlock) */
+  const float* gn_bias;
+  int in_channels, out_channels; /* in_channels == 0: the block is nn.Identity */
+  int leaky_relu;             /* LeakyReLU(0.1) after the norm (UnaryBlock has_relu) */
+} gr_unary_weights;
+
+typedef struct {
+  const float* weights;       /* (15, in, out) */
+  const float* weights_kmajor;
+  const float* weights_kmajor_packed;
+  const float* bias;          /* (out) or NULL */
+  const float* kernel_points; /* (15, 3) */
+  float sigma;
+  int in_channels, out_channels;
+} gr_kpconv_weights;
+
+typedef struct {
+  int kind;                   /* 0 = ConvBlock (KPConv + GN + LeakyReLU), 1 = ResidualBlock */
+  int strided;                /* ResidualBlock: shortcut = maxpool over the neighbour table */
+  gr_unary_weights unary1;    /* ResidualBlock only */
+  gr_kpconv_weights conv;
+  const float* gn_conv_weight; /* GroupNorm after the KPConv */
+  const float* gn_conv_bias;
+  gr_unary_weights unary2;
+  gr_unary_weights shortcut;
+} gr_block_weights;
+
+#define GR_FPN_STAGES 5
+#define GR_FPN_BLOCKS 14
+typedef struct {
+  gr_block_weights blocks[GR_FPN_BLOCKS]; /* encoder1_1 ... encoder5_3 in forward order (backbone.py:164-193) */
+  gr_unary_weights decoder4, decoder3, decoder2;
+  int group_norm;                          /* number of groups */
+  float eps;
+} gr_fpn_weights;
+
+typedef struct {
+  const float* points[GR_FPN_STAGES];
+  int n_points[GR_FPN_STAGES];
+  const int64_t* neighbors[GR_FPN_STAGES];   int neighbors_w[GR_FPN_STAGES];   int64_t neighbors_ld[GR_FPN_STAGES];
+  const int64_t* subsampling[GR_FPN_STAGES]; int subsampling_w[GR_FPN_STAGES]; int64_t subsampling_ld[GR_FPN_STAGES];
+  const int64_t* upsampling[GR_FPN_STAGES];  int upsampling_w[GR_FPN_STAGES];  int64_t upsampling_ld[GR_FPN_STAGES];
+} gr_pyramid;
+
+/* y = [LeakyReLU]( GroupNorm(x W^T + b) [+ add] ), or x W^T + b when w->gn_weight is NULL.  `act_after_add`
+ * (0 none / 2 leaky) applies when the block itself has no activation (modules.py:207-225). */
+size_t gr_unary_block_workspace_size(int64_t rows, int out_channels, int groups);
+int gr_unary_block(const gr_unary_weights* h_w, const float* x, int64_t rows, int groups, float eps, const float* add,
+                   int act_after_add, float* y, void* ws, size_t ws_bytes, void* stream);
+/* y = LeakyReLU(GroupNorm(KPConv(...))) when gn_weight is given, the raw KPConv output otherwise. */
+size_t gr_kpconv_block_workspace_size(int M, int Ns, int in_channels, int out_channels, int groups);
+int gr_kpconv_block(const gr_kpconv_weights* h_w, const float* gn_weight, const float* gn_bias, int groups, float eps,
+                    const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbor_idx, int H,
+                    int64_t ld_idx, int M, int Ns, float* y, void* ws, size_t ws_bytes, void* stream);
+/* KPConvFPN.forward: feats (n_points[0], in) -> out_l2 (n1, C2), out_l3 (n2, C3), out_l4 (n3, C4), out_f5 (n4, C5)
+ * = the list backbone.py:210-212 returns.  Every kernel is issued from this one call. */
+size_t gr_kpconv_fpn_workspace_size(const gr_fpn_weights* h_w, const gr_pyramid* h_pyr);
+int gr_kpconv_fpn(const gr_fpn_weights* h_w, const gr_pyramid* h_pyr, const float* feats, float* out_l2, float* out_l3,
+                  float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream);
+
 /* P1  point-to-node partition (modules/ops/pointcloud_partition.py:61-111). */
 size_t gr_point_to_node_workspace_size(int64_t n_points, int64_t n_nodes);
 int gr_point_to_node_partition(const float* points, int N, const float* nodes, int M, int point_limit,

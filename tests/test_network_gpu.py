@@ -56,7 +56,7 @@ def test_gemm_batched_head_slices():
 
 # ---------------------------------------------------------------------------------------------- K1-K3
 @pytest.mark.parametrize("C,Co,H", [(4, 64, 20), (32, 32, 20), (64, 64, 30), (128, 128, 43), (256, 256, 47), (512, 512, 12),
-                                    (16, 24, 89), (8, 8, 5)])
+                                    (16, 24, 89), (8, 8, 5), (32, 32, 89), (64, 64, 49), (32, 64, 7)])
 def test_kpconv_vs_oracle(C, Co, H):
     g = torch.Generator().manual_seed(C + H)
     Ns, M = 700, 500
@@ -88,6 +88,54 @@ def test_group_norm_and_fusions(N, C):
     want2 = torch.nn.functional.leaky_relu(want + add, 0.1)
     got2 = ops.group_norm(x.cuda(), 32, gamma.cuda(), beta.cuda(), add=add.cuda(), act="leaky_relu").cpu()
     assert rel_l2(got2, want2) < 1e-5
+
+
+def _randomize(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for p in module.parameters():
+        p.data = torch.randn(p.shape, generator=g) * (0.5 if p.dim() == 1 else 1.0 / max(p.shape[-1], 1) ** 0.5) + (1.0 if p.dim() == 1 else 0.0)
+    return module
+
+
+@pytest.mark.parametrize("N,Cin,Cout,relu", [(5003, 64, 128, True), (3001, 1024, 256, False), (20000, 128, 32, True), (777, 256, 512, True),
+                                             (4100, 2048, 1024, True), (60000, 64, 32, True), (967, 3072, 1024, False)])
+def test_unary_block_fused_groupnorm_statistics_vs_oracle(N, Cin, Cout, relu):
+    """UnaryBlock through gr_unary_block: the GroupNorm statistics come from the tensor-core product's epilogue
+    (direct tile epilogue, split-K reduction, or the separate pass when the FFMA kernel runs) -- all vs the oracle."""
+    blk = _randomize(gm.UnaryBlock(Cin, Cout, 32, has_relu=relu), N).eval()
+    sd = {"u." + k: v.clone() for k, v in blk.state_dict().items()}
+    x, add = _rand(N, Cin, seed=1) * 2 + 0.3, _rand(N, Cout, seed=2)
+    want = onet.unary_block(sd, "u", x, relu)
+    blk = blk.cuda()
+    got = blk(x.cuda()).cpu()
+    assert rel_l2(got, want) < 1e-5
+    got2 = blk(x.cuda()).cpu()
+    assert torch.equal(got, got2)  # fixed reduction order: bit-stable run to run
+    if not relu:
+        want3 = torch.nn.functional.leaky_relu(want + add, 0.1)
+        got3 = blk(x.cuda(), add=add.cuda(), act_after_add="leaky_relu").cpu()
+        assert rel_l2(got3, want3) < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,strided", [(64, 128, False), (128, 128, True), (256, 256, False)])
+def test_residual_and_conv_block_vs_oracle(Cin, Cout, strided):
+    g = torch.Generator().manual_seed(Cin + Cout)
+    Ns, M, H = 6000, (2500 if strided else 6000), 26
+    s_pts = torch.rand(Ns, 3, generator=g)
+    q_pts = s_pts[:M].clone() if not strided else s_pts[:M] + 0.005 * torch.randn(M, 3, generator=g)
+    idx = torch.randint(0, Ns + 1, (M, H), generator=g)
+    idx[::9, H // 3:] = Ns
+    feats = torch.randn(Ns, Cin, generator=g)
+    blk = _randomize(gm.ResidualBlock(Cin, Cout, 15, 0.3, 0.25, 32, strided=strided), 7).eval()
+    sd = {"b." + k: v.clone() for k, v in blk.state_dict().items()}
+    want = onet.residual_block(sd, "b", feats, q_pts, s_pts, idx, 0.25, strided)
+    got = blk.cuda()(feats.cuda(), q_pts.cuda(), s_pts.cuda(), idx.cuda()).cpu()
+    assert rel_l2(got, want) < 2e-5
+    cb = _randomize(gm.ConvBlock(Cin, Cout, 15, 0.3, 0.25, 32), 8).eval()
+    sd = {"c." + k: v.clone() for k, v in cb.state_dict().items()}
+    want = onet.conv_block(sd, "c", feats, q_pts, s_pts, idx, 0.25)
+    got = cb.cuda()(feats.cuda(), q_pts.cuda(), s_pts.cuda(), idx.cuda()).cpu()
+    assert rel_l2(got, want) < 1e-5
 
 
 def test_layer_norm_maxpool_upsample_gather():
@@ -257,12 +305,17 @@ def _run_gpu_model(spec):
     cfg = make_cfg()
     data = registration_collate_fn_stack_mode([dd], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
                                               cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    out = model(data)  # the product path: the backbone is ONE native call (csrc/backbone.cu)
+    # taps per block come from the per-module path, which must agree with the native call bit for bit
     taps = {}
     hooks = [getattr(model.backbone, n).register_forward_hook(lambda m, i, o, n=n: taps.__setitem__(n, o)) for n in TAP_BLOCKS]
-    out = model(data)
-    torch.cuda.synchronize()
+    by_module = model.backbone.forward_modules(data["features"], data)
     for h in hooks:
         h.remove()
+    native = model.backbone(data["features"], data)
+    torch.cuda.synchronize()
+    for a, b in zip(native, by_module):
+        assert torch.equal(a, b)
     return model, data, out, taps
 
 
@@ -305,29 +358,10 @@ def test_full_forward_vs_oracle_and_reference_golden(case):
     assert sc_o.shape[0] == out["corr_scores"].shape[0]
     with open(f"gpurun_out/e2e_parity_{case}.txt", "w") as f:
         f.write(repr(report) + "\n")
-    if report["T_err_vs_oracle_LGR_on_gpu_inputs"] >= 1e-4 or report["T_err_vs_reference"] >= 1e-4:
-        # With seeded RANDOM weights the registration can be ill-conditioned: a few dozen inliers among thousands of
-        # garbage correspondences, hard 0.1 m inlier threshold, argmax over per-patch hypotheses whose 3x3 SVDs are
-        # rank-deficient.  A mismatch is only accepted if the REFERENCE algorithm itself is unstable at this input:
-        # its own CPU restatement, fed the same scores and patch points perturbed by fp32-rounding-sized noise
-        # (1e-6 relative), must move its transform by more than the tolerance.  Otherwise the mismatch is ours.
-        g = torch.Generator().manual_seed(0)
-        moves = []
-        for _ in range(6):
-            noisy = ms_gpu[:, :-1, :-1] * (1.0 + 1e-6 * torch.randn(ms_gpu[:, :-1, :-1].shape, generator=g))
-            rp, sp = out["ref_node_corr_knn_points"].cpu(), out["src_node_corr_knn_points"].cpu()
-            rp = rp * (1.0 + 1e-6 * torch.randn(rp.shape, generator=g))
-            sp = sp * (1.0 + 1e-6 * torch.randn(sp.shape, generator=g))
-            _, _, _, T_n = onet.local_global_registration(rp, sp, out["ref_node_corr_knn_masks"].cpu(),
-                                                          out["src_node_corr_knn_masks"].cpu(), noisy, cfgd)
-            moves.append(float(np.linalg.norm(T_n.numpy() - T_tf.numpy())))
-        report["reference_LGR_move_under_1e-6_noise"] = moves
-        valid = want["matching_scores"] > -1e11
-        if torch.equal(valid, ms_gpu > -1e11):
-            report["sinkhorn_rel_l2_vs_oracle"] = rel_l2(ms_gpu[valid].exp(), want["matching_scores"][valid].exp())
-        with open(f"gpurun_out/e2e_parity_{case}.txt", "w") as f:
-            f.write(repr(report) + "\n")
-        assert max(moves) > 1e-4, report
+    # north_star tolerance, no escape hatch: 1e-4 Frobenius against the reference's golden transform AND against the
+    # reference algorithm fed our own Sinkhorn output
+    assert report["T_err_vs_oracle_LGR_on_gpu_inputs"] < 1e-4 and report["T_err_vs_reference"] < 1e-4, report
+    assert report["pair_agreement"] == 1.0, report
 
 
 # ---------------------------------------------------------------------------------------------- tcgen05 GEMM
