@@ -10,12 +10,51 @@ import torch
 from . import ext
 
 
-def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits):
+class LazyTables(list):
+    """List of neighbour tables that is filled on first access.
+
+    The table WIDTHS are data-dependent (`min(max_count, limit)`, radius_search.py:24-27), so trimming the limit-wide
+    device tables needs one device->host read.  Deferring that read to the first access lets the caller queue
+    coordinate-only GPU work (point-to-node partition, structure embedding) behind the radius searches first: the
+    host then waits for the widths while the GPU is busy instead of idle.  One `finalize` is shared by the three
+    lists of a pyramid; any list operation triggers it."""
+
+    def __init__(self, finalize):
+        super().__init__()
+        self._finalize = finalize
+
+    def _ensure(self):
+        f = self._finalize
+        if f is not None:
+            f()
+
+    def __getitem__(self, i):
+        self._ensure()
+        return list.__getitem__(self, i)
+
+    def __len__(self):
+        self._ensure()
+        return list.__len__(self)
+
+    def __iter__(self):
+        self._ensure()
+        return list.__iter__(self)
+
+    def __repr__(self):
+        self._ensure()
+        return list.__repr__(self)
+
+
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, lazy=True):
+    """utils/data.py:13-77 on the GPU.  Returns the reference's dict plus `lengths_host` (python ints per stage and
+    cloud, read in the same device->host transfer as the stage sizes, so that the model needs no sync of its own).
+    With `lazy` (default) the three table lists are LazyTables: same contents, trimmed on first access."""
     assert num_stages == len(neighbor_limits)
     dev = points.device if points.is_cuda else ext._device()
     points = points.to(dev, torch.float32).contiguous()
     lengths = lengths.to(dev, torch.int64).contiguous()
     n0 = points.shape[0]
+    nb = lengths.shape[0]
 
     # --- grid subsampling chain, device-side lengths, buffers sized by the upper bound
     pts_cap, len_dev, totals = [points], [lengths], []
@@ -26,10 +65,9 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         pts_cap.append(out)
         len_dev.append(out_len)
         totals.append(out_total)
-    if totals:
-        tot = torch.cat(totals).cpu().tolist()  # sync 1
-    else:
-        tot = []
+    host = torch.cat(totals + len_dev).cpu().tolist()  # sync 1: stage sizes and per-cloud lengths
+    tot = host[:len(totals)]
+    lengths_host = [host[len(totals) + s * nb: len(totals) + (s + 1) * nb] for s in range(num_stages)]
     sizes = [n0] + [int(t) for t in tot]
     points_list = [pts_cap[i][: sizes[i]] for i in range(num_stages)]
     lengths_list = len_dev
@@ -55,11 +93,23 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             built[i + 1] = True
             tables.append(t); counts.append(c); meta.append(("upsampling", neighbor_limits[i + 1]))
         r *= 2
-    widths = torch.cat(counts).cpu().tolist()  # sync 2
-    out = {"points": points_list, "lengths": lengths_list, "neighbors": [], "subsampling": [], "upsampling": []}
-    for t, w, (key, limit) in zip(tables, widths, meta):
-        w = min(int(w), limit)
-        out[key].append(t[:, :w] if w == t.shape[1] else t[:, :w].contiguous())
+    counts_dev = torch.cat(counts)
+    out = {"points": points_list, "lengths": lengths_list, "lengths_host": lengths_host}
+
+    def finalize():
+        widths = counts_dev.cpu().tolist()  # sync 2
+        for t, w, (key, limit) in zip(tables, widths, meta):
+            w = min(int(w), limit)
+            list.append(out[key], t[:, :w] if w == t.shape[1] else t[:, :w].contiguous())
+        for key in ("neighbors", "subsampling", "upsampling"):
+            out[key]._finalize = None
+
+    for key in ("neighbors", "subsampling", "upsampling"):
+        out[key] = LazyTables(finalize)
+    if not lazy:
+        finalize()
+        for key in ("neighbors", "subsampling", "upsampling"):
+            out[key] = list(out[key])
     return out
 
 

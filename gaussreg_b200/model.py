@@ -63,12 +63,20 @@ class GeoTransformer(nn.Module):
         _, ref_node_masks, ref_node_knn_indices, ref_node_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, K)
         _, src_node_masks, src_node_knn_indices, src_node_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, K)
 
+        # 3a. geometric structure embedding (geotransformer.py:57-72) depends on the superpoint coordinates only: it is
+        # queued BEFORE the backbone, so that the GPU is busy while the host reads the neighbour-table widths
+        # (data.LazyTables) and prepares the backbone call
+        ref_emb = self.transformer.embedding(ref_points_c)
+        src_emb = self.transformer.embedding(src_points_c)
+
         # 2. KPConv FPN (model.py:129-132)
         feats_list = self.backbone(feats, data_dict)
         feats_c, feats_f = feats_list[-1], feats_list[0]
 
-        # 3. geometric transformer (model.py:135-147)
-        ref_feats_c, src_feats_c = self.transformer(ref_points_c, src_points_c, feats_c[:ref_length_c], feats_c[ref_length_c:])
+        # 3b. geometric transformer (model.py:135-147)
+        ref_feats_c, src_feats_c = self.transformer(ref_points_c, src_points_c, feats_c[:ref_length_c], feats_c[ref_length_c:],
+                                                    embeddings=(ref_emb, src_emb))
+        del ref_emb, src_emb
         ref_feats_c_norm = ops.l2_normalize_rows(ref_feats_c)
         src_feats_c_norm = ops.l2_normalize_rows(src_feats_c)
         out["ref_feats_c"], out["src_feats_c"] = ref_feats_c_norm, src_feats_c_norm

@@ -278,6 +278,10 @@ class RPEConditionalTransformer(nn.Module):
         return (f0, f1, scores) if self.return_attention_scores else (f0, f1)
 
 
+def _squeeze_emb(e):
+    return (e[0], True) if e.dim() == 4 else (e, False)
+
+
 class GeometricTransformer(nn.Module):
     """geotransformer.py:75-155."""
 
@@ -290,13 +294,18 @@ class GeometricTransformer(nn.Module):
         self.out_proj = nn.Linear(hidden_dim, output_dim)
 
     @torch.no_grad()
-    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_masks=None, src_masks=None):
+    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_masks=None, src_masks=None, embeddings=None):
+        """`embeddings` (extension): the two structure embeddings if the caller already evaluated them."""
         rp, batched = _squeeze(ref_points)
         sp, _ = _squeeze(src_points)
         rf, _ = _squeeze(ref_feats)
         sf, _ = _squeeze(src_feats)
-        ref_emb = self.embedding(rp)
-        src_emb = self.embedding(sp)
+        if embeddings is not None:
+            ref_emb, _ = _squeeze_emb(embeddings[0])
+            src_emb, _ = _squeeze_emb(embeddings[1])
+        else:
+            ref_emb = self.embedding(rp)
+            src_emb = self.embedding(sp)
         rf = ops.linear(rf, self.in_proj.weight, self.in_proj.bias)
         sf = ops.linear(sf, self.in_proj.weight, self.in_proj.bias)
         rf, sf = self.transformer(rf, sf, ref_emb, src_emb, masks0=ref_masks, masks1=src_masks)
