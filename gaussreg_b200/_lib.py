@@ -107,6 +107,10 @@ _SIGNATURES = {
     "gr_lgr_workspace_size": (_sz, [_i32, _i32, _i32]),
     "gr_local_global_registration": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _f32, _i32, _i32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_farthest_point_sample_workspace_size": (_sz, [_i64]),
+    "gr_farthest_point_sample": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "gr_similarity_ransac_workspace_size": (_sz, [_i32]),
+    "gr_similarity_ransac": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, ctypes.c_uint64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_weighted_procrustes": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "gr_column_order_stats_workspace_size": (_sz, [_i32]),
     "gr_column_order_stats": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),

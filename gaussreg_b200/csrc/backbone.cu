@@ -7,6 +7,8 @@
 // C++ the same sequence costs well under a millisecond of host time, and a host thread per CUDA stream can drive
 // several pairs at once (the C-ABI call releases the GIL).  The GroupNorm statistics of every Linear / KPConv
 // output come out of the product's own epilogue (GnStatsOut), so no block re-reads its activations for them.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 extern "C" {
@@ -89,30 +91,62 @@ static int unary(const gr_unary_weights& w, const float* x, long long rows, int 
   return rc;
 }
 
+// Optional row chunking of the KPConv operand A (M, 15 C) (GAUSSREG_KPCONV_CHUNK_MB > 0): the layer is cut into row
+// chunks whose operand stays in the 126 MB L2 between the aggregation and the contraction.  Measured on B200 in both
+// rounds and OFF by default: 40 MB chunks cost +0.5 ms per pair, 24 MB chunks +1.0 ms -- the extra launches and the
+// partial waves of the smaller grids outweigh the DRAM traffic saved (the two kernels are latency-, not
+// bandwidth-bound).  Chunk boundaries are multiples of 128 rows (tile and statistics granularity).
+static int kpconv_chunk_rows(int M, int KC) {
+  static int mb = -1;
+  if (mb < 0) { const char* e = getenv("GAUSSREG_KPCONV_CHUNK_MB"); mb = e ? atoi(e) : 0; }
+  if (mb <= 0) return M;
+  long long rows = ((long long)mb << 20) / ((long long)KC * 4);
+  rows = rows / 128 * 128;
+  if (rows < 1024) rows = 1024;
+  if (rows >= M) return M;
+  // balance the chunks
+  const int n = (int)((M + rows - 1) / rows);
+  long long per = ((M + n - 1) / n + 127) / 128 * 128;
+  return (int)per;
+}
+
 // KPConv (kpconv.py:79-122) [+ GroupNorm + LeakyReLU]
 static int kpconv(const gr_kpconv_weights& w, const float* gn_w, const float* gn_b, int groups, float eps, const float* s_feats,
                   const float* q_pts, const float* s_pts, const int64_t* idx, int H, int64_t ld, int M, int Ns, float* y, Arena& ar,
                   void* st) {
   const int C = w.in_channels, Co = w.out_channels, KC = 15 * C;
   const size_t mk = ar.mark();
-  float* A = ar.take<float>((size_t)M * KC);
+  const int chunk = kpconv_chunk_rows(M, KC);
+  float* A = ar.take<float>((size_t)chunk * KC);
   float* row_div = ar.take<float>((size_t)M);
   const size_t fws_bytes = gr_kpconv_aggregate_workspace_size(Ns);
   char* fws = ar.take<char>(fws_bytes);
   float* tmp = gn_w ? ar.take<float>((size_t)M * Co) : y;
   GnStatsOut gn{nullptr, 0, groups, 0};
-  if (gn_w) { gn.capacity_blocks = gn_blocks_capacity(M); gn.partial = ar.take<double2>(gn.capacity_blocks * groups); }
+  size_t cap_blocks = 0;
+  if (gn_w) { cap_blocks = gn_blocks_capacity(M) + (size_t)(M / chunk + 2); gn.partial = ar.take<double2>(cap_blocks * groups); }
   int rc = GR_OK;
+  int nblk_total = 0;
+  bool stats_ok = gn_w != nullptr;
   if (!ar.dry) {
     if (!ar.ok()) return GR_ERR_WORKSPACE;
-    rc = gr_kpconv_aggregate(s_feats, C, q_pts, s_pts, idx, H, ld, M, Ns, w.kernel_points, 15, w.sigma, A, row_div, fws, fws_bytes, st);
-    if (rc == GR_OK) {
+    for (int r0 = 0; r0 < M && rc == GR_OK; r0 += chunk) {
+      const int rows = M - r0 < chunk ? M - r0 : chunk;
+      // the support-row flags (workspace) are recomputed per chunk by gr_kpconv_aggregate: Ns bytes, negligible
+      rc = gr_kpconv_aggregate(s_feats, C, q_pts + 3ll * r0, s_pts, idx + (long long)r0 * ld, H, ld, rows, Ns, w.kernel_points, 15,
+                               w.sigma, A, row_div + r0, fws, fws_bytes, st);
+      if (rc != GR_OK) break;
+      GnStatsOut g{gn.partial ? gn.partial + (size_t)nblk_total * groups : nullptr, cap_blocks - (size_t)nblk_total, groups, 0};
+      GnStatsOut* gp = (gn_w && stats_ok) ? &g : nullptr;
       if (w.weights_kmajor && KC % 4 == 0)
-        rc = gemm_ex(A, KC, w.weights_kmajor, KC, 1, tmp, Co, M, Co, KC, 1.f, w.bias, row_div, nullptr, 0, 0, st,
-                     w.weights_kmajor_packed, gn_w ? &gn : nullptr);
+        rc = gemm_ex(A, KC, w.weights_kmajor, KC, 1, tmp + (size_t)r0 * Co, Co, rows, Co, KC, 1.f, w.bias, row_div + r0, nullptr, 0, 0, st,
+                     w.weights_kmajor_packed, gp);
       else
-        rc = gemm_ex(A, KC, w.weights, Co, 0, tmp, Co, M, Co, KC, 1.f, w.bias, row_div, nullptr, 0, 0, st, nullptr, nullptr);
+        rc = gemm_ex(A, KC, w.weights, Co, 0, tmp + (size_t)r0 * Co, Co, rows, Co, KC, 1.f, w.bias, row_div + r0, nullptr, 0, 0, st, nullptr,
+                     nullptr), gp = nullptr;
+      if (gp && g.nblk > 0) nblk_total += g.nblk; else stats_ok = false;  // one chunk without statistics -> separate pass
     }
+    gn.nblk = stats_ok ? nblk_total : 0;
   }
   if (rc == GR_OK && gn_w) rc = norm_after_product(tmp, M, Co, groups, eps, gn, gn_w, gn_b, nullptr, 2, y, ar, st);
   ar.release(mk);

@@ -11,6 +11,8 @@
 
 #include "common.cuh"
 
+extern "C" int gr_get_gemm_mode(void);
+
 namespace gr {
 
 struct GemmParams {
@@ -230,6 +232,156 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(GemmParams p) {
   }
 }
 
+// ---- superpoint-sized products on the (legacy-path) tensor cores --------------------------------------------------
+// The ~480-row transformer products are far too small for 128-row tcgen05 tiles (a handful of CTAs), and the FFMA
+// kernel above spends 14-20 us on each of them (one L2 round trip per 32-deep k-slab, no overlap).  This kernel keeps
+// them on 64x64 tiles (dozens of CTAs) but runs the inner product as mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (fp32-level accuracy: the raw fp32 word serves as the truncated hi part, lo = x - trunc(x), products lo*hi + hi*lo +
+// hi*hi in fp32 accumulators) and double-buffers the k-slabs with cp.async.  4 warps, warp tile 32x32.
+// Requirements (checked by the dispatcher): 16-byte aligned operands, lda/ldb/strides % 4 == 0, K % 4 == 0
+// (and N % 4 == 0 for the (K,N) "NN" form).
+__device__ __forceinline__ void sm_cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void sm_mma_tf32(float (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned sm_lo_bits(float x) { return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u)); }
+
+template <bool TRANSB>
+__global__ void __launch_bounds__(128) gemm_mma_small_kernel(GemmParams p) {
+  constexpr int BM = 64, BN = 64, BK = 32;
+  constexpr int PA = BK + 4;                       // A tile (and the (N,K) B tile): [64][36], conflict-free fragment reads
+  constexpr int PB = TRANSB ? BK + 4 : BN + 8;     // (K,N) B tile: [32][72]
+  constexpr int B_ELEMS = TRANSB ? BN * PB : BK * PB;
+  __shared__ __align__(16) float As[2][BM * PA];
+  __shared__ __align__(16) float Bs[2][B_ELEMS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+  float* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
+
+  auto load_slab = [&](int buf, int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // A: 64 rows x 8 chunks of 16 bytes
+      const int e = tid + i * 128, r = e >> 3, c = e & 7;
+      const int gm = m0 + r, gk = k0 + 4 * c;
+      const bool ok = gm < p.M && gk < p.K;
+      sm_cp_async16(&As[buf][r * PA + 4 * c], A + (ok ? (long long)gm * p.lda + gk : 0), ok ? 16 : 0);
+    }
+    if (TRANSB) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 128, r = e >> 3, c = e & 7;
+        const int gn = n0 + r, gk = k0 + 4 * c;
+        const bool ok = gn < p.N && gk < p.K;
+        sm_cp_async16(&Bs[buf][r * PB + 4 * c], B + (ok ? (long long)gn * p.ldb + gk : 0), ok ? 16 : 0);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 32 k-rows x 16 chunks
+        const int e = tid + i * 128, r = e >> 4, c = e & 15;
+        const int gk = k0 + r, gn = n0 + 4 * c;
+        const bool ok = gk < p.K && gn < p.N;  // N % 4 == 0: a chunk is entirely inside or outside
+        sm_cp_async16(&Bs[buf][r * PB + 4 * c], B + (ok ? (long long)gk * p.ldb + gn : 0), ok ? 16 : 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_slab(0, 0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) {
+      load_slab(buf ^ 1, (kt + 1) * BK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* as = As[buf];
+    const float* bs = Bs[buf];
+#pragma unroll
+    for (int k8 = 0; k8 < BK; k8 += 8) {
+      unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float* ap = as + (wm + 16 * i + g) * PA + k8 + t;
+        const float a0 = ap[0], a1 = ap[8 * PA], a2 = ap[4], a3 = ap[8 * PA + 4];
+        ah[i][0] = __float_as_uint(a0); ah[i][1] = __float_as_uint(a1); ah[i][2] = __float_as_uint(a2); ah[i][3] = __float_as_uint(a3);
+        al[i][0] = sm_lo_bits(a0); al[i][1] = sm_lo_bits(a1); al[i][2] = sm_lo_bits(a2); al[i][3] = sm_lo_bits(a3);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float b0, b1;
+        if (TRANSB) { const float* bp = bs + (wn + 8 * j + g) * PB + k8 + t; b0 = bp[0]; b1 = bp[4]; }
+        else { const float* bp = bs + (k8 + t) * PB + wn + 8 * j + g; b0 = bp[0]; b1 = bp[4 * PB]; }
+        bh[j][0] = __float_as_uint(b0); bh[j][1] = __float_as_uint(b1);
+        bl[j][0] = sm_lo_bits(b0); bl[j][1] = sm_lo_bits(b1);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], al[i][0], al[i][1], al[i][2], al[i][3], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bl[j][0], bl[j][1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+    }
+    __syncthreads();
+  }
+  // epilogue: lane (g,t) holds rows g, g+8 and columns 2t, 2t+1 of every 16x8 tile
+  const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int gm = m0 + wm + 16 * i + g + 8 * hrow;
+      if (gm >= p.M) continue;
+      const float rd = p.row_div ? p.row_div[gm] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gn = n0 + wn + 8 * j + 2 * t + e;
+          if (gn >= p.N) continue;
+          float v = acc[i][j][2 * hrow + e] * p.alpha;
+          if (p.row_div) v = v / rd;
+          if (p.bias) v += p.bias[gn];
+          if (R) v += R[(long long)gm * p.ldr + gn];
+          C[(long long)gm * p.ldc + gn] = apply_act(v, p.act);
+        }
+    }
+}
+
+static bool mma_small_ok(const GemmParams& p, bool transb) {
+  static int knob = -1;
+  if (knob < 0) { const char* e = getenv("GAUSSREG_GEMM_SMALL_MMA"); knob = e ? atoi(e) : 1; }
+  if (!knob) return false;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(p.A) || !al16(p.B) || p.lda % 4 != 0 || p.ldb % 4 != 0 || p.sA % 4 != 0 || p.sB % 4 != 0 || p.K % 4 != 0) return false;
+  if (!transb && p.N % 4 != 0) return false;
+  return p.K >= 16;
+}
+
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
@@ -247,7 +399,15 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
   if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
   if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
-  // superpoint-sized problems: small tiles, K split over four thread groups inside the CTA
+  // superpoint-sized problems: 64x64 tiles on mma.sync (3xTF32), cp.async double buffering
+  if (gr_get_gemm_mode() == 1 && mma_small_ok(p, transb)) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, batch);
+    if (transb) gemm_mma_small_kernel<true><<<grid, 128, 0, st>>>(p);
+    else gemm_mma_small_kernel<false><<<grid, 128, 0, st>>>(p);
+    GR_CHECK_LAUNCH("gemm_mma_small_kernel");
+    return GR_OK;
+  }
+  // unaligned / odd shapes: FFMA kernel, small tiles, K split over four thread groups inside the CTA
   {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
     if (transb) sgemm_small_kernel<true><<<grid, 256, 0, st>>>(p);

@@ -11,6 +11,7 @@
 //              fused epilogue -> st.global);
 //   warp 8     one elected thread issues the tcgen05.mma chain and tcgen05.commit's.
 // Stage hand-over is by mbarriers: full[s] (256 producer arrivals) / empty[s] (tcgen05.commit).
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link-time libcuda)
 #include <stdlib.h>
 
 #include <mutex>
@@ -93,6 +94,114 @@ __device__ __forceinline__ void tile_store(const TileRegs<ROWS>& t, unsigned cha
     lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
     *reinterpret_cast<float4*>(s_hi + off) = hi;
     *reinterpret_cast<float4*>(s_lo + off) = lo;
+  }
+}
+
+// Epilogue of one 128 x BN output tile, executed by the 8 producer warps (256 threads): TMEM -> registers -> shared
+// memory transpose -> fused epilogue -> global, plus the optional GroupNorm column statistics.
+template <int BN>
+__device__ __forceinline__ void tile_epilogue(const Params& p, unsigned char* smem, uint32_t accum_bar, uint32_t tmem_acc, int tid,
+                                              int warp, int lane, int m0, int n0) {
+  // ------------------------------------------------------------------ epilogue
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+  const int q = warp & 3, half = warp >> 2;
+  float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;  // split-K: sC = M*N, raw partial sums
+  const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+  const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) &&
+                      (!R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+  // Each thread holds one accumulator ROW (TMEM lane); storing rows directly would make every warp store hit 32
+  // different lines.  The 32x32 chunk is therefore transposed through shared memory (the operand stages are free
+  // once accum_bar has fired): rows are written with a 36-float pitch, read back as 4 rows x 32 columns per warp
+  // instruction, so that global stores / residual loads are full 128-byte lines.
+  float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+#pragma unroll 1
+  for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+    uint32_t r[32], rc[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v;
+      v.x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+      v.y = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]);
+      v.z = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]);
+      v.w = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]);
+      *reinterpret_cast<float4*>(stage + lane * 36 + j) = v;
+    }
+    __syncwarp();
+    const int nbase = n0 + c0;
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int n = nbase + c4;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+      if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
+      else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
+    }
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int rr = 0; rr < 32; rr += 4) {
+      const int row = rr + rsub;
+      const int m = m0 + q * 32 + row;
+      if (m >= p.M) continue;
+      const float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+      float x[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+      if (p.row_div) { const float rd = p.row_div[m]; x[0] /= rd; x[1] /= rd; x[2] /= rd; x[3] /= rd; }
+      x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
+      if (R) {
+        const float* rp = R + (long long)m * p.ldr + n;
+        if (vec_ok && n + 3 < p.N) { const float4 t = *reinterpret_cast<const float4*>(rp); x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w; }
+        else { for (int e = 0; e < 4; ++e) if (n + e < p.N) x[e] += rp[e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (p.act == 1) x[e] = fmaxf(x[e], 0.f);
+        else if (p.act == 2) x[e] = x[e] > 0.f ? x[e] : 0.1f * x[e];
+      }
+      float* dst = Cp + (long long)m * p.ldc + n;
+      if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+      else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
+      if (p.gn_partial) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < p.N) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
+      }
+    }
+    if (p.gn_partial) {  // column sums over this warp's 32 rows (fp32, at most 8 terms per lane, then 4 lanes)
+      float2* gn_col = reinterpret_cast<float2*>(smem + 40 * 1024);  // [4 row quarters][BN]
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
+        cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+      }
+      if (rsub == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gn_col[q * BN + c0 + c4 + e] = make_float2(cs[e], cq[e]);
+      }
+    }
+  }
+  if (p.gn_partial) {
+    // fold the four row quarters per column (double, fixed order), then the columns of each group
+    const float2* gn_col = reinterpret_cast<const float2*>(smem + 40 * 1024);
+    double2* gn_cold = reinterpret_cast<double2*>(smem + 48 * 1024);  // [BN]
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid < BN) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) { const float2 v = gn_col[qq * BN + tid]; a += (double)v.x; b += (double)v.y; }
+      gn_cold[tid] = make_double2(a, b);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int cg = p.N / p.gn_groups;  // host guarantees cg | BN and N % BN-aligned groups
+    if (tid < BN / cg) {
+      const int gidx = n0 / cg + tid;
+      if (gidx < p.gn_groups) {
+        double a = 0.0, b = 0.0;
+        for (int c = tid * cg; c < (tid + 1) * cg; ++c) { a += gn_cold[c].x; b += gn_cold[c].y; }
+        p.gn_partial[(long long)blockIdx.y * p.gn_groups + gidx] = make_double2(a, b);
+      }
+    }
   }
 }
 
@@ -180,107 +289,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
         if (!packed) rb = rb_next;
       }
     }
-    // ------------------------------------------------------------------ epilogue
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;  // split-K: sC = M*N, raw partial sums
-    const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) &&
-                        (!R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
-    // Each thread holds one accumulator ROW (TMEM lane); storing rows directly would make every warp store hit 32
-    // different lines.  The 32x32 chunk is therefore transposed through shared memory (the operand stages are free
-    // once accum_bar has fired): rows are written with a 36-float pitch, read back as 4 rows x 32 columns per warp
-    // instruction, so that global stores / residual loads are full 128-byte lines.
-    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
-#pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-      uint32_t r[32], rc[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v;
-        v.x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-        v.y = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]);
-        v.z = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]);
-        v.w = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]);
-        *reinterpret_cast<float4*>(stage + lane * 36 + j) = v;
-      }
-      __syncwarp();
-      const int nbase = n0 + c0;
-      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-      const int n = nbase + c4;
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) {
-        if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
-        else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
-      }
-      float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int rr = 0; rr < 32; rr += 4) {
-        const int row = rr + rsub;
-        const int m = m0 + q * 32 + row;
-        if (m >= p.M) continue;
-        const float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
-        float x[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
-        if (p.row_div) { const float rd = p.row_div[m]; x[0] /= rd; x[1] /= rd; x[2] /= rd; x[3] /= rd; }
-        x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
-        if (R) {
-          const float* rp = R + (long long)m * p.ldr + n;
-          if (vec_ok && n + 3 < p.N) { const float4 t = *reinterpret_cast<const float4*>(rp); x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w; }
-          else { for (int e = 0; e < 4; ++e) if (n + e < p.N) x[e] += rp[e]; }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (p.act == 1) x[e] = fmaxf(x[e], 0.f);
-          else if (p.act == 2) x[e] = x[e] > 0.f ? x[e] : 0.1f * x[e];
-        }
-        float* dst = Cp + (long long)m * p.ldc + n;
-        if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-        else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
-        if (p.gn_partial) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < p.N) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
-        }
-      }
-      if (p.gn_partial) {  // column sums over this warp's 32 rows (fp32, at most 8 terms per lane, then 4 lanes)
-        float2* gn_col = reinterpret_cast<float2*>(smem + 40 * 1024);  // [4 row quarters][BN]
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
-          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
-        }
-        if (rsub == 0) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) gn_col[q * BN + c0 + c4 + e] = make_float2(cs[e], cq[e]);
-        }
-      }
-    }
-    if (p.gn_partial) {
-      // fold the four row quarters per column (double, fixed order), then the columns of each group
-      const float2* gn_col = reinterpret_cast<const float2*>(smem + 40 * 1024);
-      double2* gn_cold = reinterpret_cast<double2*>(smem + 48 * 1024);  // [BN]
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < BN) {
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) { const float2 v = gn_col[qq * BN + tid]; a += (double)v.x; b += (double)v.y; }
-        gn_cold[tid] = make_double2(a, b);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int cg = p.N / p.gn_groups;  // host guarantees cg | BN and N % BN-aligned groups
-      if (tid < BN / cg) {
-        const int gidx = n0 / cg + tid;
-        if (gidx < p.gn_groups) {
-          double a = 0.0, b = 0.0;
-          for (int c = tid * cg; c < (tid + 1) * cg; ++c) { a += gn_cold[c].x; b += gn_cold[c].y; }
-          p.gn_partial[(long long)blockIdx.y * p.gn_groups + gidx] = make_double2(a, b);
-        }
-      }
-    }
+    tile_epilogue<BN>(p, smem, accum_bar, tmem_acc, tid, warp, lane, m0, n0);
     tc_fence_before();
   } else {
     // ------------------------------------------------------------------ MMA issuer
@@ -310,6 +319,175 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
         umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
       }
       umma_commit(accum_bar);  // accumulator complete
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(2 * BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-fed variant for products with a PRE-PACKED static B (every Linear / KPConv contraction of the backbone).
+//
+// Measured on B200 (round 1, profiles/r01h): the A-streaming products of the backbone (e.g. 41907 x 64 x 960, a
+// 161 MB operand) ran at ~1.6 TB/s of A traffic -- a quarter of HBM -- because each k-block of A travelled
+// ld.global -> registers -> cvt -> st.shared with a single k-block of look-ahead.  Here
+//   * warp 9 (one thread) streams A with tensor-map TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a ring of
+//     kRaw raw fp32 tiles that runs up to kRaw k-blocks ahead of the tensor core, and the packed B tiles with plain
+//     bulk copies into the operand ring;
+//   * the raw tile is used AS IS for the hi operand: the tensor core reads only the upper 19 bits of each fp32 word
+//     (sign, exponent, 10 mantissa bits), i.e. it sees trunc_tf32(x).  Warps 0-7 only derive the low part
+//     lo = x - trunc_tf32(x) (exact in fp32) into the operand ring -- one LDS.128 / STS.128 pair per 4 elements at
+//     the SAME byte offset (TMA already wrote the UMMA canonical swizzled layout), no address arithmetic;
+//   * warp 8 issues the same three products per k-step as gemm_tf32x3_kernel and releases both rings with
+//     tcgen05.commit.
+// Out-of-range rows / k are zero-filled by TMA, so edge tiles need no predicates.
+template <int BN>
+struct CfgTma {
+  static constexpr int kABytes = BM * BK * 4;
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kOpBytes = kABytes + 2 * kBBytes;              // a_lo | b_hi | b_lo
+  static constexpr int kOps = 2;                                       // operand-ring depth
+  static constexpr int kRaw = BN == 256 ? 4 : 8;                       // raw A ring depth (16 KB each)
+  static constexpr int kSmemBytes = kRaw * kABytes + kOps * kOpBytes + 1024 /*align*/ + 512 /*barriers*/;
+};
+constexpr int kThreadsTma = kProducerThreads + 64;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsTma, 1) gemm_tf32x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p) {
+  using C = CfgTma<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* raw_ring = smem;                                   // [kRaw][16 KB]
+  unsigned char* op_ring = smem + C::kRaw * C::kABytes;             // [kOps][a_lo | b_hi | b_lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_ring + C::kOps * C::kOpBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto raw_full = [&](int r) { return bar_base + 8u * r; };                          // TMA bytes of raw tile r
+  auto raw_empty = [&](int r) { return bar_base + 8u * (C::kRaw + r); };             // tcgen05.commit
+  auto op_full = [&](int s) { return bar_base + 8u * (2 * C::kRaw + s); };           // 8 splitter warps + B bytes
+  auto op_empty = [&](int s) { return bar_base + 8u * (2 * C::kRaw + C::kOps + s); };  // tcgen05.commit
+  const uint32_t accum_bar = bar_base + 8u * (2 * C::kRaw + 2 * C::kOps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kRaw + 2 * C::kOps + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const bool split = p.k_split > 0;
+  const int kbeg = split ? blockIdx.z * p.k_split : 0;
+  const int kend = split ? min(p.K, kbeg + p.k_split) : p.K;
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+  const int rot = (int)(blockIdx.y % (unsigned)nkb);  // see gemm_tf32x3_kernel: de-synchronise the weight stream
+  auto kbr = [&](int kb) { int r = kb + rot; return r >= nkb ? r - nkb : r; };
+
+  if (tid == 0) {
+    for (int r = 0; r < C::kRaw; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), 1); }
+    for (int s = 0; s < C::kOps; ++s) { mbar_init(op_full(s), kProducerThreads / 32 + 1); mbar_init(op_empty(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ low-part derivation, then the epilogue
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int r = kb % C::kRaw, s = kb % C::kOps;
+      if (kb >= C::kOps) mbar_wait(op_empty(s), ((kb / C::kOps) - 1) & 1);  // a_lo slot free again
+      mbar_wait(raw_full(r), (kb / C::kRaw) & 1);
+      const float4* src = reinterpret_cast<const float4*>(raw_ring + r * C::kABytes);
+      float4* dst = reinterpret_cast<float4*>(op_ring + s * C::kOpBytes);
+#pragma unroll
+      for (int i = 0; i < BM * BK / 4 / kProducerThreads; ++i) {
+        const float4 v = src[tid + i * kProducerThreads];
+        float4 lo;
+        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        dst[tid + i * kProducerThreads] = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_full(s));
+    }
+    tile_epilogue<BN>(p, smem, accum_bar, tmem_acc, tid, warp, lane, m0, n0);
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int r = kb % C::kRaw, s = kb % C::kOps;
+        mbar_wait(op_full(s), (kb / C::kOps) & 1);  // implies raw tile r has landed (the splitters read it)
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(raw_ring + r * C::kABytes);
+        const uint32_t a_lo = smem_u32(op_ring + s * C::kOpBytes);
+        const uint32_t b_hi = a_lo + C::kABytes;
+        const uint32_t b_lo = b_hi + C::kBBytes;
+#pragma unroll
+        for (int k8 = 0; k8 < BK / 8; ++k8) {
+          const uint32_t ko = k8 * 32;
+          const uint32_t first = (kb | k8) != 0 ? 1u : 0u;
+          umma_tf32(tmem_acc + BN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
+          umma_tf32(tmem_acc + BN, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_tf32(tmem_acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+        }
+        umma_commit(raw_empty(r));
+        umma_commit(op_empty(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ loader (one thread): TMA for A, bulk copies for B
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      constexpr uint32_t kRowBytes = BN < 128 ? BN * 128 : 128 * 128;
+      constexpr int kCopies = BN / 128 > 0 ? BN / 128 : 1;
+      // A runs kRaw - kOps k-blocks ahead of B.  Every wait below is on the MMA of a k-block whose A and B tiles were
+      // issued earlier in this same sequence, so the single loader thread can never block itself.
+      auto issue_a = [&](int kb) {
+        const int r = kb % C::kRaw;
+        if (kb >= C::kRaw) mbar_wait(raw_empty(r), ((kb / C::kRaw) - 1) & 1);
+        mbar_arrive_expect_tx(raw_full(r), (uint32_t)C::kABytes);
+        tma_load_2d(smem_u32(raw_ring + r * C::kABytes), &tmap_a, kbeg + kbr(kb) * BK, m0, raw_full(r));
+      };
+      auto issue_b = [&](int kb) {
+        const int s = kb % C::kOps;
+        if (kb >= C::kOps) mbar_wait(op_empty(s), ((kb / C::kOps) - 1) & 1);
+        mbar_arrive_expect_tx(op_full(s), 2u * kCopies * kRowBytes);
+        const int kblock = (kbeg / BK) + kbr(kb);
+        const uint32_t b_hi_s = smem_u32(op_ring + s * C::kOpBytes + C::kABytes), b_lo_s = b_hi_s + C::kBBytes;
+#pragma unroll
+        for (int c = 0; c < kCopies; ++c) {
+          const int row0 = n0 + c * 128;
+          const int nt = row0 >> 7, rin = row0 & 127;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.B_packed) +
+                                     ((size_t)nt * p.packed_kblocks + kblock) * (2 * 16384) + (size_t)rin * 128;
+          bulk_copy_g2s(b_hi_s + c * 16384, src, kRowBytes, op_full(s));
+          bulk_copy_g2s(b_lo_s + c * 16384, src + 16384, kRowBytes, op_full(s));
+        }
+      };
+      constexpr int kLead = C::kRaw - C::kOps;
+      for (int kb = 0; kb < kLead && kb < nkb; ++kb) issue_a(kb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        issue_b(kb);
+        if (kb + kLead < nkb) issue_a(kb + kLead);
+      }
     }
     __syncwarp();
   }
@@ -351,25 +529,30 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // columns (thread = 4 consecutive columns, remaining thread bits walk rows); per-thread fp32 sums over at most 32
 // rows, folded in double in a fixed order -> gn_partial[blockIdx.x * G + g].
 constexpr int kRedRows = kGnReduceRows;
-__global__ void __launch_bounds__(256) splitk_reduce_gn_kernel(const float* __restrict__ partial, int splits, Params p) {
-  extern __shared__ double2 red_sh[];  // chs[N], then stage[R * N] when several row lanes share a column
+__global__ void __launch_bounds__(256) splitk_reduce_gn_kernel(const float* __restrict__ partial, int splits, Params p, int col_chunk) {
+  // block (x, y): rows [32 x, 32 x + 32), columns [y * col_chunk, (y + 1) * col_chunk); col_chunk is a multiple of the
+  // group width, so every group's statistics come from exactly one column block
+  extern __shared__ double2 red_sh[];  // chs[col_chunk], then stage[R * col_chunk] when several row lanes share a column
+  const int cbeg = blockIdx.y * col_chunk;
+  const int ncol = min(col_chunk, p.N - cbeg);
   double2* chs = red_sh;
-  double2* stage = red_sh + p.N;
+  double2* stage = red_sh + col_chunk;
   const int r0 = blockIdx.x * kRedRows, r1 = min(p.M, r0 + kRedRows);
   const int tid = threadIdx.x;
-  const int c4n = p.N >> 2;
+  const int c4n = ncol >> 2;
   const int lanes = c4n < 256 ? c4n : 256;
   const int R = 256 / lanes;
   const int rs = tid / lanes;
+  const int n4 = p.N >> 2;
   const long long plane = (long long)p.M * p.N;
   if (rs < R) {
     for (int cc = tid % lanes; cc < c4n; cc += lanes) {
-      const int n = cc * 4;
+      const int n = cbeg + cc * 4;
       float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) bv = make_float4(p.bias[n], p.bias[n + 1], p.bias[n + 2], p.bias[n + 3]);
       for (int r = r0 + rs; r < r1; r += R) {
-        const long long i = (long long)r * c4n + cc;
+        const long long i = (long long)r * n4 + (n >> 2);
         float4 acc = reinterpret_cast<const float4*>(partial)[i];
         for (int z = 1; z < splits; ++z) {
           const float4 v = reinterpret_cast<const float4*>(partial + z * plane)[i];
@@ -393,25 +576,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_gn_kernel(const float* __re
         if ((p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
         else { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
       }
-      double2* dst = (R == 1) ? chs + n : stage + (size_t)rs * p.N + n;
+      double2* dst = (R == 1) ? chs + 4 * cc : stage + (size_t)rs * col_chunk + 4 * cc;
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_double2((double)fs[k], (double)fq[k]);
     }
   }
   __syncthreads();
   if (R > 1) {
-    for (int c = tid; c < p.N; c += 256) {
+    for (int c = tid; c < ncol; c += 256) {
       double2 a = stage[c];
-      for (int k = 1; k < R; ++k) { const double2 b = stage[(size_t)k * p.N + c]; a.x += b.x; a.y += b.y; }
+      for (int k = 1; k < R; ++k) { const double2 b = stage[(size_t)k * col_chunk + c]; a.x += b.x; a.y += b.y; }
       chs[c] = a;
     }
     __syncthreads();
   }
   const int cg = p.N / p.gn_groups;
-  for (int g = tid; g < p.gn_groups; g += 256) {
+  for (int gl = tid; gl < ncol / cg; gl += 256) {
     double a = 0.0, b = 0.0;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += chs[c].x; b += chs[c].y; }
-    p.gn_partial[(long long)blockIdx.x * p.gn_groups + g] = make_double2(a, b);
+    for (int c = gl * cg; c < (gl + 1) * cg; ++c) { a += chs[c].x; b += chs[c].y; }
+    p.gn_partial[(long long)blockIdx.x * p.gn_groups + cbeg / cg + gl] = make_double2(a, b);
   }
 }
 
@@ -423,6 +606,60 @@ static int launch(const Params& p, int batch, cudaStream_t st) {
   gemm_tf32x3_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(p);
   GR_CHECK_LAUNCH("gemm_tf32x3_kernel");
   return GR_OK;
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// > 0: the TMA path cannot serve this call (caller falls back to the ld.global producers)
+template <int BN>
+static int launch_tma(const Params& p, int zdim, cudaStream_t st) {
+  using C = CfgTma<BN>;
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return 1;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.lda * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_tma_kernel<BN>), C::kSmemBytes));
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, zdim);
+  gemm_tf32x3_tma_kernel<BN><<<grid, kThreadsTma, C::kSmemBytes, st>>>(tm, p);
+  GR_CHECK_LAUNCH("gemm_tf32x3_tma_kernel");
+  return GR_OK;
+}
+
+static bool use_tma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_GEMM_TMA"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// one launch of the tile kernel: TMA-fed when B is pre-packed, ld.global producers otherwise
+static int launch_any(int bn, const Params& p, int zdim, cudaStream_t st) {
+  if (p.B_packed && use_tma() && p.K >= 2 * BK) {
+    const int rc = bn == 256 ? launch_tma<256>(p, zdim, st) : (bn == 128 ? launch_tma<128>(p, zdim, st) : launch_tma<64>(p, zdim, st));
+    if (rc <= 0) return rc;
+  }
+  return bn == 256 ? launch<256>(p, zdim, st) : (bn == 128 ? launch<128>(p, zdim, st) : launch<64>(p, zdim, st));
 }
 
 }  // namespace tc
@@ -526,17 +763,22 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     tc::Params q = p;
     q.C = partial; q.ldc = N; q.sC = (long long)M * N; q.bias = nullptr; q.row_div = nullptr; q.residual = nullptr;
     q.alpha = 1.f; q.act = 0; q.k_split = slice;
-    int rc = bn == 256 ? tc::launch<256>(q, splits, st) : (bn == 128 ? tc::launch<128>(q, splits, st) : tc::launch<64>(q, splits, st));
+    int rc = tc::launch_any(bn, q, splits, st);
     if (rc == GR_OK) {
       const int nblk = (M + tc::kRedRows - 1) / tc::kRedRows;
       if (gn_ok && (size_t)nblk <= gn->capacity_blocks) {
         p.gn_partial = gn->partial; p.gn_groups = gn->groups;
-        const int c4n = N / 4, lanes = c4n < 256 ? c4n : 256, R = 256 / lanes;
-        const size_t smem = ((size_t)N + (R > 1 ? (size_t)R * N : 0)) * sizeof(double2);
+        // column chunks of at most 256 (a multiple of the group width): small-M products still fill the machine
+        const int cgw = N / gn->groups;
+        int col_chunk = N;
+        if (N > 256 && 256 % cgw == 0) col_chunk = 256;
+        const int c4n = col_chunk / 4, lanes = c4n < 256 ? c4n : 256, R = 256 / lanes;
+        const size_t smem = ((size_t)col_chunk + (R > 1 ? (size_t)R * col_chunk : 0)) * sizeof(double2);
         if (smem > 48 * 1024) {
           if (ensure_smem_attr(reinterpret_cast<const void*>(tc::splitk_reduce_gn_kernel), (int)smem) != cudaSuccess) return GR_ERR_CUDA;
         }
-        tc::splitk_reduce_gn_kernel<<<nblk, 256, smem, st>>>(partial, splits, p);
+        dim3 rgrid(nblk, (N + col_chunk - 1) / col_chunk);
+        tc::splitk_reduce_gn_kernel<<<rgrid, 256, smem, st>>>(partial, splits, p, col_chunk);
         gn->nblk = nblk;
       } else {
         const long long total = (long long)M * (N / 4);
@@ -551,9 +793,7 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     p.gn_partial = gn->partial; p.gn_groups = gn->groups;
     gn->nblk = (M + 127) / 128;
   }
-  if (N > 128 && use_bn256()) return tc::launch<256>(p, batch, st);
-  if (N > 64) return tc::launch<128>(p, batch, st);
-  return tc::launch<64>(p, batch, st);
+  return tc::launch_any(bn, p, batch, st);
 }
 
 }  // namespace gr

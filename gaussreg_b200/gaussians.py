@@ -157,12 +157,28 @@ def column_order_stats(cloud, cols, ranks):
     return out.cpu().numpy()
 
 
-def read_cloud_by_opacity(cloud, point_limit=None, opacity_min=0.7, crop_percent=(5, 95)):
+def farthest_point_sample(points, k, start_idx=0):
+    """Exact farthest-point sampling on the device: (n,3) f32 points -> (k,) int64 indices in selection order, first pick
+    `start_idx` (csrc/fps.cu).  Stands in for `fpsample.bucket_fps_kdline_sampling(points, k, h=9)` (demo.py:46), which is
+    an accelerated exact FPS with a random start; third party, parity unpinned."""
+    L = _lib.lib()
+    points = points.to(torch.float32).contiguous()
+    if not points.is_cuda:
+        points = points.to(_device())
+    n = points.shape[0]
+    out = torch.empty((k,), dtype=torch.int64, device=points.device)
+    ws = _workspace(L.gr_farthest_point_sample_workspace_size(n), points.device)
+    st = L.gr_farthest_point_sample(points.data_ptr(), n, int(k), int(start_idx), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "farthest_point_sample")
+    return out
+
+
+def read_cloud_by_opacity(cloud, point_limit=None, opacity_min=0.7, crop_percent=(5, 95), fps_start_idx=0):
     """demo.py:30-75 `_read_ply_by_opacity` for a cloud already in memory.
 
-    Returns device tensors ``(points (M,3) f32, point_features (M,4) f32, index (M,) i64)``.  `point_limit`: the
-    reference subsamples with the third-party `fpsample` when more than `point_limit` rows survive
-    (demo.py:45-48); that sampler is not part of this library, so such inputs raise."""
+    Returns device tensors ``(points (M,3) f32, point_features (M,4) f32, index (M,) i64)``.  When more than
+    `point_limit` rows survive the filter the reference subsamples them with `fpsample` (demo.py:45-48, random start);
+    here that is exact farthest-point sampling on the device started at survivor `fps_start_idx`."""
     import ctypes
     L = _lib.lib()
     cloud = _as_device_cloud(cloud)
@@ -192,13 +208,14 @@ def read_cloud_by_opacity(cloud, point_limit=None, opacity_min=0.7, crop_percent
                               _stream())
     _lib.check(st, "gaussian_select")
     m = int(count.item())
-    if point_limit is not None and m > point_limit:
-        raise NotImplementedError(
-            f"{m} Gaussians survive the filter but point_limit={point_limit}: the reference subsamples with the "
-            "third-party fpsample (demo.py:45-48), which this library does not reimplement")
     if m == 0:
         raise RuntimeError("no Gaussian survives the opacity / percentile filter")
     index = index[:m]
+    if point_limit is not None and m > point_limit:
+        # demo.py:44-47: farthest-point subsample of the survivors, kept in selection order
+        cand = cloud[:, 0:3].index_select(0, index).contiguous()
+        index = index[farthest_point_sample(cand, point_limit, start_idx=fps_start_idx)]
+        m = point_limit
     # --- points, their float32 mean (ordered sum), bounding box
     points = torch.empty((m, 3), dtype=torch.float32, device=dev)
     stats_dev = torch.empty((9,), dtype=torch.float32, device=dev)

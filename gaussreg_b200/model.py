@@ -3,8 +3,11 @@
 
 Differences from the reference, by design:
   * forward-only (the `if self.training` branches of model.py:74,111,165 are out of scope);
-  * `estimated_transform` is the deterministic LocalGlobalRegistration result; the reference then
-    overwrites it with Open3D RANSAC (model.py:209-215: third-party, randomised, CPU) -- not reproduced;
+  * `estimated_transform` is the deterministic LocalGlobalRegistration result by default (the parity target).  The
+    reference then overwrites it with Open3D's similarity RANSAC (model.py:209-215: third-party, randomised, CPU);
+    `model.ransac = True` (or `create_model(cfg, ransac=True)`) applies the device restatement of that step
+    (csrc/ransac.cu: seeded, statistical parity only) and returns it as `estimated_transform`, keeping the LGR
+    result under `lgr_transform`;
   * the random init below consumes the torch / numpy RNG streams exactly like the reference, so
     `torch.manual_seed(s); np.random.seed(s); create_model(cfg)` yields the reference's weights
     (checked against tests/golden/weights_checksum.npz).
@@ -18,8 +21,11 @@ from .modules import (KPConvFPN, GeometricTransformer, SuperPointMatching, Local
 
 
 class GeoTransformer(nn.Module):
-    def __init__(self, cfg):
+    def __init__(self, cfg, ransac=False, ransac_seed=0):
         super().__init__()
+        # N3: similarity RANSAC after LGR (model.py:209-215: ransac_n 5, 10 000 iterations, threshold 0.05 in eval)
+        self.ransac, self.ransac_seed = bool(ransac), int(ransac_seed)
+        self.ransac_n, self.ransac_iterations, self.ransac_distance = 5, 10000, 0.05
         self.num_points_in_patch = cfg.model.num_points_in_patch
         self.matching_radius = cfg.model.ground_truth_matching_radius
         b = cfg.backbone
@@ -110,10 +116,20 @@ class GeoTransformer(nn.Module):
         out["matching_scores"] = matching_scores
 
         # 9. local-to-global registration (model.py:196-207); the dustbin row/col is skipped inside the kernel
+        if self.ransac:
+            # the correspondence buffers stay padded on the device: the RANSAC kernels read the count there (no sync)
+            ref_pad, src_pad, sc_pad, num, T = self.fine_matching.forward_device(ref_knn_points, src_knn_points, ref_knn_masks,
+                                                                                 src_knn_masks, matching_scores)
+            T_sim, info = ops.similarity_ransac(ref_pad, src_pad, num, self.ransac_iterations, self.ransac_n, self.ransac_distance,
+                                                seed=self.ransac_seed, fallback=T)
+            c = int(num.item())  # the reference returns (C,3) tensors: data-dependent shape
+            out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_pad[:c], src_pad[:c], sc_pad[:c]
+            out["lgr_transform"], out["estimated_transform"], out["ransac_info"] = T, T_sim, info
+            return out
         ref_corr, src_corr, corr_scores, T = self.fine_matching(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks,
                                                                 matching_scores, node_corr_scores)
         out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_corr, src_corr, corr_scores
-        out["estimated_transform"] = T
+        out["estimated_transform"] = out["lgr_transform"] = T
         return out
 
 
@@ -122,5 +138,5 @@ def ops_gather_index(table, rows):
     return table.index_select(0, rows)
 
 
-def create_model(config):
-    return GeoTransformer(config)
+def create_model(config, ransac=False, ransac_seed=0):
+    return GeoTransformer(config, ransac=ransac, ransac_seed=ransac_seed)

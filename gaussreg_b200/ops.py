@@ -535,6 +535,25 @@ def local_global_registration(matching_scores, ref_knn_points, src_knn_points, r
     return ref_corr, src_corr, scores, num, T
 
 
+def similarity_ransac(ref_corr, src_corr, num_corr=None, num_hypotheses=10000, sample_size=5, distance_threshold=0.05, seed=0,
+                      refit=False, fallback=None):
+    """registration_with_ransac_from_correspondences (utils/open3d.py:169-198) on the device ->
+    (T (4,4) similarity transform, info int32[2] = {inliers, hypothesis index}).  `num_corr`: device int32 count of valid
+    rows (as LocalGlobalRegistration.forward_device leaves it) or None when every row is valid."""
+    ref_corr, src_corr = _req(ref_corr), _req(src_corr)
+    dev = ref_corr.device
+    T = torch.empty((4, 4), dtype=_F32, device=dev)
+    info = torch.empty((2,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.gr_similarity_ransac_workspace_size(num_hypotheses), dev)
+    st = L.gr_similarity_ransac(ref_corr.data_ptr(), src_corr.data_ptr(), _ptr(num_corr), ref_corr.shape[0], int(num_hypotheses),
+                                int(sample_size), float(distance_threshold), int(seed) & ((1 << 64) - 1), int(bool(refit)),
+                                _ptr(_req(fallback)) if fallback is not None else None, T.data_ptr(), info.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(st, "similarity_ransac")
+    return T, info
+
+
 def weighted_procrustes(src_points, ref_points, weights, eps=1e-5):
     """procrustes.py:6-82 with return_transform=True."""
     squeeze = src_points.dim() == 2

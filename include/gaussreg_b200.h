@@ -211,6 +211,23 @@ size_t gr_kpconv_fpn_workspace_size(const gr_fpn_weights* h_w, const gr_pyramid*
 int gr_kpconv_fpn(const gr_fpn_weights* h_w, const gr_pyramid* h_pyr, const float* feats, float* out_l2, float* out_l3,
                   float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream);
 
+/* N1  farthest-point subsampling to `point_limit` (demo.py:44-47; restates exact FPS, the result the third-party
+ * fpsample.bucket_fps_kdline_sampling accelerates).  points (n,3) -> out_idx (k) i64 in selection order. */
+size_t gr_farthest_point_sample_workspace_size(int64_t n_points);
+int gr_farthest_point_sample(const float* points, int64_t n_points, int k, int64_t start_idx, int64_t* out_idx, void* ws,
+                             size_t ws_bytes, void* stream);
+
+/* N3  similarity-transform RANSAC over the LGR correspondences (model.py:209-215, utils/open3d.py:169-198; restates the
+ * published algorithm of open3d==0.11.2 registration_ransac_based_on_correspondence with
+ * TransformationEstimationPointToPoint(with_scaling=True): third party, randomised -> statistical parity only).
+ * ref_corr / src_corr (capacity,3); d_num_corr: DEVICE int32 count of valid rows (NULL = capacity); fallback: device (4,4)
+ * returned when no hypothesis has an inlier (NULL = identity); T_out (4,4) = [c R | t]; info[2] (may be NULL) = {inliers of
+ * the best hypothesis, its index}.  Deterministic for a given seed (counter-based sampler). */
+size_t gr_similarity_ransac_workspace_size(int num_hypotheses);
+int gr_similarity_ransac(const float* ref_corr, const float* src_corr, const int32_t* d_num_corr, int capacity,
+                         int num_hypotheses, int sample_size, float distance_threshold, uint64_t seed, int refit,
+                         const float* fallback, float* T_out, int32_t* info, void* ws, size_t ws_bytes, void* stream);
+
 /* P1  point-to-node partition (modules/ops/pointcloud_partition.py:61-111). */
 size_t gr_point_to_node_workspace_size(int64_t n_points, int64_t n_nodes);
 int gr_point_to_node_partition(const float* points, int N, const float* nodes, int M, int point_limit,

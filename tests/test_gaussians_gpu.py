@@ -88,14 +88,55 @@ def test_full_size_cloud_vs_oracle():
 
 def test_point_limit_and_edge_cases():
     cloud = make_test_cloud(5, 3000)
-    with pytest.raises(NotImplementedError):
-        G.read_cloud_by_opacity(cloud, 10)       # would need the third-party FPS
     with pytest.raises(RuntimeError):
         G.read_cloud_by_opacity(cloud[:, :10])   # not a 59-attribute cloud
     dead = cloud.copy()
     dead[:, 51] = -5.0                            # nothing passes opacity > 0.7
     with pytest.raises(RuntimeError):
         G.read_cloud_by_opacity(dead)
+
+
+def _fps_numpy(points, k, start):
+    """Exact farthest-point sampling, float32 squared distances (dx*dx + dy*dy + dz*dz), ties to the lowest index."""
+    pts = points.astype(np.float32)
+    sel = [start]
+    d = None
+    for _ in range(k - 1):
+        diff = pts - pts[sel[-1]]
+        cur = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+        d = cur if d is None else np.minimum(d, cur)
+        sel.append(int(np.argmax(d)))
+    return np.array(sel, np.int64)
+
+
+@pytest.mark.parametrize("n,k,start", [(5000, 700, 0), (100000, 300, 17), (257, 257, 5), (1, 1, 0)])
+def test_farthest_point_sample_exact(n, k, start):
+    rng = np.random.default_rng(n + k)
+    pts = rng.normal(size=(n, 3)).astype(np.float32)
+    pts[n // 3] = pts[0]  # duplicates: ties resolved to the lowest index
+    got = G.farthest_point_sample(torch.from_numpy(pts), k, start_idx=start).cpu().numpy()
+    assert np.array_equal(got, _fps_numpy(pts, k, start))
+    assert len(set(got.tolist())) == min(k, len(np.unique(pts, axis=0))) or k > len(np.unique(pts, axis=0))
+
+
+def test_point_limit_subsamples_like_the_reference_demo():
+    """demo.py:44-47: more survivors than point_limit -> farthest-point subsample of the survivors, selection order."""
+    cloud = make_test_cloud(5, 6000)
+    p_all, f_all, i_all = G.read_cloud_by_opacity(cloud, None)
+    m = i_all.numel()
+    limit = m // 3
+    p, f, i = G.read_cloud_by_opacity(cloud, limit)
+    assert p.shape == (limit, 3) and f.shape == (limit, 4) and i.shape == (limit,)
+    want = i_all.cpu().numpy()[_fps_numpy(p_all.cpu().numpy(), limit, 0)]
+    assert np.array_equal(i.cpu().numpy(), want)
+    pos = {int(v): j for j, v in enumerate(i_all.tolist())}
+    rows = [pos[int(v)] for v in i.tolist()]
+    # same Gaussians (opacity column); the colours differ because the SH view point follows the selected set's centroid
+    assert torch.equal(p.cpu(), p_all.cpu()[rows]) and torch.equal(f.cpu()[:, 0], f_all.cpu()[rows, 0])
+    # fills space: the subsample's nearest-neighbour spacing is far larger than the full set's
+    d_sub = torch.cdist(p[:500], p).topk(2, largest=False).values[:, 1].median()
+    d_all = torch.cdist(p_all[:500], p_all).topk(2, largest=False).values[:, 1].median()
+    assert d_sub > 1.3 * d_all
 
 
 def test_ply_file_to_registration_input(tmp_path):

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/r2c_pytest.log 2>&1
+tail -12 gpurun_out/r2c_pytest.log
+tools/gpu_ab.sh "$@"
