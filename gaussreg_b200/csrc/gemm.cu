@@ -372,14 +372,193 @@ __global__ void __launch_bounds__(128) gemm_mma_small_kernel(GemmParams p) {
     }
 }
 
-static bool mma_small_ok(const GemmParams& p, bool transb) {
+// ---- latency-optimised form for the superpoint-sized products (M of a few hundred rows) ---------------------------
+// Measured (profiles/r02a_launches_by_kernel.txt): the double-buffered 64x64 kernel above spends 22 us on a
+// 480 x 256 x 256 product -- 32 CTAs, each walking its 8 k-slabs one L2 round trip after the other.  These products
+// are pure latency, so here (a) tiles are 32 x 32 (120+ CTAs), (b) the FOUR WARPS SPLIT K: each warp fetches its own
+// quarter of the A and B panels with cp.async (two commit groups, no block barrier in the main loop), multiplies it
+// into a full 32 x 32 partial tile, and (c) the four partials are folded through shared memory in a fixed order before
+// the fused epilogue.  One exposed memory latency per CTA instead of K / 32.
+constexpr int kTinyKq = 64;   // K handled per warp and pass (K <= 256 in one pass; 66 KB of panels -> 3 CTAs per SM)
+
+__device__ __forceinline__ void sm_cp_async4(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+
+// A_VEC = false: A rows are not 16-byte addressable (odd pitch or K, e.g. the (N,N) attention probabilities with odd N):
+// its panel is fetched with 4-byte cp.async instead
+template <bool TRANSB, bool A_VEC>
+__global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq) {
+  extern __shared__ __align__(16) float tiny_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int PA = kq + 4;                     // A panel [32][kq + 4] (and the (N,K) B panel)
+  const int PBn = 40;                        // (K,N) B panel [kq][40]
+  const int a_elems = 32 * PA, b_elems = TRANSB ? 32 * PA : kq * PBn;
+  float* As = tiny_smem + warp * (a_elems + b_elems);
+  float* Bs = As + a_elems;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+  float* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  const int half = (kq / 2 + 7) & ~7;        // first commit group covers [0, half), the second [half, kq)
+  for (int kpass = 0; kpass < p.K; kpass += 4 * kq) {
+    const int kw = kpass + warp * kq;         // this warp's K range [kw, kw + kq)
+    if (kpass > 0) __syncwarp();
+    // ---- issue this warp's loads: two groups
+    for (int part = 0; part < 2; ++part) {
+      const int kb = part == 0 ? 0 : half, ke = part == 0 ? half : kq;
+      const int c4 = (ke - kb) >> 2;           // 16-byte chunks per row in this part
+      if (A_VEC) {
+        for (int e = lane; e < 32 * c4; e += 32) {
+          const int r = e / c4, c = e % c4;
+          const int gm = m0 + r, gk = kw + kb + 4 * c;
+          const bool ok = gm < p.M && gk < p.K;
+          sm_cp_async16(As + r * PA + kb + 4 * c, A + (ok ? (long long)gm * p.lda + gk : 0), ok ? 16 : 0);
+        }
+      } else {
+        const int c1 = ke - kb;
+        for (int e = lane; e < 32 * c1; e += 32) {
+          const int r = e / c1, c = e % c1;
+          const int gm = m0 + r, gk = kw + kb + c;
+          const bool ok = gm < p.M && gk < p.K;
+          sm_cp_async4(As + r * PA + kb + c, A + (ok ? (long long)gm * p.lda + gk : 0), ok ? 4 : 0);
+        }
+      }
+      if (TRANSB) {
+        for (int e = lane; e < 32 * c4; e += 32) {
+          const int r = e / c4, c = e % c4;
+          const int gn = n0 + r, gk = kw + kb + 4 * c;
+          const bool ok = gn < p.N && gk < p.K;
+          sm_cp_async16(Bs + r * PA + kb + 4 * c, B + (ok ? (long long)gn * p.ldb + gk : 0), ok ? 16 : 0);
+        }
+      } else {
+        for (int e = lane; e < (ke - kb) * 8; e += 32) {
+          const int r = kb + (e >> 3), c = e & 7;
+          const int gk = kw + r, gn = n0 + 4 * c;
+          const bool ok = gk < p.K && gn < p.N;
+          sm_cp_async16(Bs + r * PBn + 4 * c, B + (ok ? (long long)gk * p.ldb + gn : 0), ok ? 16 : 0);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- multiply: first half while the second is still in flight
+    for (int part = 0; part < 2; ++part) {
+      if (part == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const int kb = part == 0 ? 0 : half, ke = part == 0 ? half : kq;
+      for (int k8 = kb; k8 < ke; k8 += 8) {
+        if (kw + k8 >= p.K) break;             // zero-filled tail
+        unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float* ap = As + (16 * i + g) * PA + k8 + t;
+          const float a0 = ap[0], a1 = ap[8 * PA], a2 = ap[4], a3 = ap[8 * PA + 4];
+          ah[i][0] = __float_as_uint(a0); ah[i][1] = __float_as_uint(a1); ah[i][2] = __float_as_uint(a2); ah[i][3] = __float_as_uint(a3);
+          al[i][0] = sm_lo_bits(a0); al[i][1] = sm_lo_bits(a1); al[i][2] = sm_lo_bits(a2); al[i][3] = sm_lo_bits(a3);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float b0, b1;
+          if (TRANSB) { const float* bp = Bs + (8 * j + g) * PA + k8 + t; b0 = bp[0]; b1 = bp[4]; }
+          else { const float* bp = Bs + (k8 + t) * PBn + 8 * j + g; b0 = bp[0]; b1 = bp[4 * PBn]; }
+          bh[j][0] = __float_as_uint(b0); bh[j][1] = __float_as_uint(b1);
+          bl[j][0] = sm_lo_bits(b0); bl[j][1] = sm_lo_bits(b1);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], al[i][0], al[i][1], al[i][2], al[i][3], bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bl[j][0], bl[j][1]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm_mma_tf32(acc[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+      }
+    }
+  }
+  // ---- fold the four K-quarters (fixed order 0+1+2+3), then the epilogue on 8 outputs per thread
+  __syncthreads();
+  float* red = tiny_smem;  // [4][32][33]
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = 16 * i + g + 8 * (e >> 1), c = 8 * j + 2 * t + (e & 1);
+        red[(warp * 32 + r) * 33 + c] = acc[i][j][e];
+      }
+  __syncthreads();
+  const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = tid + i * 128, r = e >> 5, c = e & 31;
+    const int gm = m0 + r, gn = n0 + c;
+    if (gm >= p.M || gn >= p.N) continue;
+    float v = ((red[r * 33 + c] + red[(32 + r) * 33 + c]) + red[(64 + r) * 33 + c]) + red[(96 + r) * 33 + c];
+    v *= p.alpha;
+    if (p.row_div) v = v / p.row_div[gm];
+    if (p.bias) v += p.bias[gn];
+    if (R) v += R[(long long)gm * p.ldr + gn];
+    C[(long long)gm * p.ldc + gn] = apply_act(v, p.act);
+  }
+}
+
+static int launch_tiny(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
+  int kq = ((p.K + 3) / 4 + 7) & ~7;
+  if (kq > kTinyKq) kq = kTinyKq;
+  if (kq < 16) kq = 16;
+  const int PA = kq + 4;
+  const size_t per_warp = (size_t)32 * PA + (transb ? (size_t)32 * PA : (size_t)kq * 40);
+  size_t smem = 4 * per_warp * sizeof(float);
+  const size_t red = 4 * 32 * 33 * sizeof(float);
+  if (smem < red) smem = red;
+  dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
+  const bool a_vec = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && p.lda % 4 == 0 && p.sA % 4 == 0 && p.K % 4 == 0;
+#define GR_TINY(TB, AV)                                                                                                  \
+  do {                                                                                                                   \
+    if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_mma_tiny_kernel<TB, AV>), (int)smem)); \
+    gemm_mma_tiny_kernel<TB, AV><<<grid, 128, smem, st>>>(p, kq);                                                        \
+  } while (0)
+  if (transb) { if (a_vec) GR_TINY(true, true); else GR_TINY(true, false); }
+  else { if (a_vec) GR_TINY(false, true); else GR_TINY(false, false); }
+#undef GR_TINY
+  GR_CHECK_LAUNCH("gemm_mma_tiny_kernel");
+  return GR_OK;
+}
+
+static bool mma_knob() {
   static int knob = -1;
   if (knob < 0) { const char* e = getenv("GAUSSREG_GEMM_SMALL_MMA"); knob = e ? atoi(e) : 1; }
-  if (!knob) return false;
+  return knob != 0;
+}
+static bool mma_small_ok(const GemmParams& p, bool transb) {
+  if (!mma_knob()) return false;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(p.A) || !al16(p.B) || p.lda % 4 != 0 || p.ldb % 4 != 0 || p.sA % 4 != 0 || p.sB % 4 != 0 || p.K % 4 != 0) return false;
   if (!transb && p.N % 4 != 0) return false;
   return p.K >= 16;
+}
+// the tiny kernel fetches A element-wise when needed; B must be 16-byte addressable ((N,K): K % 4 == 0; (K,N): N % 4 == 0)
+static bool mma_tiny_ok(const GemmParams& p, bool transb) {
+  if (!mma_knob()) return false;
+  if ((reinterpret_cast<uintptr_t>(p.B) & 15) != 0 || p.ldb % 4 != 0 || p.sB % 4 != 0) return false;
+  if (transb ? (p.K % 4 != 0) : (p.N % 4 != 0)) return false;
+  return p.K >= 8;
 }
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -394,20 +573,27 @@ static int launch_sgemm(const GemmParams& p, int batch, bool transb, cudaStream_
 
 int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return GR_OK;
-  // pick the largest tile that still yields at least ~1.5 waves of CTAs on 148 SMs
+  if (gr_get_gemm_mode() == 1) {
+    static int tiny = -1;
+    if (tiny < 0) { const char* e = getenv("GAUSSREG_GEMM_TINY"); tiny = e ? atoi(e) : 1; }
+    const long long tiles32 = (long long)((p.M + 31) / 32) * ((p.N + 31) / 32) * batch;
+    // a few hundred rows: latency-optimised 32x32 tiles with K split over the warps
+    if (tiny && tiles32 <= 148 * 8 && mma_tiny_ok(p, transb)) return launch_tiny(p, batch, transb, st);
+    // everything else that is 16-byte addressable: 64x64 tiles on mma.sync (3xTF32), cp.async double buffering
+    if (mma_small_ok(p, transb)) {
+      dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, batch);
+      if (transb) gemm_mma_small_kernel<true><<<grid, 128, 0, st>>>(p);
+      else gemm_mma_small_kernel<false><<<grid, 128, 0, st>>>(p);
+      GR_CHECK_LAUNCH("gemm_mma_small_kernel");
+      return GR_OK;
+    }
+    if (tiny && mma_tiny_ok(p, transb) && tiles32 <= 148 * 64) return launch_tiny(p, batch, transb, st);
+  }
+  // fp32 FFMA kernels: SIMT mode, odd shapes; pick the largest tile that still yields ~1.5 waves of CTAs on 148 SMs
   const long long ctas128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * batch;
   const long long ctas64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * batch;
   if (ctas128 >= 222) return launch_sgemm<128, 128, 8, 8, 8>(p, batch, transb, st);
   if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
-  // superpoint-sized problems: 64x64 tiles on mma.sync (3xTF32), cp.async double buffering
-  if (gr_get_gemm_mode() == 1 && mma_small_ok(p, transb)) {
-    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, batch);
-    if (transb) gemm_mma_small_kernel<true><<<grid, 128, 0, st>>>(p);
-    else gemm_mma_small_kernel<false><<<grid, 128, 0, st>>>(p);
-    GR_CHECK_LAUNCH("gemm_mma_small_kernel");
-    return GR_OK;
-  }
-  // unaligned / odd shapes: FFMA kernel, small tiles, K split over four thread groups inside the CTA
   {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
     if (transb) sgemm_small_kernel<true><<<grid, 256, 0, st>>>(p);

@@ -350,8 +350,12 @@ struct CfgTma {
   static constexpr int kABytes = BM * BK * 4;
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kOpBytes = kABytes + 2 * kBBytes;              // a_lo | b_hi | b_lo
-  static constexpr int kOps = 2;                                       // operand-ring depth
-  static constexpr int kRaw = BN == 256 ? 4 : 8;                       // raw A ring depth (16 KB each)
+  // Ring depths.  ncu (profiles/r02c): the producers of a 15-k-block tile spend most of their time waiting for an
+  // operand slot, i.e. for the MMAs of k-block kb - kOps to retire -- the tensor core's issue-to-commit latency, not
+  // memory, paces narrow tiles.  BN = 64: two CTAs per SM (3 + 2 stages each, 112 KB) keep four k-blocks in flight
+  // per SM and overlap one CTA's epilogue with the other's main loop; BN = 128: 5 + 3 stages; BN = 256: 4 + 2.
+  static constexpr int kOps = BN == 128 ? 3 : 2;                       // operand-ring depth (a_lo | b_hi | b_lo)
+  static constexpr int kRaw = BN == 256 ? 4 : (BN == 128 ? 5 : 3);     // raw A ring depth (16 KB each)
   static constexpr int kSmemBytes = kRaw * kABytes + kOps * kOpBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 constexpr int kThreadsTma = kProducerThreads + 64;
@@ -363,7 +367,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreadsTma, 1) gemm_tf32x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p) {
+__global__ void __launch_bounds__(kThreadsTma, BN == 64 ? 2 : 1) gemm_tf32x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p) {
   using C = CfgTma<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -637,8 +641,12 @@ static int launch_tma(const Params& p, int zdim, cudaStream_t st) {
   const cuuint64_t gstride[1] = {(cuuint64_t)p.lda * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
   const cuuint32_t estr[2] = {1, 1};
+  static int promo = -1;
+  if (promo < 0) { const char* e = getenv("GAUSSREG_TMA_L2PROMO"); promo = e ? atoi(e) : 256; }
+  const CUtensorMapL2promotion l2p = promo >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                   : (promo >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 1;
   GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_tma_kernel<BN>), C::kSmemBytes));
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, zdim);
@@ -708,6 +716,9 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (!aligned || N < 32 || (long long)M * N * K < (1ll << 22)) return 1;
+  // superpoint-sized products without GroupNorm statistics (the transformer): a dozen 128-row tiles leave most SMs
+  // idle; the latency-optimised mma.sync kernels of gemm.cu (32x32 / 64x64 tiles) are faster there
+  if (!gn && M < 1536 && K <= 1024) return 1;
   static int kSlice = 0, kSched = 1;
   if (kSlice == 0) {
     const char* e = getenv("GAUSSREG_KSLICE");  // longest K chained into one TMEM accumulator (multiple of 32); default 768

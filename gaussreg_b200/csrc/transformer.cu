@@ -125,23 +125,23 @@ static bool mlp_fused() {
 }
 
 struct TfWs {
-  float *qkv, *U, *qb, *P, *hid, *att, *ffn, *y;
+  float *x, *qkv, *U, *qb, *P, *hid, *att, *ffn, *y;
 };
 
-static size_t carve_tf(void* ws, size_t ws_bytes, int N, int C, int H, TfWs* sets, int n_sets, bool* ok) {
+// N = rows of the larger cloud, Nt = N0 + N1 (row-wise buffers hold the stacked clouds)
+static size_t carve_tf(void* ws, size_t ws_bytes, int N, int Nt, int C, int H, TfWs* out, bool* ok) {
   Carver c(ws, ws_bytes);
-  for (int i = 0; i < n_sets; ++i) {
-    TfWs w;
-    w.qkv = c.take<float>((size_t)N * 3 * C);
-    w.U = c.take<float>((size_t)H * N * C);
-    w.qb = c.take<float>((size_t)H * N);
-    w.P = c.take<float>((size_t)H * N * N);
-    w.hid = c.take<float>((size_t)N * C);
-    w.att = c.take<float>((size_t)N * C);
-    w.ffn = c.take<float>((size_t)N * 2 * C);
-    w.y = c.take<float>((size_t)N * C);
-    if (sets) sets[i] = w;
-  }
+  TfWs w;
+  w.x = c.take<float>((size_t)Nt * C);
+  w.qkv = c.take<float>((size_t)Nt * 3 * C);
+  w.U = c.take<float>((size_t)H * N * C);
+  w.qb = c.take<float>((size_t)H * N);
+  w.P = c.take<float>((size_t)H * N * N);
+  w.hid = c.take<float>((size_t)Nt * C);
+  w.att = c.take<float>((size_t)Nt * C);
+  w.ffn = c.take<float>((size_t)Nt * 2 * C);
+  w.y = c.take<float>((size_t)Nt * C);
+  if (out) *out = w;
   *ok = c.ok;
   return c.off;
 }
@@ -156,17 +156,55 @@ static int linear(const float* x, int rows, int in, const float* W, const float*
   return gr_gemm(x, in, 0, W, in, 0, 1, y, out, 0, rows, out, in, 1, 1.f, b, nullptr, nullptr, 0, 0, act, st);
 }
 
-// x (N,C) attends mem (M,C) [emb (N,N,C) when self]; result overwrites x
-static int layer(const gr_layer_weights& L, float* x, int N, const float* mem, int M, const float* emb, int C, int H, TfWs& w,
-                 void* st) {
+// out-projection + LayerNorm + AttentionOutput on `rows` rows (rpe_transformer.py:101-103, output_layer.py:14-21):
+// x <- LN2(y + FFN(y)),  y = LN1(x + W_o hid + b_o)
+static int post_attention(const gr_layer_weights& L, float* x, const float* hid, int rows, int C, TfWs& w, void* st) {
+  // the residual x rides in the product's epilogue, LayerNorm then reads one operand
+  GR_TRY(gr_gemm(hid, C, 0, L.wo, C, 0, 1, w.att, C, 0, rows, C, C, 1, 1.f, L.bo, nullptr, x, C, 0, 0, st));
+  GR_TRY(gr_layer_norm_add(w.att, nullptr, rows, C, L.ln1_g, L.ln1_b, 1e-5f, w.y, st));
+  if (L.w1t && L.w2t && C == kMlpC && mlp_fused()) {
+    transformer_mlp_kernel<<<(rows + kMlpRows - 1) / kMlpRows, kMlpC, 0, static_cast<cudaStream_t>(st)>>>(
+        w.y, rows, L.w1t, L.b1, L.w2t, L.b2, L.ln2_g, L.ln2_b, 1e-5f, x);
+    GR_CHECK_LAUNCH("transformer_mlp_kernel");
+    return GR_OK;
+  }
+  GR_TRY(linear(w.y, rows, C, L.w1, L.b1, 2 * C, w.ffn, 1, st));
+  GR_TRY(gr_gemm(w.ffn, 2 * C, 0, L.w2, 2 * C, 0, 1, w.att, C, 0, rows, C, 2 * C, 1, 1.f, L.b2, nullptr, w.y, C, 0, 0, st));
+  GR_TRY(gr_layer_norm_add(w.att, nullptr, rows, C, L.ln2_g, L.ln2_b, 1e-5f, x, st));
+  return GR_OK;
+}
+
+// RPE self-attention of BOTH clouds (rows [0,N0) and [N0,N0+N1) of the stacked x): every row-wise product (q|k|v,
+// out-projection, FFN) and both LayerNorms run once on the N0+N1 stacked rows; only the N x N attention itself is per
+// cloud.
+static int self_layer(const gr_layer_weights& L, float* x, int N0, int N1, const float* emb0, const float* emb1, int C, int H,
+                      TfWs& w, void* st) {
+  const int dh = C / H, Nt = N0 + N1;
+  if (!(L.wqkv && L.bqkv)) return GR_ERR_BAD_ARG;
+  GR_TRY(linear(x, Nt, C, L.wqkv, L.bqkv, 3 * C, w.qkv, 0, st));
+  const int64_t ld = 3 * C;
+  for (int c = 0; c < 2; ++c) {
+    const int N = c == 0 ? N0 : N1, off = c == 0 ? 0 : N0;
+    const float* q = w.qkv + (size_t)off * ld;
+    const float *k = q + C, *v = q + 2 * C;
+    const float* emb = c == 0 ? emb0 : emb1;
+    // U[h] = q_h (N,dh) @ W_p[h*dh:(h+1)*dh, :] ; qb[h] = q_h @ b_p[h*dh:(h+1)*dh]   (see attention.cu)
+    GR_TRY(gr_gemm(q, ld, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0,
+                   st));
+    GR_TRY(gr_gemm(q, ld, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
+    GR_TRY(gr_rpe_attention_probs_ld(q, ld, k, ld, w.U, w.qb, emb, N, C, H, w.P, st));
+    GR_TRY(gr_gemm(w.P, N, (int64_t)N * N, v, ld, dh, 0, w.hid + (size_t)off * C, C, dh, N, dh, N, H, 1.f, nullptr, nullptr, nullptr, 0,
+                   0, 0, st));
+  }
+  return post_attention(L, x, w.hid, Nt, C, w, st);
+}
+
+// vanilla cross-attention: x (N rows) attends mem (M rows); result overwrites x
+static int cross_layer(const gr_layer_weights& L, float* x, int N, const float* mem, int M, int C, int H, TfWs& w, void* st) {
   const int dh = C / H;
   const float *q, *k, *v;
   int64_t ldq, ldk, ldv;
-  if (L.wqkv && L.bqkv && L.is_self) {  // x == mem: one product for q|k|v
-    GR_TRY(linear(x, N, C, L.wqkv, L.bqkv, 3 * C, w.qkv, 0, st));
-    q = w.qkv; k = w.qkv + C; v = w.qkv + 2 * C;
-    ldq = ldk = ldv = 3 * C;
-  } else if (L.wqkv && L.bqkv) {        // q from x, k|v from mem
+  if (L.wqkv && L.bqkv) {  // q from x, k|v from mem in one product
     float* kv = w.qkv + (size_t)N * C;
     GR_TRY(linear(x, N, C, L.wqkv, L.bqkv, C, w.qkv, 0, st));
     GR_TRY(linear(mem, M, C, L.wqkv + (size_t)C * C, L.bqkv + C, 2 * C, kv, 0, st));
@@ -181,65 +219,11 @@ static int layer(const gr_layer_weights& L, float* x, int N, const float* mem, i
     q = w.qkv; k = kb; v = vb;
     ldq = ldk = ldv = C;
   }
-  if (L.is_self) {
-    // U[h] = q_h (N,dh) @ W_p[h*dh:(h+1)*dh, :] ; qb[h] = q_h @ b_p[h*dh:(h+1)*dh]   (see attention.cu)
-    GR_TRY(gr_gemm(q, ldq, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0,
-                   0, 0, st));
-    GR_TRY(gr_gemm(q, ldq, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
-    GR_TRY(gr_rpe_attention_probs_ld(q, ldq, k, ldk, w.U, w.qb, emb, N, C, H, w.P, st));
-  } else {
-    GR_TRY(gr_gemm(q, ldq, dh, k, ldk, dh, 1, w.P, M, (int64_t)N * M, N, M, dh, H, 1.0f / sqrtf((float)dh), nullptr, nullptr,
-                   nullptr, 0, 0, 0, st));
-    GR_TRY(gr_softmax_rows(w.P, (int64_t)H * N, M, st));
-  }
-  // hidden[:, h*dh:(h+1)*dh] = P[h] @ v[:, h*dh:(h+1)*dh]
+  GR_TRY(gr_gemm(q, ldq, dh, k, ldk, dh, 1, w.P, M, (int64_t)N * M, N, M, dh, H, 1.0f / sqrtf((float)dh), nullptr, nullptr, nullptr, 0,
+                 0, 0, st));
+  GR_TRY(gr_softmax_rows(w.P, (int64_t)H * N, M, st));
   GR_TRY(gr_gemm(w.P, M, (int64_t)N * M, v, ldv, dh, 0, w.hid, C, dh, N, dh, M, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
-  GR_TRY(linear(w.hid, N, C, L.wo, L.bo, C, w.att, 0, st));
-  GR_TRY(gr_layer_norm_add(w.att, x, N, C, L.ln1_g, L.ln1_b, 1e-5f, w.y, st));
-  if (L.w1t && L.w2t && C == kMlpC && mlp_fused()) {
-    transformer_mlp_kernel<<<(N + kMlpRows - 1) / kMlpRows, kMlpC, 0, static_cast<cudaStream_t>(st)>>>(
-        w.y, N, L.w1t, L.b1, L.w2t, L.b2, L.ln2_g, L.ln2_b, 1e-5f, x);
-    GR_CHECK_LAUNCH("transformer_mlp_kernel");
-    return GR_OK;
-  }
-  GR_TRY(linear(w.y, N, C, L.w1, L.b1, 2 * C, w.ffn, 1, st));
-  GR_TRY(linear(w.ffn, N, 2 * C, L.w2, L.b2, C, w.att, 0, st));
-  GR_TRY(gr_layer_norm_add(w.y, w.att, N, C, L.ln2_g, L.ln2_b, 1e-5f, x, st));
-  return GR_OK;
-}
-
-// A helper stream per (device, caller stream): the two clouds of a 'self' layer are independent, and one
-// superpoint-sized kernel (a few dozen CTAs) leaves most of the 148 SMs idle, so they run side by side.
-struct SideStream {
-  int dev;
-  cudaStream_t main, side;
-  cudaEvent_t fork, join;
-};
-
-static SideStream* side_stream(cudaStream_t main) {
-  static std::mutex mu;
-  static std::vector<SideStream*> all;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lock(mu);
-  for (SideStream* s : all)
-    if (s->dev == dev && s->main == main) return s;
-  SideStream* s = new SideStream{dev, main, nullptr, nullptr, nullptr};
-  if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
-    set_last_error("transformer side stream", cudaGetLastError());
-    delete s;
-    return nullptr;
-  }
-  all.push_back(s);
-  return s;
-}
-
-static bool two_streams() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GAUSSREG_TF_STREAMS"); v = e ? atoi(e) : 2; }
-  return v >= 2;
+  return post_attention(L, x, w.hid, N, C, w, st);
 }
 
 }  // namespace gr
@@ -248,47 +232,38 @@ using namespace gr;
 
 extern "C" size_t gr_conditional_transformer_workspace_size(int N0, int N1, int C, int num_heads) {
   bool ok;
-  return carve_tf(nullptr, 0, N0 > N1 ? N0 : N1, C, num_heads, nullptr, 2, &ok);
+  return carve_tf(nullptr, 0, N0 > N1 ? N0 : N1, N0 + N1, C, num_heads, nullptr, &ok);
 }
 
 /* feats0 (N0,C) / feats1 (N1,C) are updated in place through all layers; "self" layers use emb0 (N0,N0,C) and
  * emb1 (N1,N1,C), "cross" layers run sequentially (feats0 attends feats1, then feats1 attends the UPDATED feats0).
- * The two clouds of a self layer are issued on two streams (joined again before the next cross layer and before
- * returning: from the caller's point of view all work is ordered on `stream`). */
+ * Internally the two clouds are stacked into one (N0+N1, C) matrix: the row-wise products and LayerNorms of a self
+ * layer then run once for both clouds. */
 extern "C" int gr_conditional_transformer(const gr_layer_weights* layers, int n_layers, float* feats0, float* feats1,
                                           const float* emb0, const float* emb1, int N0, int N1, int C, int num_heads,
                                           void* ws, size_t ws_bytes, void* stream) {
   if (!layers || n_layers <= 0 || !feats0 || !feats1 || N0 <= 0 || N1 <= 0 || C <= 0 || num_heads <= 0 || C % num_heads != 0)
     return GR_ERR_BAD_ARG;
   bool ok;
-  TfWs w[2];
-  carve_tf(ws, ws_bytes, N0 > N1 ? N0 : N1, C, num_heads, w, 2, &ok);
+  TfWs w;
+  carve_tf(ws, ws_bytes, N0 > N1 ? N0 : N1, N0 + N1, C, num_heads, &w, &ok);
   if (!ws || !ok) return GR_ERR_WORKSPACE;
-  cudaStream_t main = static_cast<cudaStream_t>(stream);
-  SideStream* ss = two_streams() ? side_stream(main) : nullptr;
-  if (two_streams() && !ss) return GR_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* x0 = w.x;
+  float* x1 = w.x + (size_t)N0 * C;
+  GR_CHECK_CUDA(cudaMemcpyAsync(x0, feats0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GR_CHECK_CUDA(cudaMemcpyAsync(x1, feats1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int i = 0; i < n_layers; ++i) {
     const gr_layer_weights& L = layers[i];
     if (L.is_self) {
       if (!emb0 || !emb1 || !L.wp || !L.bp) return GR_ERR_BAD_ARG;
-      if (ss) {
-        GR_CHECK_CUDA(cudaEventRecord(ss->fork, main));
-        GR_CHECK_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
-        const int rc0 = layer(L, feats0, N0, feats0, N0, emb0, C, num_heads, w[0], main);
-        const int rc1 = layer(L, feats1, N1, feats1, N1, emb1, C, num_heads, w[1], ss->side);
-        // always join, also on failure: the caller's stream must never run ahead of the helper
-        cudaEventRecord(ss->join, ss->side);
-        cudaStreamWaitEvent(main, ss->join, 0);
-        if (rc0 != GR_OK) return rc0;
-        if (rc1 != GR_OK) return rc1;
-      } else {
-        GR_TRY(layer(L, feats0, N0, feats0, N0, emb0, C, num_heads, w[0], stream));
-        GR_TRY(layer(L, feats1, N1, feats1, N1, emb1, C, num_heads, w[0], stream));
-      }
+      GR_TRY(self_layer(L, w.x, N0, N1, emb0, emb1, C, num_heads, w, stream));
     } else {
-      GR_TRY(layer(L, feats0, N0, feats1, N1, nullptr, C, num_heads, w[0], stream));
-      GR_TRY(layer(L, feats1, N1, feats0, N0, nullptr, C, num_heads, w[0], stream));
+      GR_TRY(cross_layer(L, x0, N0, x1, N1, C, num_heads, w, stream));
+      GR_TRY(cross_layer(L, x1, N1, x0, N0, C, num_heads, w, stream));
     }
   }
+  GR_CHECK_CUDA(cudaMemcpyAsync(feats0, x0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GR_CHECK_CUDA(cudaMemcpyAsync(feats1, x1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return GR_OK;
 }
