@@ -158,6 +158,23 @@ __device__ __forceinline__ void sinkhorn_lse_pass(const float* __restrict__ ps, 
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
       for (int r = 0; r < kSinkIlp; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+    if (!FIRST) {
+#pragma unroll
+      for (int r = 0; r < kSinkIlp; ++r) {
+        if (live[r] && !(sm[r] > 1e-30f && sm[r] < 1e30f)) {  // see sinkhorn_lse_pass128: redo with the true maximum
+          const int i = i0 + r * nwarp;
+          float m = -INFINITY;
+          for (int j = lane; j < K1; j += 32) m = fmaxf(m, ps[i * si + j * sj] + add[j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          float s2 = 0.f;
+          for (int j = lane; j < K1; j += 32) s2 += __expf(ps[i * si + j * sj] + add[j] - m);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          sm[r] = s2; shift[r] = m;
+        }
+      }
+    }
     if (lane == 0) {
 #pragma unroll
       for (int r = 0; r < kSinkIlp; ++r) {
@@ -237,6 +254,35 @@ __device__ __forceinline__ void sinkhorn_lse_pass128(const float* __restrict__ p
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
     for (int r = 0; r < 8; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+  if (!FIRST) {
+    // The shift is the previous iterate's log-sum-exp.  Should every term of a line flush to zero (or the sum leave the
+    // fp32 range) -- possible for trained weights with |scores| >> 10 -- redo that line with its true maximum.  All
+    // lanes hold identical totals, so the branch is warp-uniform; it never triggers on O(10) scores.
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (live[r] && !(sm[r] > 1e-30f && sm[r] < 1e30f)) {
+        const int i = ibase + 16 * r;
+        float m = lane == 0 ? ps[i * si + K * sj] + ad : -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m = fmaxf(m, ps[i * si + (lane + 32 * t) * sj] + a[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float arg = ps[i * si + (lane + 32 * t) * sj] + a[t] - m;
+          s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+        }
+        if (lane == 0) {
+          const float arg = ps[i * si + K * sj] + ad - m;
+          s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        sm[r] = s2; shift[r] = m;
+      }
+    }
+  }
   // lane r finishes line r (every lane holds all eight totals)
   float my_sum = sm[0], my_shift = shift[0];
   bool my_live = live[0];

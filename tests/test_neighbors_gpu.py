@@ -135,3 +135,86 @@ def test_reference_error_behaviour():
         ext.grid_subsampling(pts.float(), lens.int(), 0.1)  # CHECK_IS_LONG
     with pytest.raises(RuntimeError):
         ext.radius_neighbors(torch.zeros((3, 4)).t(), torch.zeros((4, 3)), lens, lens, 0.1)  # CHECK_CONTIGUOUS
+
+
+# ---------------------------------------------------------------------------------------------- property tests
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def _clouds(draw):
+    """A stacked batch of 1-4 clouds: ragged lengths, three geometries (blob / shell / lattice with exact duplicates and
+    points exactly on voxel boundaries), a random offset and scale."""
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    nb = draw(st.integers(1, 4))
+    lens = [draw(st.integers(1, 900)) for _ in range(nb)]
+    kind = draw(st.sampled_from(["blob", "shell", "lattice"]))
+    scale = draw(st.sampled_from([0.05, 0.4, 3.0]))
+    offset = draw(st.sampled_from([0.0, -7.5, 123.25]))
+    rng = np.random.default_rng(seed)
+    n = sum(lens)
+    if kind == "blob":
+        pts = rng.normal(scale=scale, size=(n, 3))
+    elif kind == "shell":
+        v = rng.normal(size=(n, 3))
+        pts = scale * v / np.linalg.norm(v, axis=1, keepdims=True) + rng.normal(scale=0.01 * scale, size=(n, 3))
+    else:
+        pts = rng.integers(-6, 7, size=(n, 3)) * (scale / 4.0)  # many exact duplicates / boundary points
+    return (pts + offset).astype(np.float32), np.array(lens, np.int64), scale
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(_clouds(), st.sampled_from([0.25, 0.5, 1.0, 2.5]))
+def test_property_grid_subsample_bit_exact(cloud, rel_voxel):
+    """G1 for arbitrary ragged batches: values AND emission order bit-identical to the reference's C++ (oracle/_ref),
+    idempotence of the per-cloud lengths, and every output point inside the bounding box of its cloud."""
+    pts, lens, scale = cloud
+    voxel = float(np.float32(rel_voxel * scale / 4.0))
+    impl = on.ref() if on.have_ref() else on.port()
+    want, wl = impl.grid_subsampling(pts, lens, voxel)
+    got, gl = _gpu_grid(pts, lens, voxel)
+    assert np.array_equal(wl, gl)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert int(gl.sum()) == got.shape[0] and np.all(gl >= 1) and np.all(gl <= lens)
+    o = 0
+    s = 0
+    for nb, ns in zip(lens, gl):
+        c, sub = pts[o:o + nb], got[s:s + ns]
+        assert np.all(sub >= c.min(0) - 1e-6 * (1 + np.abs(c.min(0)))) and np.all(sub <= c.max(0) + 1e-6 * (1 + np.abs(c.max(0))))
+        o += nb
+        s += ns
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(_clouds(), st.sampled_from([0.1, 0.3, 0.8, 2.0]), st.booleans())
+def test_property_radius_neighbors_bit_exact(cloud, rel_radius, cross):
+    """G2 for arbitrary ragged batches: indices bit-identical to the reference after canonicalising equal-distance ties,
+    plus the invariants of radius_neighbors_cpu.cpp:3-91 -- ascending distance, strict `d < r^2` in float32, neighbours
+    only from the query's own batch element, padding = number of support points."""
+    pts, lens, scale = cloud
+    radius = float(np.float32(rel_radius * scale / 2.0))
+    impl = on.ref() if on.have_ref() else on.port()
+    if cross:  # queries = a jittered subset of the support clouds (same batch layout)
+        rng = np.random.default_rng(int(lens.sum()))
+        keep = [max(1, int(n) // 3) for n in lens]
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        q = np.concatenate([pts[s:s + k] for s, k in zip(starts, keep)]) + rng.normal(scale=0.05 * scale, size=(sum(keep), 3)).astype(np.float32)
+        q, ql = q.astype(np.float32), np.array(keep, np.int64)
+    else:
+        q, ql = pts, lens
+    want = impl.radius_neighbors(q, pts, ql, lens, radius)
+    got = _gpu_radius(q, pts, ql, lens, radius)
+    assert want.shape == got.shape
+    n_s = pts.shape[0]
+    wc, _ = on.canonicalize_ties(want, q, pts, n_s)
+    assert np.array_equal(wc, got)
+    if got.shape[1]:
+        valid = got < n_s
+        d = ((q[:, None, :] - pts[np.minimum(got, n_s - 1)]) ** 2)
+        d2 = (d[..., 0] + d[..., 1]) + d[..., 2]
+        assert np.all(d2[valid] < np.float32(radius) * np.float32(radius))
+        dd = np.where(valid, d2, np.inf)
+        assert np.all(dd[:, 1:] >= dd[:, :-1])                       # ascending, padding last
+        qb = np.repeat(np.arange(len(ql)), ql)
+        sb = np.repeat(np.arange(len(lens)), lens)
+        assert np.all(sb[np.minimum(got, n_s - 1)][valid] == np.broadcast_to(qb[:, None], got.shape)[valid])

@@ -156,18 +156,38 @@ def test_layer_norm_maxpool_upsample_gather():
 
 # ---------------------------------------------------------------------------------------------- P1
 def test_point_to_node_partition_vs_oracle():
-    d = make_pair_inputs(3, 6000)
+    """P1: exact agreement is expected; the only admissible differences are TIES of the reference's own arithmetic
+    (pairwise_distance.py:19-30 evaluates x^2 - 2xy + y^2 in fp32, whose rounding noise of ~|x|^2 * 2^-23 can reorder
+    two candidates that are equidistant to that precision).  Every mismatch is checked to be such a tie, and the exact
+    rates are written to gpurun_out/p1_parity.txt."""
     data = oracle_data(dict(seed=3, n_points=6000))
     n_c, n_f = int(data["lengths"][-1][0]), int(data["lengths"][1][0])
     nodes, pts = data["points"][-1][:n_c], data["points"][1][:n_f]
     p2n, nm, ki, km = onet.point_to_node_partition(pts, nodes, 128)
     g_p2n, g_nm, g_ki, g_km = [t.cpu() for t in ops.point_to_node_partition(pts.cuda(), nodes.cuda(), 128)]
-    agree = (g_p2n == p2n).float().mean().item()
-    assert agree > 0.999, agree
+    d2 = torch.cdist(pts.double(), nodes.double()) ** 2                       # (n_f, n_c) exact to fp64
+    tie_eps = 4.0 * float((pts.double() ** 2).sum(1).max()) * 2.0 ** -23      # rounding noise of the fp32 expansion
+    bad = torch.nonzero(g_p2n != p2n).flatten()
+    for i in bad.tolist():
+        assert abs(float(d2[i, g_p2n[i]] - d2[i, p2n[i]])) <= tie_eps, (i, float(d2[i, g_p2n[i]]), float(d2[i, p2n[i]]))
     assert torch.equal(g_nm, nm)
-    rows_ok = (g_ki == ki).all(1).float().mean().item()
-    assert rows_ok > 0.99, rows_ok
+    rows_bad = torch.nonzero(~(g_ki == ki).all(1)).flatten()
+    for r in rows_bad.tolist():
+        # same multiset of points up to re-assigned tie points; order differs only between equidistant points
+        a, b = g_ki[r], ki[r]
+        diff = torch.nonzero(a != b).flatten()
+        for c in diff.tolist():
+            ia, ib = int(a[c]), int(b[c])
+            da = float(d2[ia, r]) if ia < n_f else float("inf")
+            db = float(d2[ib, r]) if ib < n_f else float("inf")
+            tied_assignment = (ia in bad.tolist()) or (ib in bad.tolist())
+            assert tied_assignment or abs(da - db) <= tie_eps, (r, c, ia, ib, da, db)
     assert torch.equal(g_km, g_ki != n_f)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/p1_parity.txt", "w") as f:
+        f.write(f"point_to_node: {n_f - bad.numel()}/{n_f} identical assignments ({bad.numel()} ties of the reference's fp32 distance); "
+                f"knn rows: {n_c - rows_bad.numel()}/{n_c} identical\n")
+    assert bad.numel() <= max(2, n_f // 2000) and rows_bad.numel() <= max(4, n_c // 50), (bad.numel(), rows_bad.numel())
     # small limit: truncation keeps the nearest ones
     _, _, ki8, km8 = onet.point_to_node_partition(pts, nodes, 8)
     _, _, g_ki8, g_km8 = [t.cpu() for t in ops.point_to_node_partition(pts.cuda(), nodes.cuda(), 8)]
@@ -263,7 +283,34 @@ def test_sinkhorn_vs_oracle():
     got = ops.sinkhorn(scores.cuda(), rm.cuda(), sm.cuda(), alpha.cuda(), 100).cpu()
     valid = want > -1e11
     assert torch.equal(valid, got > -1e11)
-    assert float((got[valid] - want[valid]).abs().max()) < 2e-3
+    err_log, err_exp = float((got[valid] - want[valid]).abs().max()), rel_l2(got[valid].exp(), want[valid].exp())
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/sinkhorn_parity.txt", "w") as f:
+        f.write(f"max |log P - log P_oracle| = {err_log:.3e}, rel-L2 of P = {err_exp:.3e}\n")
+    # rel-L2 <= 1e-5 on the transport plan; the log-domain values agree to 1e-4 absolute
+    assert err_exp < 1e-5 and err_log < 1e-4, (err_log, err_exp)
+
+
+def test_sinkhorn_large_magnitude_scores_stay_finite():
+    """Scores of magnitude ~100 (trained weights can produce them): the log-sum-exp shift taken from the previous
+    iterate must not underflow a whole line (guarded: the line is redone with its true maximum)."""
+    g = torch.Generator().manual_seed(3)
+    P, K = 8, 128
+    scores = torch.randn(P, K, K, generator=g) * 60.0
+    scores[0] = 100.0 * torch.eye(K) - 50.0          # one dominant entry per line, everything else far below
+    scores[1, :, :] = -100.0
+    scores[1, torch.arange(K), torch.arange(K).flip(0)] = 100.0
+    rm = torch.ones(P, K, dtype=torch.bool)
+    sm = torch.ones(P, K, dtype=torch.bool)
+    rm[2, 100:] = False
+    sm[3, :5] = False
+    alpha = torch.tensor(1.0)
+    want = onet.log_optimal_transport(scores, rm, sm, alpha, 100)
+    got = ops.sinkhorn(scores.cuda(), rm.cuda(), sm.cuda(), alpha.cuda(), 100).cpu()
+    valid = want > -1e11
+    assert torch.equal(valid, got > -1e11)
+    assert bool(torch.isfinite(got[valid]).all())
+    assert float((got[valid] - want[valid]).abs().max()) < 5e-3  # |values| up to ~300: 1e-5 relative
     assert rel_l2(got[valid].exp(), want[valid].exp()) < 1e-4
 
 
