@@ -443,6 +443,141 @@ def config4_sharded(model, rank, world, dev, pairs_per_rank=128, distinct=8):
             "finite": bool(torch.isfinite(T).all()), "shape": list(T.shape)}
 
 
+def _events_ms(fn, reps, flush=None):
+    """Median CUDA-event time of fn() on the current stream (optional L2 flush before every repetition)."""
+    ts = []
+    for i in range(reps + 2):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts = sorted(ts[2:])
+    return ts[len(ts) // 2]
+
+
+def kernel_class_microbench(model, resident_pair, dev, peaks):
+    """Live per-class numbers on the REAL layer shapes of the bench pair (CUDA events, 256 MB L2 flush before every call):
+    K1 (KPConv = aggregation + contraction) with SURVEY.md section 8(d)'s compulsory-byte formula
+    8MH + 12(M+Ns) + 4 Ns C + 60 C C' + 4 M C', GroupNorm (2*4*N*C), and the backbone's tensor-core products."""
+    from gaussreg_b200 import ops
+    from gaussreg_b200.config import make_cfg, NEIGHBOR_LIMITS
+    from gaussreg_b200.data import precompute_data_stack_mode
+    cfg = make_cfg()
+    pts, feats, lens = resident_pair
+    d = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius,
+                                   NEIGHBOR_LIMITS, lazy=False)
+    P, NB, SUB = d["points"], d["neighbors"], d["subsampling"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    bb = model.backbone
+    layers = [(bb.encoder1_2, P[0], P[0], NB[0]), (bb.encoder2_1, P[1], P[0], SUB[0]), (bb.encoder2_2, P[1], P[1], NB[1]),
+              (bb.encoder2_3, P[1], P[1], NB[1]), (bb.encoder3_1, P[2], P[1], SUB[1]), (bb.encoder3_2, P[2], P[2], NB[2]),
+              (bb.encoder3_3, P[2], P[2], NB[2]), (bb.encoder4_1, P[3], P[2], SUB[2]), (bb.encoder4_2, P[3], P[3], NB[3]),
+              (bb.encoder4_3, P[3], P[3], NB[3]), (bb.encoder5_1, P[4], P[3], SUB[3]), (bb.encoder5_2, P[4], P[4], NB[4]),
+              (bb.encoder5_3, P[4], P[4], NB[4])]
+    k1_ms = k1_bytes = k1_flop = agg_ms = 0.0
+    for blk, q, sp, idx in layers:
+        conv = blk.KPConv
+        C, Co = conv.in_channels, conv.out_channels
+        M, H = idx.shape
+        Ns = sp.shape[0]
+        x = torch.randn(Ns, C, generator=g).to(dev)
+        k1_ms += _events_ms(lambda: ops.kpconv(x, q, sp, idx, conv.weights, conv.bias, conv.kernel_points, conv.sigma), 3, flush)
+        agg_ms += _events_ms(lambda: ops.kpconv_aggregate(x, q, sp, idx, conv.kernel_points, conv.sigma), 3, flush)
+        k1_bytes += 8.0 * M * H + 12.0 * (M + Ns) + 4.0 * Ns * C + 60.0 * C * Co + 4.0 * M * Co
+        k1_flop += 2.0 * M * H * 15 * C + 2.0 * M * 15 * C * Co
+    out = {"K1_kpconv": {"achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_pair": k1_bytes,
+                         "ms_per_pair": k1_ms, "aggregation_ms_per_pair": agg_ms, "layers": len(layers),
+                         "gflop_per_pair": k1_flop / 1e9,
+                         "note": "13 residual-block KPConv layers (aggregation on mma.sync + contraction on tcgen05), SURVEY 8(d) "
+                                 "compulsory bytes; the (M,15C) operand still crosses L2/HBM between the two kernels"}}
+    # GroupNorm on the largest activation of every stage
+    gn_ms = gn_bytes = 0.0
+    for n, C in ((P[0].shape[0], 128), (P[1].shape[0], 256), (P[2].shape[0], 512), (P[3].shape[0], 1024), (P[4].shape[0], 2048)):
+        x = torch.randn(n, C, generator=g).to(dev)
+        gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        gn_ms += _events_ms(lambda: ops.group_norm(x, 32, gam, bet, act="leaky_relu"), 3, flush)
+        gn_bytes += 2.0 * 4.0 * n * C
+    out["group_norm"] = {"achieved": gn_bytes / (gn_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": gn_ms,
+                         "note": "standalone op (statistics + apply) on the five stage outputs; inside the backbone the statistics "
+                                 "come from the producing GEMM's epilogue and only finalize + apply run"}
+    # the backbone's Linear / contraction shapes on the TMA-fed tcgen05 kernel
+    shapes = [(P[0].shape[0], 32, 480), (P[1].shape[0], 64, 960), (P[2].shape[0], 128, 1920), (P[3].shape[0], 256, 3840),
+              (P[1].shape[0], 256, 64), (P[1].shape[0], 64, 256), (P[2].shape[0], 512, 1536), (P[3].shape[0], 1024, 3072),
+              (P[1].shape[0], 256, 768)]
+    gm_ms = gm_flop = 0.0
+    for M, N, K in shapes:
+        A = torch.randn(M, K, generator=g).to(dev)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        o = torch.empty(M, N, device=dev)
+        gm_ms += _events_ms(lambda: ops.linear(A, W, out=o), 3, flush)
+        gm_flop += 2.0 * M * N * K
+    tf = gm_flop / (gm_ms * 1e-3) / 1e12
+    out["tcgen05_gemm_backbone_shapes"] = {"achieved": tf, "unit": "TFLOP/s fp32-equivalent", "peak": peaks["tf_sustained"],
+                                           "frac": tf / peaks["tf_sustained"], "tf32_mma_tflops": 3.0 * tf,
+                                           "frac_of_tf32_peak": 3.0 * tf / (peaks["tf_sustained"] / 2.0), "ms": gm_ms,
+                                           "shapes_MNK": [list(x) for x in shapes]}
+    return out
+
+
+def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microbench=True):
+    """`roofline` object of the JSON line.  Dominant kernel = the fused structure-embedding kernel (T1, the largest
+    single kernel of the step): FLOPs as executed (2 N^2 (1+k) 256^2 per cloud, fp32-equivalent: every product is three
+    kind::tf32 MMAs) divided by its CUDA-event time inside the profiled step, against the measured bf16 sustained peak."""
+    t1_ms, t1_flop = per_op.get("gr_structure_embedding_fused", 0.0), work.get("gr_structure_embedding_fused", 0.0)
+    n_t1 = max(1, sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused"))
+    achieved = t1_flop / (t1_ms * 1e-3) / 1e12 if t1_ms > 0 else 0.0
+    t1_rows = t1_flop / n_t1 / (2.0 * 4 * 256 * 256)  # (n, m) pairs per launch = N^2
+    roofline = {
+        "kernel": "tc::structure_embedding_tc256_kernel (T1: in-kernel sinusoid -> tcgen05.mma kind::tf32 3xTF32 -> max_k -> sum; "
+                  "TMEM ping-pong accumulators)",
+        "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+        "peak_source": peaks["source"] + " bf16 sustained (cuBLAS, MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate and "
+                       "every fp32-accurate product costs 3 MMAs, so the tensor-pipe occupancy is ~6 x frac",
+        "tf32_mma_tflops": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (peaks["tf_sustained"] / 2.0),
+        "launches_per_step": n_t1, "avg_launch_ms": t1_ms / n_t1, "flop_per_launch_fp32_equiv": t1_flop / n_t1,
+        "share_of_step": t1_ms / max(sum(per_op.values()), 1e-9),
+        "algorithmic_bytes_per_launch": 4.0 * t1_rows * (256 + 4), "traffic": None,
+    }
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        k = tj.get("kernels", {}).get("structure_embedding_tc256_kernel")
+        if k:
+            roofline["traffic"] = k["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tj.get("source")
+        roofline["traffic_other_kernels"] = {n: v["dram_bytes_per_launch"] for n, v in tj.get("kernels", {}).items()
+                                             if n != "structure_embedding_tc256_kernel"}
+    hbm = {}
+    n_calls = {}
+    for r in lib.records:
+        n_calls[r[0]] = n_calls.get(r[0], 0) + 1
+    k = "gr_radius_neighbors"
+    if per_op.get(k, 0.0) > 0:
+        gbs = work[k] / (per_op[k] * 1e-3) / 1e9
+        hbm[k] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                  "algorithmic_bytes_per_step": work[k], "calls_per_step": n_calls.get(k, 0), "ms_per_step": per_op[k],
+                  "note": "13 searches of the profiled step (latency-bound at batch 1: 86 MB of compulsory bytes per pair)"}
+    if microbench:
+        try:
+            hbm.update(kernel_class_microbench(model, resident_pair, dev, peaks))
+        except Exception as ex:
+            hbm["microbench_error"] = repr(ex)[:200]
+    rpe = rpe_microbench(dev) if microbench else None
+    if rpe is not None:
+        rpe["peak"] = peaks["hbm_gbs"]
+        rpe["frac"] = rpe["achieved"] / peaks["hbm_gbs"]
+        hbm["rpe_scores_softmax_v2_kernel"] = rpe
+    roofline["other_kernel_classes"] = hbm
+    return roofline
+
+
 def warm_steps(args):
     return max(args.warmup, 3)
 
@@ -582,60 +717,7 @@ def run_ours(args, rank, world, local_rank):
         value = world * args.steps / (total_ms / 1e3)
         e2e_value = world * args.steps / (e2e_ms / 1e3)
         top = max(per_op, key=per_op.get)
-        # dominant kernels: the tcgen05 3xTF32 tensor-core kernels (gemm_tf32x3_kernel + structure_embedding_tc_kernel)
-        tc_keys = ["gr_gemm[tcgen05]", "gr_linear_packed[tcgen05]", "gr_structure_embedding_fused"]
-        tc_ms = sum(per_op.get(k, 0.0) for k in tc_keys)
-        tc_flop = sum(work.get(k, 0.0) for k in tc_keys)
-        n_tc = sum(1 for r in lib.records if r[0] in tc_keys)
-        achieved_tf = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        roofline = {
-            "kernel": "gemm_tf32x3_kernel + structure_embedding_tc256_kernel (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
-            "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
-            "peak_source": peaks["source"] + " bf16 sustained (cuBLAS); kind::tf32 issues at half the bf16 rate and every fp32 "
-                                             "product costs 3 MMAs, so tensor-pipe occupancy ~= 6 x frac",
-            "tensor_pipe_equiv_frac": 6.0 * achieved_tf / peaks["tf_sustained"],
-            # the MMA rate actually issued (3 tf32 MMAs per fp32 product) against the tf32 peak (= bf16 peak / 2)
-            "tf32_mma_tflops": 3.0 * achieved_tf, "tf32_peak_tflops": peaks["tf_sustained"] / 2.0,
-            "launches_per_step": n_tc, "avg_launch_ms": tc_ms / max(n_tc, 1),
-            "flop_per_step_fp32_equiv": tc_flop, "share_of_step": tc_ms / max(sum(per_op.values()), 1e-9),
-        }
-        t1_ms, t1_flop = per_op.get("gr_structure_embedding_fused", 0.0), work.get("gr_structure_embedding_fused", 0.0)
-        if t1_ms > 0:
-            n_t1 = sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused")
-            t1_rows = int(t1_flop / max(n_t1, 1) / (2.0 * 4 * 256 * 256))  # pair-rows per launch (N^2)
-            roofline["largest_single_kernel"] = {
-                "kernel": "structure_embedding_tc256_kernel", "achieved": t1_flop / (t1_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                "frac": t1_flop / (t1_ms * 1e-3) / 1e12 / peaks["tf_sustained"], "avg_launch_ms": t1_ms / max(n_t1, 1),
-                "tf32_mma_tflops": 3.0 * t1_flop / (t1_ms * 1e-3) / 1e12,
-                "frac_of_tf32_peak": 3.0 * t1_flop / (t1_ms * 1e-3) / 1e12 / (peaks["tf_sustained"] / 2.0),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01f_launches_by_kernel.txt)
-                "traffic": 198.4e6, "traffic_source": "ncu capture of a bench step (N=479/488 superpoints), not re-measured live",
-                "algorithmic_bytes": 4.0 * t1_rows * (256 + 4),  # (N^2, 256) output + d/a indices
-            }
-        # HBM-class kernels of the same profiled step: algorithmic bytes / event time against the measured copy peak
-        hbm = {}
-        n_calls = {}
-        for r in lib.records:
-            n_calls[r[0]] = n_calls.get(r[0], 0) + 1
-        for k in ("gr_radius_neighbors", "gr_kpconv_aggregate", "gr_group_norm"):
-            if per_op.get(k, 0.0) > 0:
-                gbs = work[k] / (per_op[k] * 1e-3) / 1e9
-                hbm[k] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                          "algorithmic_bytes_per_step": work[k], "calls_per_step": n_calls.get(k, 0), "ms_per_step": per_op[k]}
-        rpe = rpe_microbench(dev)
-        if rpe is not None:
-            rpe["peak"] = peaks["hbm_gbs"]
-            rpe["frac"] = rpe["achieved"] / peaks["hbm_gbs"]
-            hbm["rpe_scores_softmax_v2_kernel"] = rpe
-        roofline["hbm_class_kernels"] = hbm
-        traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(traffic_path):
-            tj = json.load(open(traffic_path))
-            roofline["traffic"] = tj["tensor_core_kernels"]["dram_bytes_per_launch"]
-            roofline["traffic_source"] = tj["source"]
-            roofline["algorithmic_bytes_per_launch"] = sum(
-                4.0 * (sh[0] * sh[2] + sh[1] * sh[2] + sh[0] * sh[1]) * sh[3] * v[0] for sh, v in gemm_shapes.items()) / max(n_tc, 1)
+        roofline = build_roofline(lib, per_op, work, peaks, model, resident[0], dev, microbench=(world == 1))
         cpu = None
         throughput = None
         gpu_torch = None

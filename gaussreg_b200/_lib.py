@@ -107,6 +107,7 @@ _SIGNATURES = {
     "gr_lgr_workspace_size": (_sz, [_i32, _i32, _i32]),
     "gr_local_global_registration": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _f32, _i32, _i32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_gaussian_transform": (_i32, [_vp, _i64, _i64, _vp, _f32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "gr_farthest_point_sample_workspace_size": (_sz, [_i64]),
     "gr_farthest_point_sample": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),
     "gr_similarity_ransac_workspace_size": (_sz, [_i32]),

@@ -105,6 +105,10 @@ __device__ __forceinline__ void tile_epilogue(const Params& p, unsigned char* sm
   // ------------------------------------------------------------------ epilogue
   mbar_wait(accum_bar, 0);
   tc_fence_after();
+  // The operand stages are reused as the transposition buffer below.  The mbarrier chain (producer stores -> full ->
+  // MMA -> commit -> accum) already orders every earlier write / tensor-core read before this point; the CTA-scope
+  // barrier among the 256 epilogue threads states the same hand-over in a form compute-sanitizer's racecheck can see.
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   const int q = warp & 3, half = warp >> 2;
   float* __restrict__ Cp = p.C + (long long)blockIdx.z * p.sC;  // split-K: sC = M*N, raw partial sums
   const float* __restrict__ R = p.residual ? p.residual + (long long)blockIdx.z * p.sR : nullptr;

@@ -837,6 +837,9 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
   GR_CHECK_CUDA(cudaMemsetAsync(w.tab_first, 0x7f, w.tab_slots * sizeof(int), st));
   GR_CHECK_CUDA(cudaMemsetAsync(w.tab_cnt, 0, w.tab_slots * sizeof(uint32_t), st));
   GR_CHECK_CUDA(cudaMemsetAsync(w.vfill, 0, ((size_t)n + 1) * sizeof(uint32_t), st));
+  // the scan below walks all n + 1 capacity slots of vcnt; only the first (number of voxels) + 1 are written by
+  // voxel_init_kernel -- clear the tail so that no kernel reads uninitialised memory (initcheck-clean)
+  GR_CHECK_CUDA(cudaMemsetAsync(w.vcnt, 0, ((size_t)n + 2) * sizeof(uint32_t), st));
   prep_offsets_kernel<<<1, 256, 0, st>>>(lengths, w.off, nullptr, nullptr, batch, w.bbox, w.scalars, 8);
   GR_CHECK_LAUNCH("prep_offsets_kernel");
   if (n > 0) {

@@ -4,6 +4,8 @@ Same function names, arguments and returned dict as the reference, but every ten
 CUDA device and the 4 grid subsamples + 13 radius searches are gaussreg_b200 kernels.  Host syncs:
 one for the stage lengths, one for the 13 neighbour-table widths (the reference's tensors have
 data-dependent shapes)."""
+import os
+
 import numpy as np
 import torch
 
@@ -48,58 +50,100 @@ class LazyTables(list):
 def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, lazy=True):
     """utils/data.py:13-77 on the GPU.  Returns the reference's dict plus `lengths_host` (python ints per stage and
     cloud, read in the same device->host transfer as the stage sizes, so that the model needs no sync of its own).
-    With `lazy` (default) the three table lists are LazyTables: same contents, trimmed on first access."""
+    With `lazy` (default) the three table lists are LazyTables: same contents, trimmed on first access.
+
+    Issue order: the four grid subsamples form a dependent chain whose long kernels (the hash-order replay) occupy a
+    handful of SMs; every kernel of the pyramid takes its true sizes from device memory (the host only knows upper
+    bounds), so all 13 radius searches are queued on a helper stream behind per-stage events and run UNDERNEATH the
+    chain.  The host then reads the stage sizes as soon as the chain is done, and the table widths lazily."""
     assert num_stages == len(neighbor_limits)
     dev = points.device if points.is_cuda else ext._device()
     points = points.to(dev, torch.float32).contiguous()
     lengths = lengths.to(dev, torch.int64).contiguous()
     n0 = points.shape[0]
     nb = lengths.shape[0]
+    main = torch.cuda.current_stream(dev)
+    side = ext.side_stream(dev) if os.environ.get("GAUSSREG_PYRAMID_STREAMS", "2") != "1" else None
 
-    # --- grid subsampling chain, device-side lengths, buffers sized by the upper bound
-    pts_cap, len_dev, totals = [points], [lengths], []
+    # --- buffers first (all on the caller's stream / allocator pool): every stage is sized by the upper bound n0
+    specs = []  # (key, query stage, support stage, radius, limit)
+    r = radius
+    for i in range(num_stages):
+        specs.append(("neighbors", i, i, r, neighbor_limits[i]))
+        if i < num_stages - 1:
+            specs.append(("subsampling", i + 1, i, r, neighbor_limits[i]))
+            specs.append(("upsampling", i, i + 1, r * 2, neighbor_limits[i + 1]))
+        r *= 2
+    tables = [torch.empty((n0, limit), dtype=torch.int64, device=dev) for (_, _, _, _, limit) in specs]
+    counts_dev = torch.zeros((len(specs),), dtype=torch.int32, device=dev)
+    grids = [ext.radius_grid_workspace(points, lengths) for _ in range(num_stages)]  # sized by the upper bound n0
+    if side is not None:
+        # the helper stream starts where the caller's stream is NOW: inputs are ready, and every kernel that may still
+        # read a recycled buffer (the previous pair's forward) has been ordered before it
+        start = torch.cuda.Event()
+        start.record(main)
+        side.wait_event(start)
+
+    # --- grid subsampling chain, device-side lengths, capacity-sized outputs
+    pts_cap, len_dev, totals, ready = [points], [lengths], [], [None]
     for i in range(1, num_stages):
         voxel_size_i = voxel_size * (2 ** i)
-        out, out_len, out_total = ext.grid_subsample_device(pts_cap[-1], len_dev[-1], voxel_size_i,
-                                                            n_points=pts_cap[-1].shape[0])
+        out, out_len, out_total = ext.grid_subsample_device(pts_cap[-1], len_dev[-1], voxel_size_i, n_points=n0)
         pts_cap.append(out)
         len_dev.append(out_len)
         totals.append(out_total)
-    host = torch.cat(totals + len_dev).cpu().tolist()  # sync 1: stage sizes and per-cloud lengths
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ready.append(ev)
+    sizes_dev = torch.cat(totals + len_dev) if totals else torch.cat(len_dev)
+
+    # --- radius searches (limit-wide tables, widths come back later).  Stage i's support cloud is searched with radius
+    # r_i by "neighbors" and "subsampling" of stage i and (r_i = 2 r_{i-1}) by "upsampling" of stage i-1: one cell grid per
+    # stage serves all three (5 grids for 13 searches).
+    built = [False] * num_stages
+
+    def searches():
+        waited = 0
+        for j, (key, qs, ss, rad, limit) in enumerate(specs):
+            need = max(qs, ss)
+            if side is not None:
+                while waited < need:
+                    waited += 1
+                    side.wait_event(ready[waited])
+            ext.radius_neighbors_device(pts_cap[qs], pts_cap[ss], len_dev[qs], len_dev[ss], rad, limit, out=tables[j],
+                                        grid_ws=grids[ss], reuse_grid=built[ss], max_count=counts_dev[j:j + 1])
+            built[ss] = True
+
+    done = None
+    if side is not None:
+        with torch.cuda.stream(side):
+            searches()
+            done = torch.cuda.Event()
+            done.record(side)
+    else:
+        searches()
+
+    host = sizes_dev.cpu().tolist()  # sync 1: stage sizes and per-cloud lengths (waits for the subsample chain only)
     tot = host[:len(totals)]
     lengths_host = [host[len(totals) + s * nb: len(totals) + (s + 1) * nb] for s in range(num_stages)]
     sizes = [n0] + [int(t) for t in tot]
     points_list = [pts_cap[i][: sizes[i]] for i in range(num_stages)]
-    lengths_list = len_dev
-
-    # --- radius searches into limit-wide tables, then one sync for the widths
-    # Stage i's support cloud is searched with radius r_i by "neighbors" and "subsampling" of stage i and (r_i = 2 r_{i-1})
-    # by "upsampling" of stage i-1: one cell grid per stage serves all three (5 grids for 13 searches).
-    tables, counts, meta = [], [], []
-    grids = [ext.radius_grid_workspace(points_list[i], lengths_list[i]) for i in range(num_stages)]
-    built = [False] * num_stages
-    r = radius
-    for i in range(num_stages):
-        cur_p, cur_l = points_list[i], lengths_list[i]
-        t, c = ext.radius_neighbors_device(cur_p, cur_p, cur_l, cur_l, r, neighbor_limits[i], grid_ws=grids[i], reuse_grid=built[i])
-        built[i] = True
-        tables.append(t); counts.append(c); meta.append(("neighbors", neighbor_limits[i]))
-        if i < num_stages - 1:
-            sub_p, sub_l = points_list[i + 1], lengths_list[i + 1]
-            t, c = ext.radius_neighbors_device(sub_p, cur_p, sub_l, cur_l, r, neighbor_limits[i], grid_ws=grids[i], reuse_grid=True)
-            tables.append(t); counts.append(c); meta.append(("subsampling", neighbor_limits[i]))
-            t, c = ext.radius_neighbors_device(cur_p, sub_p, cur_l, sub_l, r * 2, neighbor_limits[i + 1], grid_ws=grids[i + 1],
-                                               reuse_grid=built[i + 1])
-            built[i + 1] = True
-            tables.append(t); counts.append(c); meta.append(("upsampling", neighbor_limits[i + 1]))
-        r *= 2
-    counts_dev = torch.cat(counts)
-    out = {"points": points_list, "lengths": lengths_list, "lengths_host": lengths_host}
+    out = {"points": points_list, "lengths": len_dev, "lengths_host": lengths_host}
 
     def finalize():
-        widths = counts_dev.cpu().tolist()  # sync 2
-        for t, w, (key, limit) in zip(tables, widths, meta):
+        if done is not None:
+            # read the widths on the HELPER stream: the copy then completes as soon as the searches do, instead of queueing
+            # behind whatever the caller's stream is running by now (the structure embedding) -- the host can trim the
+            # tables and issue the backbone while that kernel is still busy
+            with torch.cuda.stream(side):
+                widths = counts_dev.cpu().tolist()  # sync 2
+            torch.cuda.current_stream(dev).wait_event(done)  # the searches' tables become visible to the caller's stream
+        else:
+            widths = counts_dev.cpu().tolist()  # sync 2
+        for t, w, (key, qs, _, _, limit) in zip(tables, widths, specs):
             w = min(int(w), limit)
+            t = t[: sizes[qs]]
             list.append(out[key], t[:, :w] if w == t.shape[1] else t[:, :w].contiguous())
         for key in ("neighbors", "subsampling", "upsampling"):
             out[key]._finalize = None

@@ -49,6 +49,15 @@ def _workspace(nbytes, dev):
     return buf
 
 
+def release_workspaces(device=None):
+    """Drop the grow-only scratch buffers (all devices, or one): they are keyed by (device, stream) and otherwise live
+    for the life of the process.  Call it after a batch of unusually large clouds, or before tearing streams down; the
+    next op simply allocates again."""
+    idx = None if device is None else torch.device(device).index
+    for key in [k for k in _ws_cache if idx is None or k[0] == idx]:
+        del _ws_cache[key]
+
+
 def grid_subsample_device(points, lengths, voxel_size, n_points=None):
     """Sync-free core: returns (out_points[capacity n], out_lengths, out_total) all on the device.
 
@@ -94,14 +103,31 @@ def radius_grid_workspace(s_points, s_lengths):
     return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=s_points.device)
 
 
-def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None, grid_ws=None, reuse_grid=False):
+_side_streams = {}
+
+
+def side_stream(dev):
+    """A helper stream per (device, current stream): work that does not depend on the caller's latest kernels (the radius
+    searches of a pyramid, while the grid-subsample chain is still running) is queued there.  Kept for the life of the
+    process: the per-stream workspaces are keyed by it."""
+    key = (dev.index, _stream())
+    s = _side_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _side_streams[key] = s
+    return s
+
+
+def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None, grid_ws=None, reuse_grid=False,
+                            max_count=None):
     """Sync-free core: fills a (Nq, ld) int64 table (first min(count, ld) sorted neighbours per row,
     padded with Ns) and returns (table, max_count device scalar).  `grid_ws` (radius_grid_workspace) keeps the
     support cloud's cell grid; pass reuse_grid=True on later searches of the same (support, radius)."""
     L = _lib.lib()
     dev = q_points.device
     nq, ns, batch = q_points.shape[0], s_points.shape[0], q_lengths.shape[0]
-    max_count = torch.empty((1,), dtype=torch.int32, device=dev)
+    if max_count is None:
+        max_count = torch.empty((1,), dtype=torch.int32, device=dev)
     if out is None and ld > 0:
         out = torch.empty((nq, ld), dtype=torch.int64, device=dev)
     if grid_ws is None:

@@ -645,3 +645,41 @@ def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, n
                                       _req(emb1).data_ptr(), N0, N1, C, num_heads, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(st, "conditional_transformer")
     return f0, f1
+
+
+# ------------------------------------------------------------------------------------------------
+# device guard: every op runs on the device (and that device's current stream) of its first tensor argument
+# ------------------------------------------------------------------------------------------------
+def _first_tensor_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            return a.device if a.is_cuda else None
+        if isinstance(a, torch.nn.Module):
+            for p in a.parameters():
+                return p.device if p.is_cuda else None
+    return None
+
+
+def _device_guarded(fn):
+    """Tensors on a GPU that is not the current one (threads per GPU, an explicit `cuda:1` model in a `cuda:0` process)
+    would otherwise be launched on the wrong device: `_stream()` and the workspaces follow torch's CURRENT device.  The
+    guard switches to the tensor's device for the duration of the call; on the common single-device path it costs one
+    integer comparison."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_tensor_device(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
+for _name, _obj in list(globals().items()):
+    if callable(_obj) and getattr(_obj, "__module__", None) == __name__ and not _name.startswith("_") and \
+            _name not in ("invalidate_weight_caches",):
+        globals()[_name] = _device_guarded(_obj)
+del _name, _obj

@@ -217,6 +217,13 @@ size_t gr_farthest_point_sample_workspace_size(int64_t n_points);
 int gr_farthest_point_sample(const float* points, int64_t n_points, int k, int64_t start_idx, int64_t* out_idx, void* ws,
                              size_t ws_bytes, void* stream);
 
+/* N4  Gaussian merge (gs_fusion.py:231-262): the second 3DGS cloud under the estimated similarity transform -- positions,
+ * log-scales, rotation quaternions (quaternion_to_matrix / matrix_to_quaternion, :70-159) and SH bands 1-3 (sh_rotation,
+ * :53-68).  cloud / out: (n,59) f32 device rows with pitches ld_in / ld_out; h_rotation: HOST 3x3 unit rotation (row-major);
+ * log_scale = log(scale); h_translation: HOST float[3]; h_sh: HOST double[9 + 25 + 49] band matrices. */
+int gr_gaussian_transform(const float* cloud, int64_t ld_in, int64_t n, const float* h_rotation, float scale, float log_scale,
+                          const float* h_translation, const double* h_sh, float* out, int64_t ld_out, void* stream);
+
 /* N3  similarity-transform RANSAC over the LGR correspondences (model.py:209-215, utils/open3d.py:169-198; restates the
  * published algorithm of open3d==0.11.2 registration_ransac_based_on_correspondence with
  * TransformationEstimationPointToPoint(with_scaling=True): third party, randomised -> statistical parity only).
