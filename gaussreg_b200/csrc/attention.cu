@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) rpe_scores_softmax_kernel(const float* __
                                                                  const float* __restrict__ U, const float* __restrict__ qb,
                                                                  const float* __restrict__ emb, int N, int C, float scale,
                                                                  float* __restrict__ P, long long ldq, long long ldk) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   float* sU = sm;                 // [H][C]
   float* sq = sU + H * C;         // [C]
@@ -132,6 +134,8 @@ constexpr int kRpeKeys = 8;  // keys per warp iteration
 __global__ void __launch_bounds__(256, 2) rpe_scores_softmax_v2_kernel(const float* __restrict__ U, const float* __restrict__ qb,
                                                                        const float* __restrict__ emb, int N, float scale,
                                                                        float* __restrict__ P) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int H = 4, C = 256, C4 = C / 4;
   extern __shared__ float ss[];  // [H][N] scores of this query row
   __shared__ float red[H][8];
@@ -220,6 +224,8 @@ __global__ void __launch_bounds__(256, 2) rpe_scores_softmax_v2_kernel(const flo
 
 // in-place row softmax, one warp per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long long rows, int cols) {
+  pdl_wait();
+  pdl_trigger();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -237,6 +243,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
 // F.normalize(x, p=2, dim=1): x / max(|x|, eps)
 __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                                 float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -275,7 +283,7 @@ extern "C" int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const floa
     const size_t smem = (size_t)num_heads * N * sizeof(float);
     auto kern = rpe_scores_softmax_v2_kernel;
     if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem));
-    kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(U, qb, emb, N, scale, P);
+    GR_CHECK_CUDA(launch_pdl(kern, dim3(N), dim3(256), (size_t)(smem), static_cast<cudaStream_t>(stream), U, qb, emb, N, scale, P));
     GR_CHECK_LAUNCH("rpe_scores_softmax_v2_kernel");
     return GR_OK;
   }
@@ -284,7 +292,7 @@ extern "C" int gr_rpe_attention_probs_ld(const float* q, int64_t ldq, const floa
   if (smem > 200 * 1024) return GR_ERR_CAPACITY;
   auto kern = rpe_scores_softmax_kernel<4>;
   if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem));
-  kern<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(q, k, U, qb, emb, N, C, scale, P, ldq, ldk);
+  GR_CHECK_CUDA(launch_pdl(kern, dim3(N), dim3(256), (size_t)(smem), static_cast<cudaStream_t>(stream), q, k, U, qb, emb, N, C, scale, P, ldq, ldk));
   GR_CHECK_LAUNCH("rpe_scores_softmax_kernel");
   return GR_OK;
 }
@@ -298,7 +306,7 @@ extern "C" int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream) {
   if (rows < 0 || cols <= 0) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!x) return GR_ERR_BAD_ARG;
-  softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols);
+  GR_CHECK_CUDA(launch_pdl(softmax_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, rows, cols));
   GR_CHECK_LAUNCH("softmax_rows_kernel");
   return GR_OK;
 }
@@ -307,7 +315,7 @@ extern "C" int gr_l2_normalize_rows(const float* x, int64_t rows, int C, float e
   if (rows < 0 || C <= 0) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!x || !y) return GR_ERR_BAD_ARG;
-  l2_normalize_rows_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, C, eps, y);
+  GR_CHECK_CUDA(launch_pdl(l2_normalize_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), x, rows, C, eps, y));
   GR_CHECK_LAUNCH("l2_normalize_rows_kernel");
   return GR_OK;
 }

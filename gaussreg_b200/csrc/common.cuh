@@ -58,6 +58,30 @@ int group_norm_from_partial(const float* x, long long n_rows, int C, int groups,
 // rows covered by one partial block of the split-K reduction (gemm_tc.cu)
 constexpr int kGnReduceRows = 32;
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Most of this library's kernels are short (2-20 us) links of long dependent chains; measured on B200, the step's wall
+// time exceeds the sum of its kernel times by ~1.6 us per launch.  A kernel launched with the programmatic-stream-
+// serialization attribute may be scheduled while its predecessor is still running: everything before its
+// `pdl_wait()` (parameter loads, shared-memory carving, barrier / TMEM set-up) overlaps the predecessor's tail, and
+// `pdl_wait()` returns once the predecessor has completed and its memory is visible.  `pdl_trigger()` lets the NEXT
+// kernel in the stream start being scheduled.  Rules kept by every kernel that is launched through launch_pdl():
+// no global memory access before pdl_wait(); pdl_trigger() right after it.  GAUSSREG_PDL=0 turns the attribute off
+// (the two instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- workspace carving ----------------------------------------------------------------------
 struct Carver {
   char* base;

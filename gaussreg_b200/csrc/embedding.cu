@@ -16,6 +16,8 @@ __device__ __forceinline__ float sq_norm3f(float a, float b, float c) {
 // one CTA per anchor n: row of distances into shared memory, k+1 smallest by (d, index), drop the first
 __global__ void __launch_bounds__(128) pairdist_knn_kernel(const float* __restrict__ pts, int N, float sigma_d, int k,
                                                            float* __restrict__ d_idx, int* __restrict__ knn) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float row[];  // N distances
   __shared__ unsigned long long sh_best[4];
   __shared__ unsigned long long sh_prev;
@@ -60,6 +62,8 @@ __global__ void __launch_bounds__(128) pairdist_knn_kernel(const float* __restri
 // a_idx[n, m, j] for j < k
 __global__ void __launch_bounds__(256) angle_index_kernel(const float* __restrict__ pts, int N, int k, const int* __restrict__ knn,
                                                           float factor_a, float* __restrict__ a_idx) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * N * k;
   if (t >= total) return;
@@ -83,6 +87,8 @@ __global__ void __launch_bounds__(256) angle_index_kernel(const float* __restric
 // E[r, 2i] = sin(x[r] * div[i]); E[r, 2i+1] = cos(x[r] * div[i]);  C = 2 * n_div
 __global__ void __launch_bounds__(256) sinusoid_rows_kernel(const float* __restrict__ x, long long rows,
                                                             const float* __restrict__ div, int n_div, float* __restrict__ E) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = rows * n_div;
   if (t >= total) return;
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(256) sinusoid_rows_kernel(const float* __restr
 // out[r, c] = D[r, c] + max_j A[(r*k + j), c]
 __global__ void __launch_bounds__(256) embedding_combine_kernel(const float* __restrict__ D, const float* __restrict__ A,
                                                                 long long rows, int C, int k, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rows * C) return;
   const int c = (int)(t % C);
@@ -119,11 +127,11 @@ extern "C" int gr_embedding_indices(const float* points, int N, float sigma_d, f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)N * sizeof(float);
   if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(pairdist_knn_kernel), (int)smem));
-  pairdist_knn_kernel<<<N, 128, smem, st>>>(points, N, sigma_d, angle_k, d_idx, knn);
+  GR_CHECK_CUDA(launch_pdl(pairdist_knn_kernel, dim3(N), dim3(128), (size_t)(smem), st, points, N, sigma_d, angle_k, d_idx, knn));
   GR_CHECK_LAUNCH("pairdist_knn_kernel");
   const float factor_a = (float)(180.0 / ((double)sigma_a * 3.141592653589793));  // geotransformer.py:14
   const long long total = (long long)N * N * angle_k;
-  angle_index_kernel<<<ceil_div(total, 256), 256, 0, st>>>(points, N, angle_k, knn, factor_a, a_idx);
+  GR_CHECK_CUDA(launch_pdl(angle_index_kernel, dim3(ceil_div(total, 256)), dim3(256), (size_t)(0), st, points, N, angle_k, knn, factor_a, a_idx));
   GR_CHECK_LAUNCH("angle_index_kernel");
   return GR_OK;
 }
@@ -132,7 +140,7 @@ extern "C" int gr_sinusoid_rows(const float* x, int64_t rows, const float* div_t
   if (rows < 0 || n_div <= 0) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!x || !div_term || !E) return GR_ERR_BAD_ARG;
-  sinusoid_rows_kernel<<<ceil_div(rows * n_div, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, div_term, n_div, E);
+  GR_CHECK_CUDA(launch_pdl(sinusoid_rows_kernel, dim3(ceil_div(rows * n_div, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), x, rows, div_term, n_div, E));
   GR_CHECK_LAUNCH("sinusoid_rows_kernel");
   return GR_OK;
 }
@@ -141,7 +149,7 @@ extern "C" int gr_embedding_combine(const float* D, const float* A, int64_t rows
   if (rows < 0 || C <= 0 || k <= 0) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!D || !A || !out) return GR_ERR_BAD_ARG;
-  embedding_combine_kernel<<<ceil_div(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(D, A, rows, C, k, out);
+  GR_CHECK_CUDA(launch_pdl(embedding_combine_kernel, dim3(ceil_div(rows * C, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), D, A, rows, C, k, out));
   GR_CHECK_LAUNCH("embedding_combine_kernel");
   return GR_OK;
 }

@@ -31,6 +31,8 @@ constexpr int kEmbThreads = kEmbProducers + 32;          // + the MMA warp
 // W (N, K) row-major -> for every (n-tile of 128, k-block of 32): [hi tile 16 KB][lo tile 16 KB] in the
 // K-major SWIZZLE_128B byte order the tensor core reads.
 __global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int nt = blockIdx.y, kb = blockIdx.x;
   const int kblocks = (K + 31) / 32;
   unsigned char* base = reinterpret_cast<unsigned char*>(out) + ((size_t)(nt * kblocks + kb)) * 2 * kEmbTile;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
     const float* __restrict__ bias_d, const float* __restrict__ bias_a, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEmbStages * kEmbStageBytes);
@@ -296,6 +300,8 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const float* __restrict__ wd_packed, const float* __restrict__ wa_packed,
     const float* __restrict__ bias_d, const float* __restrict__ bias_a, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kE2Stages * kE2StageBytes);
@@ -515,7 +521,7 @@ using namespace gr;
 extern "C" int gr_pack_weight_tf32x3(const float* W, int N, int K, float* out, void* stream) {
   if (N <= 0 || K <= 0 || !W || !out) return GR_ERR_BAD_ARG;
   dim3 grid((K + 31) / 32, ((N + 255) / 256) * 2);
-  tc::pack_weight_tf32x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, N, K, out);
+  GR_CHECK_CUDA(launch_pdl(tc::pack_weight_tf32x3_kernel, dim3(grid), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), W, N, K, out));
   GR_CHECK_LAUNCH("pack_weight_tf32x3_kernel");
   return GR_OK;
 }
@@ -562,19 +568,16 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
       GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::structure_embedding_tc256_kernel<2>, d_idx, a_idx, (long long)rows, angle_k, div_term,
                                        wd_packed, wa_packed, bias_d, bias_a, out));
     } else {
-      tc::structure_embedding_tc256_kernel<1><<<tiles, tc::kEmbThreads, tc::kE2Smem, static_cast<cudaStream_t>(stream)>>>(
-          d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+      GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_tc256_kernel<1>, dim3(tiles), dim3(tc::kEmbThreads), (size_t)(tc::kE2Smem), static_cast<cudaStream_t>(stream), d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out));
     }
     GR_CHECK_LAUNCH("structure_embedding_tc256_kernel");
     return GR_OK;
   }
   dim3 grid(tc::kEmbC / tc::kEmbBN, (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM));
   if (cw)
-    tc::structure_embedding_tc_kernel<true><<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
-        d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+    GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_tc_kernel<true>, dim3(grid), dim3(tc::kEmbThreads), (size_t)(tc::kEmbSmem), static_cast<cudaStream_t>(stream), d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out));
   else
-    tc::structure_embedding_tc_kernel<false><<<grid, tc::kEmbThreads, tc::kEmbSmem, static_cast<cudaStream_t>(stream)>>>(
-        d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out);
+    GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_tc_kernel<false>, dim3(grid), dim3(tc::kEmbThreads), (size_t)(tc::kEmbSmem), static_cast<cudaStream_t>(stream), d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out));
   GR_CHECK_LAUNCH("structure_embedding_tc_kernel");
   return GR_OK;
 }

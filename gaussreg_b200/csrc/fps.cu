@@ -23,6 +23,8 @@ __device__ __forceinline__ unsigned long long fps_key(float d, int i) {
 __global__ void __launch_bounds__(kFpsThreads) fps_step_kernel(const float* __restrict__ pts, int n, float* __restrict__ dist, int iter,
                                                                int start, long long* __restrict__ sel,
                                                                unsigned long long* __restrict__ partial, int nblk) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned long long sh[kFpsThreads];
   __shared__ int s_cur;
   const int tid = threadIdx.x;
@@ -88,8 +90,8 @@ extern "C" int gr_farthest_point_sample(const float* points, int64_t n_points, i
   if (nblk > kFpsMaxBlocks) nblk = kFpsMaxBlocks;
   if (nblk < 1) nblk = 1;
   for (int it = 0; it < k; ++it) {
-    fps_step_kernel<<<nblk, kFpsThreads, 0, st>>>(points, (int)n_points, dist, it, (int)start_idx, reinterpret_cast<long long*>(out_idx),
-                                                  partial, nblk);
+    GR_CHECK_CUDA(launch_pdl(fps_step_kernel, dim3(nblk), dim3(kFpsThreads), (size_t)(0), st, points, (int)n_points, dist, it, (int)start_idx, reinterpret_cast<long long*>(out_idx),
+                                                  partial, nblk));
     if (it == 0 || it == k - 1) GR_CHECK_LAUNCH("fps_step_kernel");
   }
   count_launch(k > 2 ? k - 2 : 0);

@@ -20,6 +20,8 @@ struct FuseParams {
 
 __global__ void __launch_bounds__(128) gaussian_transform_kernel(const float* __restrict__ in, long long ld_in, long long n, FuseParams p,
                                                                  float* __restrict__ out, long long ld_out) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* a = in + i * ld_in;
@@ -112,7 +114,7 @@ extern "C" int gr_gaussian_transform(const float* cloud, int64_t ld_in, int64_t 
   for (int i = 0; i < 49; ++i) p.m3[i] = h_sh[34 + i];
   for (int i = 0; i < 3; ++i) p.t[i] = h_translation[i];
   p.scale = scale; p.log_scale = log_scale; p.apply_scale = scale != 1.0f;
-  gaussian_transform_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(cloud, ld_in, n, p, out, ld_out);
+  GR_CHECK_CUDA(launch_pdl(gaussian_transform_kernel, dim3(ceil_div(n, 128)), dim3(128), (size_t)(0), static_cast<cudaStream_t>(stream), cloud, ld_in, n, p, out, ld_out));
   GR_CHECK_LAUNCH("gaussian_transform_kernel");
   return GR_OK;
 }

@@ -9,6 +9,8 @@ namespace gr {
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, int Ns, int C,
                                                       const long long* __restrict__ idx, int H, long long ldi, int M,
                                                       float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int m = blockIdx.x;
   extern __shared__ int sh_idx[];
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
                                                               const long long* __restrict__ idx, long long ldi,
                                                               const float* __restrict__ skip, int C2, int M,
                                                               float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int m = blockIdx.x;
   const long long j = idx[(long long)m * ldi];
   const bool pad = j >= Nc || j < 0;
@@ -43,6 +47,8 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x, int n, int C,
                                                           const long long* __restrict__ idx, long long rows,
                                                           float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -60,8 +66,7 @@ extern "C" int gr_maxpool(const float* x, int Ns, int C, const int64_t* idx, int
   if (C <= 0 || H <= 0 || M < 0 || Ns < 0) return GR_ERR_BAD_ARG;
   if (M == 0) return GR_OK;
   if (!x || !idx || !out) return GR_ERR_BAD_ARG;
-  maxpool_kernel<<<M, C >= 256 ? 256 : (C >= 128 ? 128 : 64), H * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
-      x, Ns, C, reinterpret_cast<const long long*>(idx), H, ld_idx, M, out);
+  GR_CHECK_CUDA(launch_pdl(maxpool_kernel, dim3(M), dim3(C >= 256 ? 256 : (C >= 128 ? 128 : 64)), (size_t)(H * sizeof(int)), static_cast<cudaStream_t>(stream), x, Ns, C, reinterpret_cast<const long long*>(idx), H, ld_idx, M, out));
   GR_CHECK_LAUNCH("maxpool_kernel");
   return GR_OK;
 }
@@ -71,8 +76,8 @@ extern "C" int gr_upsample_concat(const float* coarse, int Nc, int C1, const int
   if (C1 <= 0 || C2 < 0 || M < 0 || Nc < 0) return GR_ERR_BAD_ARG;
   if (M == 0) return GR_OK;
   if (!coarse || !idx || !out || (C2 > 0 && !skip)) return GR_ERR_BAD_ARG;
-  upsample_concat_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(coarse, Nc, C1, reinterpret_cast<const long long*>(idx),
-                                                                           ld_idx, skip, C2, M, out);
+  GR_CHECK_CUDA(launch_pdl(upsample_concat_kernel, dim3(M), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), coarse, Nc, C1, reinterpret_cast<const long long*>(idx),
+                                                                           ld_idx, skip, C2, M, out));
   GR_CHECK_LAUNCH("upsample_concat_kernel");
   return GR_OK;
 }
@@ -81,8 +86,8 @@ extern "C" int gr_gather_rows(const float* x, int n, int C, const int64_t* idx, 
   if (C <= 0 || rows < 0 || n < 0) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!x || !idx || !out) return GR_ERR_BAD_ARG;
-  gather_rows_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, C, reinterpret_cast<const long long*>(idx),
-                                                                                        rows, out);
+  GR_CHECK_CUDA(launch_pdl(gather_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), x, n, C, reinterpret_cast<const long long*>(idx),
+                                                                                        rows, out));
   GR_CHECK_LAUNCH("gather_rows_kernel");
   return GR_OK;
 }

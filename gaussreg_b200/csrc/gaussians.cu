@@ -28,6 +28,8 @@ struct SelState { unsigned int prefix; unsigned int rank; };
 __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ cloud, long long n, int ld, SelectQueries qs,
                                                           const SelState* __restrict__ state, int shift,
                                                           unsigned int* __restrict__ hist) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned int sh[kMaxQueries * 256];
   for (int i = threadIdx.x; i < qs.n * 256; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
@@ -53,6 +55,8 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restric
 // one warp per query: pick the digit holding the wanted rank, clear the histogram for the next pass
 __global__ void select_pick_kernel(unsigned int* __restrict__ hist, SelState* __restrict__ state, int nq, int last,
                                    float* __restrict__ out_values) {
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.x;
   if (q >= nq) return;
   __shared__ unsigned int cnt[256];
@@ -74,6 +78,8 @@ __global__ void select_pick_kernel(unsigned int* __restrict__ hist, SelState* __
 }
 
 __global__ void select_init_kernel(SelState* __restrict__ state, SelectQueries qs, unsigned int* __restrict__ hist) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < qs.n) { state[i].prefix = 0u; state[i].rank = qs.rank[i]; }
   if (i < kMaxQueries * 256) hist[i] = 0u;
@@ -90,6 +96,8 @@ struct CropBox { double lo[3], hi[3]; };
 
 __global__ void __launch_bounds__(256) gaussian_flag_kernel(const float* __restrict__ cloud, long long n, int ld, int opacity_col,
                                                             float opacity_min, CropBox box, uint32_t* __restrict__ flag) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   uint32_t f = 0u;
@@ -108,6 +116,8 @@ __global__ void __launch_bounds__(256) gaussian_flag_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) gaussian_compact_kernel(const uint32_t* __restrict__ scan, long long n,
                                                                long long* __restrict__ out_index, long long* __restrict__ out_count) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *out_count = (long long)scan[n];
   if (i >= n) return;
@@ -118,6 +128,8 @@ __global__ void __launch_bounds__(256) gaussian_compact_kernel(const uint32_t* _
 __global__ void __launch_bounds__(256) gather_points_kernel(const float* __restrict__ cloud, int ld, const long long* __restrict__ index,
                                                             long long m, float* __restrict__ out_points,
                                                             unsigned int* __restrict__ mnmx) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const float inf = __int_as_float(0x7f800000);
   float x = inf, y = inf, z = inf;
@@ -136,6 +148,8 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float* __restr
 }
 
 __global__ void mnmx_init_kernel(unsigned int* __restrict__ mnmx) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x < 3) mnmx[threadIdx.x] = 0xffffffffu;
   else if (threadIdx.x < 6) mnmx[threadIdx.x] = 0u;
 }
@@ -145,6 +159,8 @@ __global__ void mnmx_init_kernel(unsigned int* __restrict__ mnmx) {
 // threads 0..2 add them sequentially (no reassociation, so the bits match numpy's).
 __global__ void __launch_bounds__(1024) sequential_colsum_kernel(const float* __restrict__ pts, long long m,
                                                                  const unsigned int* __restrict__ mnmx, float* __restrict__ out_stats) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float buf[2][3 * 1024];
   float acc = 0.f;
   const long long nchunk = (m + 1023) / 1024;
@@ -176,6 +192,8 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 
 __global__ void __launch_bounds__(128) gaussian_features_kernel(const float* __restrict__ cloud, int ld, const long long* __restrict__ index,
                                                                 long long m, ViewPoint view, float* __restrict__ out_feats) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float* row = cloud + (index ? index[i] : i) * ld;
@@ -237,6 +255,8 @@ struct Center3 { float c[3]; };
 // demo.py:85-110: points = points - center ; [points = points * scale]  (float32, each operation rounded)
 __global__ void __launch_bounds__(256) points_normalize_kernel(float* __restrict__ pts, long long m, Center3 ctr, float scale,
                                                                int apply_scale) {
+  pdl_wait();
+  pdl_trigger();
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= 3 * m) return;
   float v = __fsub_rn(pts[k], ctr.c[k % 3]);
@@ -273,14 +293,14 @@ extern "C" int gr_column_order_stats(const float* cloud, int64_t n, int ld, cons
     qs.rank[q] = (unsigned int)ranks[q];
   }
   for (int q = n_queries; q < kMaxQueries; ++q) { qs.col[q] = 0; qs.rank[q] = 0u; }
-  select_init_kernel<<<ceil_div(kMaxQueries * 256, 256), 256, 0, st>>>(state, qs, hist);
+  GR_CHECK_CUDA(launch_pdl(select_init_kernel, dim3(ceil_div(kMaxQueries * 256, 256)), dim3(256), (size_t)(0), st, state, qs, hist));
   GR_CHECK_LAUNCH("select_init_kernel");
   const int blocks = (int)min((long long)148 * 8, (long long)ceil_div(n, 256));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    select_hist_kernel<<<blocks, 256, 0, st>>>(cloud, (long long)n, ld, qs, state, shift, hist);
+    GR_CHECK_CUDA(launch_pdl(select_hist_kernel, dim3(blocks), dim3(256), (size_t)(0), st, cloud, (long long)n, ld, qs, state, shift, hist));
     GR_CHECK_LAUNCH("select_hist_kernel");
-    select_pick_kernel<<<n_queries, 256, 0, st>>>(hist, state, n_queries, pass == 3, out_values);
+    GR_CHECK_CUDA(launch_pdl(select_pick_kernel, dim3(n_queries), dim3(256), (size_t)(0), st, hist, state, n_queries, pass == 3, out_values));
     GR_CHECK_LAUNCH("select_pick_kernel");
   }
   return GR_OK;
@@ -304,12 +324,12 @@ extern "C" int gr_gaussian_select(const float* cloud, int64_t n, int ld, int opa
   uint32_t* scan_ws = c.take<uint32_t>(scan_workspace_elems(n + 2));
   CropBox box;
   for (int a = 0; a < 3; ++a) { box.lo[a] = lo[a]; box.hi[a] = hi[a]; }
-  gaussian_flag_kernel<<<ceil_div(n + 1, 256), 256, 0, st>>>(cloud, (long long)n, ld, opacity_col, opacity_min, box, flag);
+  GR_CHECK_CUDA(launch_pdl(gaussian_flag_kernel, dim3(ceil_div(n + 1, 256)), dim3(256), (size_t)(0), st, cloud, (long long)n, ld, opacity_col, opacity_min, box, flag));
   GR_CHECK_LAUNCH("gaussian_flag_kernel");
   const int rc = exclusive_scan_u32(flag, flag, n + 1, scan_ws, st);
   if (rc != GR_OK) return rc;
-  gaussian_compact_kernel<<<ceil_div(n > 0 ? n : 1, 256), 256, 0, st>>>(flag, (long long)n, reinterpret_cast<long long*>(out_index),
-                                                                       reinterpret_cast<long long*>(out_count));
+  GR_CHECK_CUDA(launch_pdl(gaussian_compact_kernel, dim3(ceil_div(n > 0 ? n : 1, 256)), dim3(256), (size_t)(0), st, flag, (long long)n, reinterpret_cast<long long*>(out_index),
+                                                                       reinterpret_cast<long long*>(out_count)));
   GR_CHECK_LAUNCH("gaussian_compact_kernel");
   return GR_OK;
 }
@@ -322,12 +342,12 @@ extern "C" int gr_gather_points_stats(const float* cloud, int ld, const int64_t*
   if (!ws || ws_bytes < 64) return GR_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned int* mnmx = static_cast<unsigned int*>(ws);
-  mnmx_init_kernel<<<1, 32, 0, st>>>(mnmx);
+  GR_CHECK_CUDA(launch_pdl(mnmx_init_kernel, dim3(1), dim3(32), (size_t)(0), st, mnmx));
   GR_CHECK_LAUNCH("mnmx_init_kernel");
-  gather_points_kernel<<<ceil_div(m, 256), 256, 0, st>>>(cloud, ld, reinterpret_cast<const long long*>(index), (long long)m,
-                                                         out_points, mnmx);
+  GR_CHECK_CUDA(launch_pdl(gather_points_kernel, dim3(ceil_div(m, 256)), dim3(256), (size_t)(0), st, cloud, ld, reinterpret_cast<const long long*>(index), (long long)m,
+                                                         out_points, mnmx));
   GR_CHECK_LAUNCH("gather_points_kernel");
-  sequential_colsum_kernel<<<1, 1024, 0, st>>>(out_points, (long long)m, mnmx, out_stats);
+  GR_CHECK_CUDA(launch_pdl(sequential_colsum_kernel, dim3(1), dim3(1024), (size_t)(0), st, out_points, (long long)m, mnmx, out_stats));
   GR_CHECK_LAUNCH("sequential_colsum_kernel");
   return GR_OK;
 }
@@ -341,8 +361,7 @@ extern "C" int gr_gaussian_features(const float* cloud, int ld, const int64_t* i
   if (!cloud || !out_feats) return GR_ERR_BAD_ARG;
   ViewPoint v;
   for (int a = 0; a < 3; ++a) v.c[a] = view_point[a];
-  gaussian_features_kernel<<<ceil_div(m, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      cloud, ld, reinterpret_cast<const long long*>(index), (long long)m, v, out_feats);
+  GR_CHECK_CUDA(launch_pdl(gaussian_features_kernel, dim3(ceil_div(m, 128)), dim3(128), (size_t)(0), static_cast<cudaStream_t>(stream), cloud, ld, reinterpret_cast<const long long*>(index), (long long)m, v, out_feats));
   GR_CHECK_LAUNCH("gaussian_features_kernel");
   return GR_OK;
 }
@@ -354,8 +373,8 @@ extern "C" int gr_points_normalize(float* points, int64_t m, const float* center
   if (!points) return GR_ERR_BAD_ARG;
   Center3 c;
   for (int a = 0; a < 3; ++a) c.c[a] = center3[a];
-  points_normalize_kernel<<<ceil_div(3 * m, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(points, (long long)m, c, scale,
-                                                                                            apply_scale);
+  GR_CHECK_CUDA(launch_pdl(points_normalize_kernel, dim3(ceil_div(3 * m, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), points, (long long)m, c, scale,
+                                                                                            apply_scale));
   GR_CHECK_LAUNCH("points_normalize_kernel");
   return GR_OK;
 }

@@ -33,6 +33,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <int BM, int BN, int BK, int TM, int TN, bool TRANSB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmParams
 // flight per CTA: these products are pure latency (a few dozen CTAs of work), not throughput.
 template <bool TRANSB>
 __global__ void __launch_bounds__(256) sgemm_small_kernel(GemmParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int BM = 32, BN = 32, BK = 32, G = 4, NT = 64;
   __shared__ __align__(16) float As[G][BK][BM + 4];
   __shared__ __align__(16) float Bs[G][BK][BN + 4];
@@ -253,6 +257,8 @@ __device__ __forceinline__ unsigned sm_lo_bits(float x) { return __float_as_uint
 
 template <bool TRANSB>
 __global__ void __launch_bounds__(128) gemm_mma_small_kernel(GemmParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int BM = 64, BN = 64, BK = 32;
   constexpr int PA = BK + 4;                       // A tile (and the (N,K) B tile): [64][36], conflict-free fragment reads
   constexpr int PB = TRANSB ? BK + 4 : BN + 8;     // (K,N) B tile: [32][72]
@@ -390,6 +396,8 @@ __device__ __forceinline__ void sm_cp_async4(void* dst, const void* src, int src
 // its panel is fetched with 4-byte cp.async instead
 template <bool TRANSB, bool A_VEC>
 __global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float tiny_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int PA = kq + 4;                     // A panel [32][kq + 4] (and the (N,K) B panel)
@@ -532,7 +540,7 @@ static int launch_tiny(const GemmParams& p, int batch, bool transb, cudaStream_t
 #define GR_TINY(TB, AV)                                                                                                  \
   do {                                                                                                                   \
     if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_mma_tiny_kernel<TB, AV>), (int)smem)); \
-    gemm_mma_tiny_kernel<TB, AV><<<grid, 128, smem, st>>>(p, kq);                                                        \
+    GR_CHECK_CUDA(launch_pdl(gemm_mma_tiny_kernel<TB, AV>, grid, dim3(128), smem, st, p, kq));                                                        \
   } while (0)
   if (transb) { if (a_vec) GR_TINY(true, true); else GR_TINY(true, false); }
   else { if (a_vec) GR_TINY(false, true); else GR_TINY(false, false); }
@@ -565,8 +573,8 @@ template <int BM, int BN, int BK, int TM, int TN>
 static int launch_sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
   constexpr int NT = (BM / TM) * (BN / TN);
-  if (transb) sgemm_kernel<BM, BN, BK, TM, TN, true><<<grid, NT, 0, st>>>(p);
-  else sgemm_kernel<BM, BN, BK, TM, TN, false><<<grid, NT, 0, st>>>(p);
+  if (transb) GR_CHECK_CUDA(launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, true>, dim3(grid), dim3(NT), (size_t)(0), st, p));
+  else GR_CHECK_CUDA(launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, false>, dim3(grid), dim3(NT), (size_t)(0), st, p));
   GR_CHECK_LAUNCH("sgemm_kernel");
   return GR_OK;
 }
@@ -582,8 +590,8 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
     // everything else that is 16-byte addressable: 64x64 tiles on mma.sync (3xTF32), cp.async double buffering
     if (mma_small_ok(p, transb)) {
       dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, batch);
-      if (transb) gemm_mma_small_kernel<true><<<grid, 128, 0, st>>>(p);
-      else gemm_mma_small_kernel<false><<<grid, 128, 0, st>>>(p);
+      if (transb) GR_CHECK_CUDA(launch_pdl(gemm_mma_small_kernel<true>, grid, dim3(128), 0, st, p));
+      else GR_CHECK_CUDA(launch_pdl(gemm_mma_small_kernel<false>, grid, dim3(128), 0, st, p));
       GR_CHECK_LAUNCH("gemm_mma_small_kernel");
       return GR_OK;
     }
@@ -596,8 +604,8 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
   if (ctas64 >= 148) return launch_sgemm<64, 64, 8, 4, 4>(p, batch, transb, st);
   {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
-    if (transb) sgemm_small_kernel<true><<<grid, 256, 0, st>>>(p);
-    else sgemm_small_kernel<false><<<grid, 256, 0, st>>>(p);
+    if (transb) GR_CHECK_CUDA(launch_pdl(sgemm_small_kernel<true>, dim3(grid), dim3(256), (size_t)(0), st, p));
+    else GR_CHECK_CUDA(launch_pdl(sgemm_small_kernel<false>, dim3(grid), dim3(256), (size_t)(0), st, p));
     GR_CHECK_LAUNCH("sgemm_small_kernel");
     return GR_OK;
   }

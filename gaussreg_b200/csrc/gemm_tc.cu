@@ -211,6 +211,8 @@ __device__ __forceinline__ void tile_epilogue(const Params& p, unsigned char* sm
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel(Params p) {
+  pdl_wait();
+  pdl_trigger();
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -409,6 +411,9 @@ __global__ void __launch_bounds__(kThreadsTma, BN == 64 ? 2 : 1) gemm_tf32x3_tma
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  // barriers, TMEM and the tensor-map prefetch are set up: only now wait for the producer of A / the residual
+  pdl_wait();
+  pdl_trigger();
 
   if (warp < 8) {
     // ------------------------------------------------------------------ low-part derivation, then the epilogue
@@ -508,6 +513,8 @@ __global__ void __launch_bounds__(kThreadsTma, BN == 64 ? 2 : 1) gemm_tf32x3_tma
 
 // C = epilogue(sum_z partial[z]) in a fixed order; one thread per 4 consecutive columns (N % 4 == 0)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, Params p) {
+  pdl_wait();
+  pdl_trigger();
   const int n4 = p.N >> 2;
   const long long total = (long long)p.M * n4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,6 +545,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // rows, folded in double in a fixed order -> gn_partial[blockIdx.x * G + g].
 constexpr int kRedRows = kGnReduceRows;
 __global__ void __launch_bounds__(256) splitk_reduce_gn_kernel(const float* __restrict__ partial, int splits, Params p, int col_chunk) {
+  pdl_wait();
+  pdl_trigger();
   // block (x, y): rows [32 x, 32 x + 32), columns [y * col_chunk, (y + 1) * col_chunk); col_chunk is a multiple of the
   // group width, so every group's statistics come from exactly one column block
   extern __shared__ double2 red_sh[];  // chs[col_chunk], then stage[R * col_chunk] when several row lanes share a column
@@ -611,7 +620,7 @@ static int launch(const Params& p, int batch, cudaStream_t st) {
   using C = Cfg<BN>;
   GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_kernel<BN>), C::kSmemBytes));
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(p);
+  GR_CHECK_CUDA(launch_pdl(gemm_tf32x3_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)(C::kSmemBytes), st, p));
   GR_CHECK_LAUNCH("gemm_tf32x3_kernel");
   return GR_OK;
 }
@@ -654,7 +663,7 @@ static int launch_tma(const Params& p, int zdim, cudaStream_t st) {
     return 1;
   GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_tma_kernel<BN>), C::kSmemBytes));
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, zdim);
-  gemm_tf32x3_tma_kernel<BN><<<grid, kThreadsTma, C::kSmemBytes, st>>>(tm, p);
+  GR_CHECK_CUDA(launch_pdl(gemm_tf32x3_tma_kernel<BN>, grid, dim3(kThreadsTma), (size_t)C::kSmemBytes, st, tm, p));
   GR_CHECK_LAUNCH("gemm_tf32x3_tma_kernel");
   return GR_OK;
 }
@@ -793,11 +802,11 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
           if (ensure_smem_attr(reinterpret_cast<const void*>(tc::splitk_reduce_gn_kernel), (int)smem) != cudaSuccess) return GR_ERR_CUDA;
         }
         dim3 rgrid(nblk, (N + col_chunk - 1) / col_chunk);
-        tc::splitk_reduce_gn_kernel<<<rgrid, 256, smem, st>>>(partial, splits, p, col_chunk);
+        if (launch_pdl(tc::splitk_reduce_gn_kernel, rgrid, dim3(256), smem, st, partial, splits, p, col_chunk) != cudaSuccess) rc = GR_ERR_CUDA;
         gn->nblk = nblk;
       } else {
         const long long total = (long long)M * (N / 4);
-        tc::splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, p);
+        if (launch_pdl(tc::splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, partial, splits, p) != cudaSuccess) rc = GR_ERR_CUDA;
       }
       count_launch();
       if (cudaGetLastError() != cudaSuccess) rc = GR_ERR_CUDA;

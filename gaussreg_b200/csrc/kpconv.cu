@@ -18,6 +18,8 @@ constexpr int kKP = 15;
 // flag[j] = (sum_c feat[j, c] > 0)   (kpconv.py:113-114); one warp per row
 __global__ void __launch_bounds__(256) row_positive_kernel(const float* __restrict__ feats, int n, int C,
                                                            unsigned char* __restrict__ flag) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int lane = threadIdx.x & 31;
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(128) kpconv_aggregate_kernel(
     const float* __restrict__ feats, int C, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
     const long long* __restrict__ idx, int H, long long ldi, int M, int Ns, const float* __restrict__ kp, float sigma,
     const unsigned char* __restrict__ pos_flag, float* __restrict__ A, float* __restrict__ row_div) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float smem[];
   constexpr int QPW = 32 / GROUP;  // queries per warp
   const int Hp = (H + 3) & ~3;
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(kAggThreads, S == 0 ? 4 : (S <= 4 ? 4 : 3)) kp
     const float* __restrict__ feats, int C, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
     const long long* __restrict__ idx, int H, long long ldi, int M, int Ns, const float* __restrict__ kp, float sigma,
     const unsigned char* __restrict__ pos_flag, float* __restrict__ A, float* __restrict__ row_div, int dbg_wrap) {
+  pdl_wait();
+  pdl_trigger();
   const int wpb = kAggThreads / 32;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   AggQuery Q;
@@ -378,6 +384,8 @@ __global__ void __launch_bounds__(kAggThreads, S <= 4 ? 4 : (S <= 6 ? 3 : 2)) kp
     const float* __restrict__ feats, int C, const float* __restrict__ q_pts, const float* __restrict__ s_pts,
     const long long* __restrict__ idx, int H, long long ldi, int M, int Ns, const float* __restrict__ kp, float sigma,
     const unsigned char* __restrict__ pos_flag, float* __restrict__ A, float* __restrict__ row_div) {
+  pdl_wait();
+  pdl_trigger();
   using L = AggCp<S>;
   constexpr int Hp = L::Hp, U = L::U;
   extern __shared__ __align__(16) float agg_smem[];
@@ -532,7 +540,7 @@ static int launch_aggregate_cp(const float* feats, int C, const float* q, const 
   const int wpb = kAggThreads / 32;
   int blocks = ceil_div(M, wpb);
   if (blocks > sms * per_sm) blocks = sms * per_sm;
-  kern<<<blocks, kAggThreads, L::kSmemBytes, st>>>(feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div);
+  GR_CHECK_CUDA(launch_pdl(kern, dim3(blocks), dim3(kAggThreads), (size_t)(L::kSmemBytes), st, feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div));
   GR_CHECK_LAUNCH("kpconv_aggregate_cp_kernel");
   return GR_OK;
 }
@@ -548,7 +556,7 @@ static int launch_aggregate_mma(const float* feats, int C, const float* q, const
   if (blocks > cap) blocks = cap;
   static int dbg = -2;
   if (dbg == -2) { const char* e = getenv("GAUSSREG_AGG_DEBUG_WRAP"); dbg = e ? atoi(e) : 0; }
-  kpconv_aggregate_mma_kernel<S><<<blocks, kAggThreads, 0, st>>>(feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div, dbg);
+  GR_CHECK_CUDA(launch_pdl(kpconv_aggregate_mma_kernel<S>, dim3(blocks), dim3(kAggThreads), (size_t)(0), st, feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div, dbg));
   GR_CHECK_LAUNCH("kpconv_aggregate_mma_kernel");
   return GR_OK;
 }
@@ -566,7 +574,7 @@ static int launch_aggregate(const float* feats, int C, const float* q, const flo
   auto kern = kpconv_aggregate_kernel<GROUP, CPL>;
   if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem));
   const int qpb = QPW * warps;
-  kern<<<ceil_div(M, qpb), warps * 32, smem, st>>>(feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div);
+  GR_CHECK_CUDA(launch_pdl(kern, dim3(ceil_div(M, qpb)), dim3(warps * 32), (size_t)(smem), st, feats, C, q, s, idx, H, ldi, M, Ns, kp, sigma, flag, A, row_div));
   GR_CHECK_LAUNCH("kpconv_aggregate_kernel");
   return GR_OK;
 }
@@ -590,7 +598,7 @@ extern "C" int gr_kpconv_aggregate(const float* s_feats, int C, const float* q_p
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* flag = static_cast<unsigned char*>(ws);
   if (Ns > 0) {
-    row_positive_kernel<<<ceil_div(Ns, 8), 256, 0, st>>>(s_feats, Ns, C, flag);
+    GR_CHECK_CUDA(launch_pdl(row_positive_kernel, dim3(ceil_div(Ns, 8)), dim3(256), (size_t)(0), st, s_feats, Ns, C, flag));
     GR_CHECK_LAUNCH("row_positive_kernel");
   }
   const long long* idx = reinterpret_cast<const long long*>(neighbor_idx);

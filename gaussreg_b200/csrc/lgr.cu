@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_correspondence_kernel(
     const float* __restrict__ ms, int K, int ld /* K or K+1 */, const unsigned char* __restrict__ ref_masks,
     const unsigned char* __restrict__ src_masks, int topk, float conf, int mutual, int* __restrict__ counts,
     int* __restrict__ cand_rc /* (P, K*topk) packed row<<16|col */, float* __restrict__ cand_score) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float e[];  // K x (K+1) exp scores (padded rows: conflict-free row and column walks)
   const int KP = K + 1;
   __shared__ int row_top[kLgrThreads][kLgrMaxPerRow];
@@ -226,6 +228,8 @@ __global__ void __launch_bounds__(128) lgr_compact_kernel(const int* __restrict_
                                                           const float* __restrict__ ref_knn_points, const float* __restrict__ src_knn_points,
                                                           int K, float* __restrict__ ref_corr, float* __restrict__ src_corr,
                                                           float* __restrict__ corr_scores, int* __restrict__ offsets, int* __restrict__ total) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int s_off;
   const int b = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -255,6 +259,8 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
                                                                      const float* __restrict__ corr_scores, const int* __restrict__ offsets,
                                                                      int P, int thr, float radius, float eps, float* __restrict__ T_local,
                                                                      int* __restrict__ inliers) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double sh[32];
   __shared__ float T[12];
   __shared__ int s_cnt;
@@ -290,6 +296,8 @@ __global__ void __launch_bounds__(1024) lgr_refine_kernel(const float* __restric
                                                           const float* __restrict__ T_local, const int* __restrict__ inliers, float radius,
                                                           float eps, int steps, float* __restrict__ w /* scratch, C */,
                                                           float* __restrict__ T_out /* 16 */, int* __restrict__ best_out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double sh[32];
   __shared__ float T[12];
   __shared__ int s_best;
@@ -335,6 +343,8 @@ __global__ void __launch_bounds__(1024) lgr_refine_kernel(const float* __restric
 __global__ void __launch_bounds__(kLgrThreads) procrustes_batched_kernel(const float* __restrict__ src, const float* __restrict__ ref,
                                                                          const float* __restrict__ w, int n, float eps,
                                                                          float* __restrict__ T_out /* (B,4,4) */) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double sh[32];
   __shared__ float T[12];
   const long long b = blockIdx.x;
@@ -389,17 +399,17 @@ extern "C" int gr_local_global_registration(const float* matching_scores, int P,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)K * (K + 1) * sizeof(float);
   if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(lgr_correspondence_kernel), (int)smem));
-  lgr_correspondence_kernel<<<P, kLgrThreads, smem, st>>>(matching_scores, K, ld, ref_knn_masks, src_knn_masks, topk,
-                                                           confidence_threshold, mutual, counts, cand_rc, cand_score);
+  GR_CHECK_CUDA(launch_pdl(lgr_correspondence_kernel, dim3(P), dim3(kLgrThreads), (size_t)(smem), st, matching_scores, K, ld, ref_knn_masks, src_knn_masks, topk,
+                                                           confidence_threshold, mutual, counts, cand_rc, cand_score));
   GR_CHECK_LAUNCH("lgr_correspondence_kernel");
-  lgr_compact_kernel<<<P, 128, 0, st>>>(counts, P, cap_pp, cand_rc, cand_score, ref_knn_points, src_knn_points, K, ref_corr_points,
-                                        src_corr_points, corr_scores, offsets, num_corr);
+  GR_CHECK_CUDA(launch_pdl(lgr_compact_kernel, dim3(P), dim3(128), (size_t)(0), st, counts, P, cap_pp, cand_rc, cand_score, ref_knn_points, src_knn_points, K, ref_corr_points,
+                                        src_corr_points, corr_scores, offsets, num_corr));
   GR_CHECK_LAUNCH("lgr_compact_kernel");
-  lgr_hypothesis_kernel<<<P, kLgrThreads, 0, st>>>(ref_corr_points, src_corr_points, corr_scores, offsets, P, correspondence_threshold,
-                                                   acceptance_radius, 1e-5f, T_local, inliers);
+  GR_CHECK_CUDA(launch_pdl(lgr_hypothesis_kernel, dim3(P), dim3(kLgrThreads), (size_t)(0), st, ref_corr_points, src_corr_points, corr_scores, offsets, P, correspondence_threshold,
+                                                   acceptance_radius, 1e-5f, T_local, inliers));
   GR_CHECK_LAUNCH("lgr_hypothesis_kernel");
-  lgr_refine_kernel<<<1, 1024, 0, st>>>(ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers, acceptance_radius,
-                                        1e-5f, num_refinement_steps, w, transform, counts + P);
+  GR_CHECK_CUDA(launch_pdl(lgr_refine_kernel, dim3(1), dim3(1024), (size_t)(0), st, ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers, acceptance_radius,
+                                        1e-5f, num_refinement_steps, w, transform, counts + P));
   GR_CHECK_LAUNCH("lgr_refine_kernel");
   return GR_OK;
 }
@@ -410,7 +420,7 @@ extern "C" int gr_weighted_procrustes(const float* src_points, const float* ref_
   if (B < 0 || n <= 0) return GR_ERR_BAD_ARG;
   if (B == 0) return GR_OK;
   if (!src_points || !ref_points || !weights || !transforms) return GR_ERR_BAD_ARG;
-  procrustes_batched_kernel<<<B, kLgrThreads, 0, static_cast<cudaStream_t>(stream)>>>(src_points, ref_points, weights, n, eps, transforms);
+  GR_CHECK_CUDA(launch_pdl(procrustes_batched_kernel, dim3(B), dim3(kLgrThreads), (size_t)(0), static_cast<cudaStream_t>(stream), src_points, ref_points, weights, n, eps, transforms));
   GR_CHECK_LAUNCH("procrustes_batched_kernel");
   return GR_OK;
 }

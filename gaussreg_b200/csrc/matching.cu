@@ -14,6 +14,8 @@ namespace gr {
 __global__ void __launch_bounds__(256) match_exp_rows_kernel(float* __restrict__ S, int Nr, int Ns,
                                                              const unsigned char* __restrict__ rmask,
                                                              const unsigned char* __restrict__ smask, float* __restrict__ rowsum) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= Nr) return;
   const int lane = threadIdx.x & 31;
@@ -30,6 +32,8 @@ __global__ void __launch_bounds__(256) match_exp_rows_kernel(float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) match_colsum_kernel(const float* __restrict__ S, int Nr, int Ns, float* __restrict__ colsum) {
+  pdl_wait();
+  pdl_trigger();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Ns) return;
   float s = 0.f;
@@ -42,6 +46,8 @@ __global__ void __launch_bounds__(256) match_keys_kernel(const float* __restrict
                                                          const float* __restrict__ rowsum, const float* __restrict__ colsum,
                                                          const unsigned char* __restrict__ rmask, const unsigned char* __restrict__ smask,
                                                          int dual, unsigned long long* __restrict__ keys, int* __restrict__ n_valid) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) {
     int a = 0, b = 0;
@@ -66,6 +72,8 @@ constexpr int kTopChunk = 2048;
 // each CTA sorts a chunk of 2048 keys (descending) in shared memory and keeps the first `keep`
 __global__ void __launch_bounds__(1024) topk_chunk_kernel(const unsigned long long* __restrict__ in, long long n, int keep,
                                                           unsigned long long* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned long long sh[kTopChunk];
   const long long base = (long long)blockIdx.x * kTopChunk;
   for (int i = threadIdx.x; i < kTopChunk; i += blockDim.x) sh[i] = (base + i < n) ? in[base + i] : 0ull;
@@ -88,6 +96,8 @@ __global__ void __launch_bounds__(1024) topk_chunk_kernel(const unsigned long lo
 __global__ void match_decode_kernel(const unsigned long long* __restrict__ keys, int k, int Ns, const int* __restrict__ n_valid,
                                     long long* __restrict__ ref_idx, long long* __restrict__ src_idx, float* __restrict__ scores,
                                     int* __restrict__ count) {
+  pdl_wait();
+  pdl_trigger();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = min(k, *n_valid);
   if (t == 0) *count = c;
@@ -254,41 +264,41 @@ __device__ __forceinline__ void sinkhorn_lse_pass128(const float* __restrict__ p
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
     for (int r = 0; r < 8; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
-  if (!FIRST) {
-    // The shift is the previous iterate's log-sum-exp.  Should every term of a line flush to zero (or the sum leave the
-    // fp32 range) -- possible for trained weights with |scores| >> 10 -- redo that line with its true maximum.  All
-    // lanes hold identical totals, so the branch is warp-uniform; it never triggers on O(10) scores.
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (live[r] && !(sm[r] > 1e-30f && sm[r] < 1e30f)) {
-        const int i = ibase + 16 * r;
-        float m = lane == 0 ? ps[i * si + K * sj] + ad : -INFINITY;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) m = fmaxf(m, ps[i * si + (lane + 32 * t) * sj] + a[t]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float s2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float arg = ps[i * si + (lane + 32 * t) * sj] + a[t] - m;
-          s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
-        }
-        if (lane == 0) {
-          const float arg = ps[i * si + K * sj] + ad - m;
-          s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        sm[r] = s2; shift[r] = m;
-      }
-    }
-  }
   // lane r finishes line r (every lane holds all eight totals)
   float my_sum = sm[0], my_shift = shift[0];
   bool my_live = live[0];
 #pragma unroll
   for (int r = 1; r < 8; ++r)
     if (lane == r) { my_sum = sm[r]; my_shift = shift[r]; my_live = live[r]; }
+  if (!FIRST) {
+    // The shift is the previous iterate's log-sum-exp.  Should every term of a line flush to zero (or the sum leave the
+    // fp32 range) -- possible for trained weights with |scores| >> 10 -- that line is redone with its true maximum by the
+    // whole warp.  One ballot per pass; it never fires on O(10) scores.
+    unsigned bad = __ballot_sync(0xffffffffu, lane < nl && my_live && !(my_sum > 1e-30f && my_sum < 1e30f));
+    while (bad) {
+      const int r = __ffs(bad) - 1;
+      bad &= bad - 1;
+      const int i = ibase + 16 * r;
+      float m = lane == 0 ? ps[i * si + K * sj] + ad : -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) m = fmaxf(m, ps[i * si + (lane + 32 * t) * sj] + a[t]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float arg = ps[i * si + (lane + 32 * t) * sj] + a[t] - m;
+        s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+      }
+      if (lane == 0) {
+        const float arg = ps[i * si + K * sj] + ad - m;
+        s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == r) { my_sum = s2; my_shift = m; }
+    }
+  }
   if (lane < nl) {
     const int i = ibase + 16 * lane;
     out[i] = my_live ? bias[i] - ((EXP2 ? log2f(my_sum) : logf(my_sum)) + my_shift) : 0.f;
@@ -301,6 +311,8 @@ template <bool FAST128, bool EXP2 = false>
 __global__ void __launch_bounds__(FAST128 ? kSink128Threads : kSinkThreads, FAST128 ? 2 : 1) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
                                                        const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
                                                        int K, int iters, float inf, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int K1 = K + 1;
   float* ps = sm;               // K1*K1
@@ -412,23 +424,23 @@ extern "C" int gr_superpoint_matching(float* xy, int Nr, int Ns, const uint8_t* 
   int* n_valid = c.take<int>(4);
   if (!ws || !c.ok) return GR_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  match_exp_rows_kernel<<<ceil_div(Nr, 8), 256, 0, st>>>(xy, Nr, Ns, ref_masks, src_masks, rowsum);
+  GR_CHECK_CUDA(launch_pdl(match_exp_rows_kernel, dim3(ceil_div(Nr, 8)), dim3(256), (size_t)(0), st, xy, Nr, Ns, ref_masks, src_masks, rowsum));
   GR_CHECK_LAUNCH("match_exp_rows_kernel");
-  match_colsum_kernel<<<ceil_div(Ns, 256), 256, 0, st>>>(xy, Nr, Ns, colsum);
+  GR_CHECK_CUDA(launch_pdl(match_colsum_kernel, dim3(ceil_div(Ns, 256)), dim3(256), (size_t)(0), st, xy, Nr, Ns, colsum));
   GR_CHECK_LAUNCH("match_colsum_kernel");
-  match_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xy, Nr, Ns, rowsum, colsum, ref_masks, src_masks, dual_normalization, keys, n_valid);
+  GR_CHECK_CUDA(launch_pdl(match_keys_kernel, dim3(ceil_div(n, 256)), dim3(256), (size_t)(0), st, xy, Nr, Ns, rowsum, colsum, ref_masks, src_masks, dual_normalization, keys, n_valid));
   GR_CHECK_LAUNCH("match_keys_kernel");
   const unsigned long long* cur = keys;
   long long cur_n = n;
   for (int l = 0; l < nl; ++l) {
-    topk_chunk_kernel<<<ceil_div(cur_n, kTopChunk), 1024, 0, st>>>(cur, cur_n, k, level[l]);
+    GR_CHECK_CUDA(launch_pdl(topk_chunk_kernel, dim3(ceil_div(cur_n, kTopChunk)), dim3(1024), (size_t)(0), st, cur, cur_n, k, level[l]));
     GR_CHECK_LAUNCH("topk_chunk_kernel");
     cur = level[l]; cur_n = level_n[l];
   }
-  topk_chunk_kernel<<<1, 1024, 0, st>>>(cur, cur_n, k, fin);
+  GR_CHECK_CUDA(launch_pdl(topk_chunk_kernel, dim3(1), dim3(1024), (size_t)(0), st, cur, cur_n, k, fin));
   GR_CHECK_LAUNCH("topk_chunk_kernel");
-  match_decode_kernel<<<ceil_div(k, 256), 256, 0, st>>>(fin, k, Ns, n_valid, reinterpret_cast<long long*>(ref_idx),
-                                                        reinterpret_cast<long long*>(src_idx), scores, count);
+  GR_CHECK_CUDA(launch_pdl(match_decode_kernel, dim3(ceil_div(k, 256)), dim3(256), (size_t)(0), st, fin, k, Ns, n_valid, reinterpret_cast<long long*>(ref_idx),
+                                                        reinterpret_cast<long long*>(src_idx), scores, count));
   GR_CHECK_LAUNCH("match_decode_kernel");
   return GR_OK;
 }
@@ -447,16 +459,16 @@ extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const 
   if (exp2_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN_EXP2"); exp2_knob = e ? atoi(e) : 1; }  // measured: 0.63 -> 0.52 ms
   if (K == 128 && fast_knob && exp2_knob) {
     GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<true, true>), (int)smem));
-    sinkhorn_kernel<true, true><<<P, kSink128Threads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha,
-                                                                                                K, num_iterations, inf, out);
+    GR_CHECK_CUDA(launch_pdl(sinkhorn_kernel<true, true>, dim3(P), dim3(kSink128Threads), (size_t)(smem), static_cast<cudaStream_t>(stream), scores, row_masks, col_masks, alpha,
+                                                                                                K, num_iterations, inf, out));
   } else if (K == 128 && fast_knob) {
     GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<true>), (int)smem));
-    sinkhorn_kernel<true><<<P, kSink128Threads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
-                                                                                          num_iterations, inf, out);
+    GR_CHECK_CUDA(launch_pdl(sinkhorn_kernel<true>, dim3(P), dim3(kSink128Threads), (size_t)(smem), static_cast<cudaStream_t>(stream), scores, row_masks, col_masks, alpha, K,
+                                                                                          num_iterations, inf, out));
   } else {
     if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<false>), (int)smem));
-    sinkhorn_kernel<false><<<P, kSinkThreads, smem, static_cast<cudaStream_t>(stream)>>>(scores, row_masks, col_masks, alpha, K,
-                                                                                         num_iterations, inf, out);
+    GR_CHECK_CUDA(launch_pdl(sinkhorn_kernel<false>, dim3(P), dim3(kSinkThreads), (size_t)(smem), static_cast<cudaStream_t>(stream), scores, row_masks, col_masks, alpha, K,
+                                                                                         num_iterations, inf, out));
   }
   GR_CHECK_LAUNCH("sinkhorn_kernel");
   return GR_OK;

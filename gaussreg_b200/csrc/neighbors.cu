@@ -33,6 +33,8 @@ struct BBox {
 __global__ void prep_offsets_kernel(const int64_t* __restrict__ len_a, int* __restrict__ off_a,
                                     const int64_t* __restrict__ len_b, int* __restrict__ off_b, int batch,
                                     BBox* __restrict__ bbox, int* __restrict__ scalars, int n_scalars) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) {
     int64_t acc = 0;
     off_a[0] = 0;
@@ -55,6 +57,8 @@ __global__ void prep_offsets_kernel(const int64_t* __restrict__ len_a, int* __re
 // per-cloud min / max corner (strict comparisons in the reference == plain min/max here)
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ pts, const int* __restrict__ off, int batch,
                                                    BBox* __restrict__ bbox) {
+  pdl_wait();
+  pdl_trigger();
   const int n = off[batch];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
@@ -101,6 +105,8 @@ struct CellGrid {
 
 __global__ void cell_geometry_kernel(const BBox* __restrict__ bbox, const int* __restrict__ s_off, int batch,
                                      float radius, CellGrid* __restrict__ grids) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   CellGrid g;
@@ -140,6 +146,8 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const float* __restrict
                                                          int batch, const CellGrid* __restrict__ grids,
                                                          uint32_t* __restrict__ cell_cnt, int* __restrict__ cell_of,
                                                          int* __restrict__ rank_of) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s_off[batch]) return;
   const int b = find_segment(s_off, batch, i);
@@ -156,6 +164,8 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const float* __restri
                                                            int batch, const uint32_t* __restrict__ cell_start,
                                                            const int* __restrict__ cell_of, const int* __restrict__ rank_of,
                                                            float4* __restrict__ sorted) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s_off[batch]) return;
   const uint32_t p = cell_start[cell_of[i]] + (uint32_t)rank_of[i];
@@ -176,6 +186,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32) radius_search_kernel(
     const float* __restrict__ q, const float4* __restrict__ sorted, const uint32_t* __restrict__ cell_start,
     const CellGrid* __restrict__ grids, const int* __restrict__ q_off, const int* __restrict__ s_off, int batch, float r2,
     long long* __restrict__ out, long long ld, int* __restrict__ max_count) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned long long sh_hits[kSearchWarps][kHitCap];
   __shared__ int sh_max;
   if (threadIdx.x == 0) sh_max = 0;
@@ -345,6 +357,8 @@ struct VoxelGeom {
 
 __global__ void voxel_geometry_kernel(const BBox* __restrict__ bbox, const int* __restrict__ off, int batch, float voxel,
                                       float inv_voxel, VoxelGeom* __restrict__ geom) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   VoxelGeom g;
@@ -384,6 +398,8 @@ __global__ void __launch_bounds__(256) voxel_insert_kernel(const float* __restri
                                                            unsigned long long* __restrict__ tab_key,
                                                            int* __restrict__ tab_first, uint32_t* __restrict__ tab_cnt,
                                                            int* __restrict__ slot_of) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= off[batch]) return;
   const int b = find_segment(off, batch, i);
@@ -413,6 +429,8 @@ __global__ void __launch_bounds__(256) voxel_insert_kernel(const float* __restri
 __global__ void __launch_bounds__(256) voxel_flag_kernel(const int* __restrict__ off, int batch,
                                                          const int* __restrict__ tab_first, const int* __restrict__ slot_of,
                                                          uint32_t* __restrict__ flag, int n_cap) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n_cap) return;
   flag[i] = (i < off[batch] && tab_first[slot_of[i]] == i) ? 1u : 0u;
@@ -426,6 +444,8 @@ __global__ void __launch_bounds__(256) voxel_init_kernel(const float* __restrict
                                                          unsigned long long* __restrict__ vkey, uint32_t* __restrict__ vcnt,
                                                          int64_t* __restrict__ out_lengths, int64_t* __restrict__ out_total,
                                                          int n_cap) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = off[batch];
   if (i <= batch) {
@@ -447,6 +467,8 @@ __global__ void __launch_bounds__(256) voxel_scatter_kernel(const int* __restric
                                                             const int* __restrict__ slot_of, const int* __restrict__ tab_vid,
                                                             const uint32_t* __restrict__ voff, uint32_t* __restrict__ vfill,
                                                             int* __restrict__ plist) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= off[batch]) return;
   const int v = tab_vid[slot_of[i]];
@@ -460,6 +482,8 @@ __global__ void __launch_bounds__(128) voxel_barycenter_kernel(const float* __re
                                                                int batch, const uint32_t* __restrict__ fscan,
                                                                const uint32_t* __restrict__ voff, int* __restrict__ plist,
                                                                float* __restrict__ bary) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nv = fscan[off[batch]];
   if (v >= nv) return;
@@ -605,6 +629,8 @@ __global__ void __launch_bounds__(kReplayThreads, 1) hash_order_replay_kernel(
     const int* __restrict__ off, int batch, const uint32_t* __restrict__ fscan, const unsigned long long* __restrict__ vkey,
     const float* __restrict__ bary, unsigned int* g_list0, unsigned int* g_list1, unsigned int* g_w, unsigned int* g_tmp,
     unsigned int* g_bkc, unsigned int* g_ft, unsigned int* g_cn, unsigned int* g_fill, float* __restrict__ out_points) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ unsigned int smem[];
   __shared__ unsigned int sh_scan[33];
   const int b = blockIdx.x / CL;
@@ -764,43 +790,41 @@ extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_
   GR_CHECK_CUDA(cudaMemsetAsync(out_max_count, 0, sizeof(int32_t), st));
   if (reuse_grid) {
     // only the query offsets change (the bounding boxes this kernel resets are not needed once the grid exists)
-    prep_offsets_kernel<<<1, 256, 0, st>>>(q_lengths, w.q_off, nullptr, nullptr, batch, w.bbox, w.scalars, 8);
+    GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, q_lengths, w.q_off, nullptr, nullptr, batch, w.bbox, w.scalars, 8));
     GR_CHECK_LAUNCH("prep_offsets_kernel");
     if (nq > 0) {
       const float r2 = radius * radius;
-      radius_search_kernel<<<ceil_div(nq, kSearchWarps), kSearchWarps * 32, 0, st>>>(
-          q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
-          (long long)ld, out_max_count);
+      GR_CHECK_CUDA(launch_pdl(radius_search_kernel, dim3(ceil_div(nq, kSearchWarps)), dim3(kSearchWarps * 32), (size_t)(0), st, q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
+          (long long)ld, out_max_count));
       GR_CHECK_LAUNCH("radius_search_kernel");
     }
     return GR_OK;
   }
   GR_CHECK_CUDA(cudaMemsetAsync(w.cell_cnt, 0, ncell * sizeof(uint32_t), st));
-  prep_offsets_kernel<<<1, 256, 0, st>>>(q_lengths, w.q_off, s_lengths, w.s_off, batch, w.bbox, w.scalars, 8);
+  GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, q_lengths, w.q_off, s_lengths, w.s_off, batch, w.bbox, w.scalars, 8));
   GR_CHECK_LAUNCH("prep_offsets_kernel");
   if (ns > 0) {
-    bbox_kernel<<<ceil_div(ns, 256), 256, 0, st>>>(s_points, w.s_off, batch, w.bbox);
+    GR_CHECK_CUDA(launch_pdl(bbox_kernel, dim3(ceil_div(ns, 256)), dim3(256), (size_t)(0), st, s_points, w.s_off, batch, w.bbox));
     GR_CHECK_LAUNCH("bbox_kernel");
   }
-  cell_geometry_kernel<<<ceil_div(batch, 128), 128, 0, st>>>(w.bbox, w.s_off, batch, radius, w.grids);
+  GR_CHECK_CUDA(launch_pdl(cell_geometry_kernel, dim3(ceil_div(batch, 128)), dim3(128), (size_t)(0), st, w.bbox, w.s_off, batch, radius, w.grids));
   GR_CHECK_LAUNCH("cell_geometry_kernel");
   if (ns > 0) {
-    cell_count_kernel<<<ceil_div(ns, 256), 256, 0, st>>>(s_points, w.s_off, batch, w.grids, w.cell_cnt, w.cell_of,
-                                                         w.rank_of);
+    GR_CHECK_CUDA(launch_pdl(cell_count_kernel, dim3(ceil_div(ns, 256)), dim3(256), (size_t)(0), st, s_points, w.s_off, batch, w.grids, w.cell_cnt, w.cell_of,
+                                                         w.rank_of));
     GR_CHECK_LAUNCH("cell_count_kernel");
   }
   int rc = exclusive_scan_u32(w.cell_cnt, w.cell_cnt, (int64_t)ncell, w.scan_ws, st);
   if (rc != GR_OK) return rc;
   if (ns > 0) {
-    cell_scatter_kernel<<<ceil_div(ns, 256), 256, 0, st>>>(s_points, w.s_off, batch, w.cell_cnt, w.cell_of, w.rank_of,
-                                                           w.sorted);
+    GR_CHECK_CUDA(launch_pdl(cell_scatter_kernel, dim3(ceil_div(ns, 256)), dim3(256), (size_t)(0), st, s_points, w.s_off, batch, w.cell_cnt, w.cell_of, w.rank_of,
+                                                           w.sorted));
     GR_CHECK_LAUNCH("cell_scatter_kernel");
   }
   if (nq > 0) {
     const float r2 = radius * radius;  // radius_neighbors_cpu.cpp:12 (host float multiply, one rounding)
-    radius_search_kernel<<<ceil_div(nq, kSearchWarps), kSearchWarps * 32, 0, st>>>(
-        q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
-        (long long)ld, out_max_count);
+    GR_CHECK_CUDA(launch_pdl(radius_search_kernel, dim3(ceil_div(nq, kSearchWarps)), dim3(kSearchWarps * 32), (size_t)(0), st, q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
+        (long long)ld, out_max_count));
     GR_CHECK_LAUNCH("radius_search_kernel");
   }
   return GR_OK;
@@ -840,34 +864,33 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
   // the scan below walks all n + 1 capacity slots of vcnt; only the first (number of voxels) + 1 are written by
   // voxel_init_kernel -- clear the tail so that no kernel reads uninitialised memory (initcheck-clean)
   GR_CHECK_CUDA(cudaMemsetAsync(w.vcnt, 0, ((size_t)n + 2) * sizeof(uint32_t), st));
-  prep_offsets_kernel<<<1, 256, 0, st>>>(lengths, w.off, nullptr, nullptr, batch, w.bbox, w.scalars, 8);
+  GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, lengths, w.off, nullptr, nullptr, batch, w.bbox, w.scalars, 8));
   GR_CHECK_LAUNCH("prep_offsets_kernel");
   if (n > 0) {
-    bbox_kernel<<<ceil_div(n, 256), 256, 0, st>>>(points, w.off, batch, w.bbox);
+    GR_CHECK_CUDA(launch_pdl(bbox_kernel, dim3(ceil_div(n, 256)), dim3(256), (size_t)(0), st, points, w.off, batch, w.bbox));
     GR_CHECK_LAUNCH("bbox_kernel");
   }
   const float inv_voxel = (float)(1.0 / (double)voxel_size);  // "1. / voxel_size" narrowed by cloud.h:83
-  voxel_geometry_kernel<<<ceil_div(batch, 128), 128, 0, st>>>(w.bbox, w.off, batch, voxel_size, inv_voxel, w.geom);
+  GR_CHECK_CUDA(launch_pdl(voxel_geometry_kernel, dim3(ceil_div(batch, 128)), dim3(128), (size_t)(0), st, w.bbox, w.off, batch, voxel_size, inv_voxel, w.geom));
   GR_CHECK_LAUNCH("voxel_geometry_kernel");
   if (n > 0) {
-    voxel_insert_kernel<<<ceil_div(n, 256), 256, 0, st>>>(points, w.off, batch, w.geom, w.tab_key, w.tab_first, w.tab_cnt,
-                                                          w.slot_of);
+    GR_CHECK_CUDA(launch_pdl(voxel_insert_kernel, dim3(ceil_div(n, 256)), dim3(256), (size_t)(0), st, points, w.off, batch, w.geom, w.tab_key, w.tab_first, w.tab_cnt,
+                                                          w.slot_of));
     GR_CHECK_LAUNCH("voxel_insert_kernel");
   }
-  voxel_flag_kernel<<<blocks, 256, 0, st>>>(w.off, batch, w.tab_first, w.slot_of, w.fscan, n);
+  GR_CHECK_CUDA(launch_pdl(voxel_flag_kernel, dim3(blocks), dim3(256), (size_t)(0), st, w.off, batch, w.tab_first, w.slot_of, w.fscan, n));
   GR_CHECK_LAUNCH("voxel_flag_kernel");
   int rc = exclusive_scan_u32(w.fscan, w.fscan, (int64_t)n + 1, w.scan_ws, st);
   if (rc != GR_OK) return rc;
-  voxel_init_kernel<<<ceil_div((int64_t)max(n, batch + 1), 256), 256, 0, st>>>(
-      points, w.off, batch, w.geom, w.fscan, w.tab_first, w.tab_cnt, w.slot_of, w.tab_vid, w.vkey, w.vcnt, out_lengths,
-      out_total, n);
+  GR_CHECK_CUDA(launch_pdl(voxel_init_kernel, dim3(ceil_div((int64_t)max(n, batch + 1), 256)), dim3(256), (size_t)(0), st, points, w.off, batch, w.geom, w.fscan, w.tab_first, w.tab_cnt, w.slot_of, w.tab_vid, w.vkey, w.vcnt, out_lengths,
+      out_total, n));
   GR_CHECK_LAUNCH("voxel_init_kernel");
   if (n == 0) return GR_OK;
   rc = exclusive_scan_u32(w.vcnt, w.vcnt, (int64_t)n + 1, w.scan_ws, st);
   if (rc != GR_OK) return rc;
-  voxel_scatter_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.off, batch, w.slot_of, w.tab_vid, w.vcnt, w.vfill, w.plist);
+  GR_CHECK_CUDA(launch_pdl(voxel_scatter_kernel, dim3(ceil_div(n, 256)), dim3(256), (size_t)(0), st, w.off, batch, w.slot_of, w.tab_vid, w.vcnt, w.vfill, w.plist));
   GR_CHECK_LAUNCH("voxel_scatter_kernel");
-  voxel_barycenter_kernel<<<ceil_div(n, 128), 128, 0, st>>>(points, w.off, batch, w.fscan, w.vcnt, w.plist, w.bary);
+  GR_CHECK_CUDA(launch_pdl(voxel_barycenter_kernel, dim3(ceil_div(n, 128)), dim3(128), (size_t)(0), st, points, w.off, batch, w.fscan, w.vcnt, w.plist, w.bary));
   GR_CHECK_LAUNCH("voxel_barycenter_kernel");
   {
     // clouds that may exceed the shared-memory phases get a cluster of kReplayCluster CTAs each
@@ -890,8 +913,8 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
                                        (const uint32_t*)w.fscan, (const unsigned long long*)w.vkey, (const float*)w.bary, w.list0,
                                        w.list1, w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points));
     } else {
-      hash_order_replay_kernel<1><<<batch, kReplayThreads, smem, st>>>(w.off, batch, w.fscan, w.vkey, w.bary, w.list0, w.list1,
-                                                                        w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points);
+      GR_CHECK_CUDA(launch_pdl(hash_order_replay_kernel<1>, dim3(batch), dim3(kReplayThreads), (size_t)(smem), st, w.off, batch, w.fscan, w.vkey, w.bary, w.list0, w.list1,
+                                                                        w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points));
     }
   }
   GR_CHECK_LAUNCH("hash_order_replay_kernel");

@@ -21,6 +21,8 @@ __host__ __device__ inline int gn_rows_per_block(long long n_rows) {
 // thread bits walk rows.  Per-thread accumulation in fp32 over at most a few dozen values, then double.
 __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const float* __restrict__ x, int N, int C, int G,
                                                                 int rows_per_block, double2* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double2 sh[];  // [max(C, 256)]
   const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
   const int tid = threadIdx.x;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const float* __r
 // stats[g] = (mean, rstd); one CTA per group, fixed-order tree over the block partials
 __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const double2* __restrict__ partial, int nblk, int G, long long count,
                                                                  float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double shs[8], shq[8];
   const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s = 0.0, q = 0.0;
@@ -94,6 +98,8 @@ __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const double2* 
 // span a row, the remaining thread bits walk rows.  fp32 accumulation over at most 32 rows, then double.
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, int N, int C, int G, int rows_per_block,
                                                               double2* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double2 sh[];  // chs[C] channel sums, then stage[R * C] when several row lanes share a channel
   double2* chs = sh;
   double2* stage = sh + C;
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
                                                               const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ add,
                                                               int act, float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const int c4 = C >> 2, cg = C / G;
   const long long total4 = (long long)n_rows * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -181,6 +189,8 @@ __global__ void __launch_bounds__(kGnSmallThreads) groupnorm_small_kernel(const 
                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                         float eps, const float* __restrict__ add, int act,
                                                                         float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double shs[32], shq[32];
   __shared__ float s_stats[2];
   const int g = blockIdx.x;
@@ -248,6 +258,8 @@ __global__ void __launch_bounds__(kGnSmallThreads) groupnorm_small_kernel(const 
 __global__ void __launch_bounds__(256) layernorm_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows,
                                                             int C, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -303,7 +315,7 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
   {
     const int cg = C / groups;
     if (small_knob && cg % 8 == 0 && cg / 4 <= kGnSmallThreads && (long long)n_rows * C * 4 <= (16ll << 20)) {
-      groupnorm_small_kernel<<<groups, kGnSmallThreads, 0, st>>>(x, (int)n_rows, C, groups, gamma, beta, eps, add, act, y);
+      GR_CHECK_CUDA(launch_pdl(groupnorm_small_kernel, dim3(groups), dim3(kGnSmallThreads), (size_t)(0), st, x, (int)n_rows, C, groups, gamma, beta, eps, add, act, y));
       GR_CHECK_LAUNCH("groupnorm_small_kernel");
       return GR_OK;
     }
@@ -313,21 +325,21 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
   if (variant == 0) {
     const size_t smem = (size_t)(C > 256 ? C : 256) * sizeof(double2);
     if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(groupnorm_partial_kernel), (int)smem));
-    groupnorm_partial_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
+    GR_CHECK_CUDA(launch_pdl(groupnorm_partial_kernel, dim3(nblk), dim3(256), (size_t)(smem), st, x, (int)n_rows, C, groups, rpb, partial));
     GR_CHECK_LAUNCH("groupnorm_partial_kernel");
   } else {
     const int lanes = (C / 4) < 256 ? (C / 4) : 256;
     const int R = 256 / lanes;
     const size_t smem = ((size_t)C + (R > 1 ? (size_t)R * C : 0)) * sizeof(double2);
     GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(groupnorm_stats_kernel), 96 * 1024));
-    groupnorm_stats_kernel<<<nblk, 256, smem, st>>>(x, (int)n_rows, C, groups, rpb, partial);
+    GR_CHECK_CUDA(launch_pdl(groupnorm_stats_kernel, dim3(nblk), dim3(256), (size_t)(smem), st, x, (int)n_rows, C, groups, rpb, partial));
     GR_CHECK_LAUNCH("groupnorm_stats_kernel");
   }
-  groupnorm_finalize_kernel<<<groups, 256, 0, st>>>(partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_finalize_kernel, dim3(groups), dim3(256), 0, st, partial, nblk, groups, (long long)n_rows * (C / groups), eps, stats));
   GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
   const long long total4 = (long long)n_rows * (C / 4);
   const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
-  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_apply_kernel, dim3(blocks), dim3(256), 0, st, x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y));
   GR_CHECK_LAUNCH("groupnorm_apply_kernel");
   return GR_OK;
 }
@@ -338,11 +350,11 @@ int group_norm_from_partial(const float* x, long long n_rows, int C, int groups,
                             float2* stats, void* stream) {
   if (n_rows <= 0) return GR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  groupnorm_finalize_kernel<<<groups, 256, 0, st>>>(partial, nblk, groups, n_rows * (long long)(C / groups), eps, stats);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_finalize_kernel, dim3(groups), dim3(256), 0, st, partial, nblk, groups, n_rows * (long long)(C / groups), eps, stats));
   GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
   const long long total4 = n_rows * (long long)(C / 4);
   const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
-  groupnorm_apply_kernel<<<blocks, 256, 0, st>>>(x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_apply_kernel, dim3(blocks), dim3(256), 0, st, x, (int)n_rows, C, groups, stats, gamma, beta, add, act, y));
   GR_CHECK_LAUNCH("groupnorm_apply_kernel");
   return GR_OK;
 }
@@ -354,7 +366,7 @@ extern "C" int gr_layer_norm_add(const float* a, const float* b, int64_t rows, i
   if (rows < 0 || C <= 0 || C % 32 != 0 || C > 1024) return GR_ERR_BAD_ARG;
   if (rows == 0) return GR_OK;
   if (!a || !y || !gamma || !beta) return GR_ERR_BAD_ARG;
-  layernorm_add_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, (int)rows, C, gamma, beta, eps, y);
+  GR_CHECK_CUDA(launch_pdl(layernorm_add_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), a, b, (int)rows, C, gamma, beta, eps, y));
   GR_CHECK_LAUNCH("layernorm_add_kernel");
   return GR_OK;
 }

@@ -31,6 +31,8 @@ __device__ __forceinline__ void locate(const PairMap& m, long long r, int* pair,
 
 __global__ void __launch_bounds__(256) pair_major_rows_kernel(const float* __restrict__ in, int C, long long n_rows, PairMap q,
                                                               float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_rows * C) return;
   const long long r = t / C;
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(256) pair_major_rows_kernel(const float* __res
 __global__ void __launch_bounds__(256) pair_major_table_kernel(const long long* __restrict__ in, long long ld, int W, long long n_rows,
                                                                PairMap q, PairMap s, long long* __restrict__ out,
                                                                int* __restrict__ widths) {
+  pdl_wait();
+  pdl_trigger();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -80,7 +84,7 @@ extern "C" int gr_pair_major_rows(const float* in, int C, int64_t n_rows, const 
   if (n_rows == 0) return GR_OK;
   if (!in || !out) return GR_ERR_BAD_ARG;
   PairMap q{reinterpret_cast<const long long*>(ref_off), reinterpret_cast<const long long*>(src_off), P};
-  pair_major_rows_kernel<<<ceil_div(n_rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, C, (long long)n_rows, q, out);
+  GR_CHECK_CUDA(launch_pdl(pair_major_rows_kernel, dim3(ceil_div(n_rows * C, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), in, C, (long long)n_rows, q, out));
   GR_CHECK_LAUNCH("pair_major_rows_kernel");
   return GR_OK;
 }
@@ -100,8 +104,8 @@ extern "C" int gr_pair_major_table(const int64_t* in, int64_t ld, int W, int64_t
   if (!in || !out) return GR_ERR_BAD_ARG;
   PairMap q{reinterpret_cast<const long long*>(q_ref_off), reinterpret_cast<const long long*>(q_src_off), P};
   PairMap s{reinterpret_cast<const long long*>(s_ref_off), reinterpret_cast<const long long*>(s_src_off), P};
-  pair_major_table_kernel<<<ceil_div(n_rows, 8), 256, 0, st>>>(reinterpret_cast<const long long*>(in), (long long)ld, W,
-                                                               (long long)n_rows, q, s, reinterpret_cast<long long*>(out), widths);
+  GR_CHECK_CUDA(launch_pdl(pair_major_table_kernel, dim3(ceil_div(n_rows, 8)), dim3(256), (size_t)(0), st, reinterpret_cast<const long long*>(in), (long long)ld, W,
+                                                               (long long)n_rows, q, s, reinterpret_cast<long long*>(out), widths));
   GR_CHECK_LAUNCH("pair_major_table_kernel");
   return GR_OK;
 }

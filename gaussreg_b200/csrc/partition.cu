@@ -21,6 +21,8 @@ constexpr int kNodeTile = 1024;
 __global__ void __launch_bounds__(256) nearest_node_kernel(const float* __restrict__ pts, int N, const float* __restrict__ nodes,
                                                            int M, int* __restrict__ p2n, float* __restrict__ dmin,
                                                            uint32_t* __restrict__ node_cnt) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float4 sh[kNodeTile];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   float y0 = 0.f, y1 = 0.f, y2 = 0.f, yy = 0.f;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(256) nearest_node_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) node_scatter_kernel(const int* __restrict__ p2n, int N, const uint32_t* __restrict__ node_off,
                                                            uint32_t* __restrict__ node_fill, int* __restrict__ plist) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m = p2n[n];
@@ -63,6 +67,8 @@ __global__ void __launch_bounds__(128) node_knn_kernel(const float* __restrict__
                                                        const int* __restrict__ plist, int N, int M, int K,
                                                        long long* __restrict__ knn_idx, unsigned char* __restrict__ knn_mask,
                                                        unsigned char* __restrict__ node_mask) {
+  pdl_wait();
+  pdl_trigger();
   const int m = blockIdx.x;
   const uint32_t s = node_off[m], e = node_off[m + 1];
   const int cnt = (int)(e - s);
@@ -114,14 +120,14 @@ extern "C" int gr_point_to_node_partition(const float* points, int N, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GR_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(M + 1) * sizeof(uint32_t), st));
   GR_CHECK_CUDA(cudaMemsetAsync(fill, 0, (size_t)(M + 1) * sizeof(uint32_t), st));
-  nearest_node_kernel<<<ceil_div(N, 256), 256, 0, st>>>(points, N, nodes, M, point_to_node, dmin, cnt);
+  GR_CHECK_CUDA(launch_pdl(nearest_node_kernel, dim3(ceil_div(N, 256)), dim3(256), (size_t)(0), st, points, N, nodes, M, point_to_node, dmin, cnt));
   GR_CHECK_LAUNCH("nearest_node_kernel");
   int rc = exclusive_scan_u32(cnt, cnt, M + 1, sws, st);
   if (rc != GR_OK) return rc;
-  node_scatter_kernel<<<ceil_div(N, 256), 256, 0, st>>>(point_to_node, N, cnt, fill, plist);
+  GR_CHECK_CUDA(launch_pdl(node_scatter_kernel, dim3(ceil_div(N, 256)), dim3(256), (size_t)(0), st, point_to_node, N, cnt, fill, plist));
   GR_CHECK_LAUNCH("node_scatter_kernel");
-  node_knn_kernel<<<M, 128, 0, st>>>(dmin, cnt, plist, N, M, point_limit, reinterpret_cast<long long*>(knn_indices), knn_masks,
-                                     node_masks);
+  GR_CHECK_CUDA(launch_pdl(node_knn_kernel, dim3(M), dim3(128), (size_t)(0), st, dmin, cnt, plist, N, M, point_limit, reinterpret_cast<long long*>(knn_indices), knn_masks,
+                                     node_masks));
   GR_CHECK_LAUNCH("node_knn_kernel");
   return GR_OK;
 }

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kRansacThreads) ransac_hypotheses_kernel(const
                                                                           const int* __restrict__ num_dev, int cap, int n_hyp,
                                                                           int sample_n, float thr, unsigned long long seed,
                                                                           unsigned long long* __restrict__ keys, float* __restrict__ Ts) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[kRansacTile * 6];
   int n = num_dev ? *num_dev : cap;
   n = n < 0 ? 0 : (n > cap ? cap : n);
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(const float* __restr
                                                             const unsigned long long* __restrict__ keys, const float* __restrict__ Ts,
                                                             const float* __restrict__ fallback, float* __restrict__ T_out,
                                                             int* __restrict__ info) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned long long s_key[256];
   __shared__ int s_idx[256];
   __shared__ double s_red[256];
@@ -282,11 +286,10 @@ extern "C" int gr_similarity_ransac(const float* ref_corr, const float* src_corr
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* keys = static_cast<unsigned long long*>(ws);
   float* Ts = reinterpret_cast<float*>(keys + num_hypotheses);
-  ransac_hypotheses_kernel<<<ceil_div(num_hypotheses, kRansacThreads), kRansacThreads, 0, st>>>(
-      ref_corr, src_corr, d_num_corr, capacity, num_hypotheses, sample_size, distance_threshold, (unsigned long long)seed, keys, Ts);
+  GR_CHECK_CUDA(launch_pdl(ransac_hypotheses_kernel, dim3(ceil_div(num_hypotheses, kRansacThreads)), dim3(kRansacThreads), (size_t)(0), st, ref_corr, src_corr, d_num_corr, capacity, num_hypotheses, sample_size, distance_threshold, (unsigned long long)seed, keys, Ts));
   GR_CHECK_LAUNCH("ransac_hypotheses_kernel");
-  ransac_select_kernel<<<1, 256, 0, st>>>(ref_corr, src_corr, d_num_corr, capacity, num_hypotheses, distance_threshold, refit, keys, Ts,
-                                          fallback, T_out, info);
+  GR_CHECK_CUDA(launch_pdl(ransac_select_kernel, dim3(1), dim3(256), (size_t)(0), st, ref_corr, src_corr, d_num_corr, capacity, num_hypotheses, distance_threshold, refit, keys, Ts,
+                                          fallback, T_out, info));
   GR_CHECK_LAUNCH("ransac_select_kernel");
   return GR_OK;
 }

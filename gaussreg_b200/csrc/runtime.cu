@@ -1,4 +1,6 @@
 // Library-level bookkeeping: version string, last-error text, launch counter.
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -14,6 +16,12 @@ void set_last_error(const char* what, cudaError_t e) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 cudaError_t ensure_smem_attr(const void* kernel, int bytes) {
   struct Key { const void* k; int dev; int bytes; };

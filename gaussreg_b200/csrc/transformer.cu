@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(kMlpC) transformer_mlp_kernel(const float* __r
                                                                const float* __restrict__ b1, const float* __restrict__ w2t,
                                                                const float* __restrict__ b2, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float xs[kMlpRows][kMlpC];
   __shared__ __align__(16) float hs[kMlpRows][2 * kMlpC];
   __shared__ __align__(16) float ys[kMlpRows][kMlpC];
@@ -163,8 +165,7 @@ static int post_attention(const gr_layer_weights& L, float* x, const float* hid,
   GR_TRY(gr_gemm(hid, C, 0, L.wo, C, 0, 1, w.att, C, 0, rows, C, C, 1, 1.f, L.bo, nullptr, x, C, 0, 0, st));
   GR_TRY(gr_layer_norm_add(w.att, nullptr, rows, C, L.ln1_g, L.ln1_b, 1e-5f, w.y, st));
   if (L.w1t && L.w2t && C == kMlpC && mlp_fused()) {
-    transformer_mlp_kernel<<<(rows + kMlpRows - 1) / kMlpRows, kMlpC, 0, static_cast<cudaStream_t>(st)>>>(
-        w.y, rows, L.w1t, L.b1, L.w2t, L.b2, L.ln2_g, L.ln2_b, 1e-5f, x);
+    GR_CHECK_CUDA(launch_pdl(transformer_mlp_kernel, dim3((rows + kMlpRows - 1) / kMlpRows), dim3(kMlpC), (size_t)(0), static_cast<cudaStream_t>(st), w.y, rows, L.w1t, L.b1, L.w2t, L.b2, L.ln2_g, L.ln2_b, 1e-5f, x));
     GR_CHECK_LAUNCH("transformer_mlp_kernel");
     return GR_OK;
   }
