@@ -511,6 +511,314 @@ __global__ void __launch_bounds__(kThreadsTma, BN == 64 ? 2 : 1) gemm_tf32x3_tma
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent form of the TMA-fed kernel: one CTA per SM walks the output tiles of the whole problem.
+//
+// Measured (tools/gemm_bench.py, round 2): with one tile per CTA a 128 x 256 x 64 product spends ~12 us per tile in
+// serial prologue -> first loads -> MMA -> epilogue -> exit, i.e. the small-K products of the backbone (a third of its
+// GEMM launches) move their operands at 1.5 TB/s.  Here the roles never stop:
+//   warp 9        loader   streams A (tensor-map TMA) and the packed B tiles of tile after tile into the rings,
+//   warps 4-7     splitters derive the low parts,
+//   warp 8        MMA      accumulates tile i into TMEM buffer i & 1,
+//   warps 0-3     epilogue drains buffer (i-1) & 1 (TMEM -> transpose -> fused epilogue / GroupNorm statistics -> global)
+// so the epilogue of one tile overlaps the loads and MMAs of the next, and barrier / TMEM / tensor-map set-up happens
+// once per SM.  Two accumulator sets of 2 BN columns each need 4 BN <= 512 TMEM columns: BN <= 128 (wider outputs are
+// walked as several column tiles; their A tiles are re-read from L2).
+template <int BN>
+struct CfgPersist {
+  static constexpr int kABytes = BM * BK * 4;
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kOpBytes = kABytes + 2 * kBBytes;
+  static constexpr int kOps = BN == 128 ? 2 : 3;
+  static constexpr int kRaw = BN == 128 ? 5 : 4;
+  static constexpr int kEpiBytes = 8 * 32 * 36 * 4 + 4 * BN * 8 + BN * 16;  // 8 transposition tiles | gn_col | gn_cold
+  static constexpr int kSmemBytes = kRaw * kABytes + kOps * kOpBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
+};
+constexpr int kThreadsPersist = 448;  // 8 epilogue warps, 4 splitter warps, MMA warp, loader warp
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsPersist, 1) gemm_tf32x3_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p,
+                                                                                int tiles_m, int tiles_n, int n_splits) {
+  using C = CfgPersist<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* raw_ring = smem;
+  unsigned char* op_ring = smem + C::kRaw * C::kABytes;
+  unsigned char* epi = op_ring + C::kOps * C::kOpBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::kEpiBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto raw_full = [&](int r) { return bar_base + 8u * r; };
+  auto raw_empty = [&](int r) { return bar_base + 8u * (C::kRaw + r); };
+  auto op_full = [&](int s) { return bar_base + 8u * (2 * C::kRaw + s); };
+  auto op_empty = [&](int s) { return bar_base + 8u * (2 * C::kRaw + C::kOps + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * C::kRaw + 2 * C::kOps + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * C::kRaw + 2 * C::kOps + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kRaw + 2 * C::kOps + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = tiles_m * tiles_n * n_splits;
+  const bool split = p.k_split > 0;
+
+  if (tid == 0) {
+    for (int r = 0; r < C::kRaw; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), 1); }
+    for (int s = 0; s < C::kOps; ++s) { mbar_init(op_full(s), 4 + 1); mbar_init(op_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(4 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  // tile t -> (m tile, n tile, k slice): n fastest, so that the CTAs of one wave share their A rows through L2
+  auto tile_coords = [&](int t, int& mt, int& nt, int& z) { nt = t % tiles_n; mt = (t / tiles_n) % tiles_m; z = t / (tiles_n * tiles_m); };
+  auto k_range = [&](int z, int& kbeg, int& nkb) {
+    kbeg = split ? z * p.k_split : 0;
+    const int kend = split ? min(p.K, kbeg + p.k_split) : p.K;
+    nkb = (kend - kbeg + BK - 1) / BK;
+  };
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps: TMEM lane quarter q = warp & 3,
+    // column half = warp >> 2 (a warp may only touch the 32 TMEM lanes of its quarter)
+    const int q = warp & 3, half = warp >> 2;
+    float* stage = reinterpret_cast<float*>(epi) + warp * (32 * 36);
+    float2* gn_col = reinterpret_cast<float2*>(epi + 8 * 32 * 36 * 4);   // [4][BN]
+    double2* gn_cold = reinterpret_cast<double2*>(epi + 8 * 32 * 36 * 4 + 4 * BN * 8);  // [BN]
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int mt, nt, z;
+      tile_coords(t, mt, nt, z);
+      const int m0 = mt * BM, n0 = nt * BN, b = it & 1;
+      mbar_wait(acc_full(b), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(b * 2 * BN);
+      float* __restrict__ Cp = p.C + (long long)z * p.sC;
+      const float* __restrict__ R = p.residual ? p.residual + (long long)z * p.sR : nullptr;
+      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) &&
+                          (!R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t r[32], rc[32];
+        tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
+        if (c0 + 32 >= (half + 1) * (BN / 2)) {  // last TMEM read of this warp: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          v.y = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]);
+          v.z = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]);
+          v.w = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]);
+          *reinterpret_cast<float4*>(stage + lane * 36 + j) = v;
+        }
+        __syncwarp();
+        const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+        const int n = n0 + c0 + c4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
+          else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
+        }
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + rsub;
+          const int m = m0 + q * 32 + row;
+          if (m >= p.M) continue;
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+          float x[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+          if (p.row_div) { const float rd = p.row_div[m]; x[0] /= rd; x[1] /= rd; x[2] /= rd; x[3] /= rd; }
+          x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
+          if (R) {
+            const float* rp = R + (long long)m * p.ldr + n;
+            if (vec_ok && n + 3 < p.N) { const float4 tt = *reinterpret_cast<const float4*>(rp); x[0] += tt.x; x[1] += tt.y; x[2] += tt.z; x[3] += tt.w; }
+            else { for (int e = 0; e < 4; ++e) if (n + e < p.N) x[e] += rp[e]; }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.act == 1) x[e] = fmaxf(x[e], 0.f);
+            else if (p.act == 2) x[e] = x[e] > 0.f ? x[e] : 0.1f * x[e];
+          }
+          float* dst = Cp + (long long)m * p.ldc + n;
+          if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
+          if (p.gn_partial) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
+          }
+        }
+        if (p.gn_partial) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+          }
+          if (rsub == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gn_col[q * BN + c0 + c4 + e] = make_float2(cs[e], cq[e]);
+          }
+        }
+        __syncwarp();  // the transposition tile is rewritten by the next chunk
+      }
+      if (p.gn_partial) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (tid < BN) {
+          double a = 0.0, bsum = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { const float2 v = gn_col[qq * BN + tid]; a += (double)v.x; bsum += (double)v.y; }
+          gn_cold[tid] = make_double2(a, bsum);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int cg = p.N / p.gn_groups;
+        if (tid < BN / cg) {
+          const int gidx = n0 / cg + tid;
+          if (gidx < p.gn_groups) {
+            double a = 0.0, bsum = 0.0;
+            for (int c = tid * cg; c < (tid + 1) * cg; ++c) { a += gn_cold[c].x; bsum += gn_cold[c].y; }
+            p.gn_partial[(long long)mt * p.gn_groups + gidx] = make_double2(a, bsum);
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // gn_col / gn_cold are free for the next tile
+      }
+    }
+    tc_fence_before();
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ splitters: lo = x - trunc_tf32(x)
+    const int stid = tid - 256;
+    int kit = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt, z, kbeg, nkb;
+      tile_coords(t, mt, nt, z);
+      k_range(z, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        const int r = kit % C::kRaw, s = kit % C::kOps;
+        if (kit >= C::kOps) mbar_wait(op_empty(s), ((kit / C::kOps) - 1) & 1);
+        mbar_wait(raw_full(r), (kit / C::kRaw) & 1);
+        const float4* src = reinterpret_cast<const float4*>(raw_ring + r * C::kABytes);
+        float4* dst = reinterpret_cast<float4*>(op_ring + s * C::kOpBytes);
+#pragma unroll
+        for (int i = 0; i < BM * BK / 4 / 128; ++i) {
+          const float4 v = src[stid + i * 128];
+          float4 lo;
+          lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          dst[stid + i * 128] = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_full(s));
+      }
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int kit = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int mt, nt, z, kbeg, nkb;
+        tile_coords(t, mt, nt, z);
+        k_range(z, kbeg, nkb);
+        const int b = it & 1;
+        if (it >= 2) mbar_wait(acc_empty(b), ((it >> 1) - 1) & 1);  // the epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(b * 2 * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int r = kit % C::kRaw, s = kit % C::kOps;
+          mbar_wait(op_full(s), (kit / C::kOps) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(raw_ring + r * C::kABytes);
+          const uint32_t a_lo = smem_u32(op_ring + s * C::kOpBytes);
+          const uint32_t b_hi = a_lo + C::kABytes;
+          const uint32_t b_lo = b_hi + C::kBBytes;
+#pragma unroll
+          for (int k8 = 0; k8 < BK / 8; ++k8) {
+            const uint32_t ko = k8 * 32;
+            const uint32_t first = (kb | k8) != 0 ? 1u : 0u;
+            umma_tf32(tacc + BN, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
+            umma_tf32(tacc + BN, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+            umma_tf32(tacc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+          }
+          umma_commit(raw_empty(r));
+          umma_commit(op_empty(s));
+        }
+        umma_commit(acc_full(b));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ loader
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      constexpr uint32_t kRowBytes = BN < 128 ? BN * 128 : 128 * 128;
+      // flattened k-block stream over this CTA's tiles; A runs kLead k-blocks ahead of B (see gemm_tf32x3_tma_kernel)
+      constexpr int kLead = C::kRaw - C::kOps >= 1 ? C::kRaw - C::kOps : 0;
+      struct Cursor { int t, kb, nkb, kbeg, m0, n0, rot; };
+      auto open_tile = [&](Cursor& c) {
+        if (c.t >= total_tiles) { c.nkb = 0; return; }
+        int mt, nt, z;
+        tile_coords(c.t, mt, nt, z);
+        k_range(z, c.kbeg, c.nkb);
+        c.m0 = mt * BM; c.n0 = nt * BN; c.kb = 0;
+        c.rot = mt % c.nkb;
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.kb >= c.nkb) { c.t += gridDim.x; open_tile(c); }
+      };
+      auto kbr = [&](const Cursor& c) { int r = c.kb + c.rot; return r >= c.nkb ? r - c.nkb : r; };
+      Cursor ca, cb;
+      ca.t = cb.t = blockIdx.x;
+      open_tile(ca); open_tile(cb);
+      int ia = 0, ib = 0;  // issued k-blocks
+      auto issue_a = [&]() {
+        const int r = ia % C::kRaw;
+        if (ia >= C::kRaw) mbar_wait(raw_empty(r), ((ia / C::kRaw) - 1) & 1);
+        mbar_arrive_expect_tx(raw_full(r), (uint32_t)C::kABytes);
+        tma_load_2d(smem_u32(raw_ring + r * C::kABytes), &tmap_a, ca.kbeg + kbr(ca) * BK, ca.m0, raw_full(r));
+        ++ia; advance(ca);
+      };
+      auto issue_b = [&]() {
+        const int s = ib % C::kOps;
+        if (ib >= C::kOps) mbar_wait(op_empty(s), ((ib / C::kOps) - 1) & 1);
+        mbar_arrive_expect_tx(op_full(s), 2u * kRowBytes);
+        const int kblock = (cb.kbeg / BK) + kbr(cb);
+        const uint32_t b_hi_s = smem_u32(op_ring + s * C::kOpBytes + C::kABytes), b_lo_s = b_hi_s + C::kBBytes;
+        const int nt = cb.n0 >> 7, rin = cb.n0 & 127;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.B_packed) +
+                                   ((size_t)nt * p.packed_kblocks + kblock) * (2 * 16384) + (size_t)rin * 128;
+        bulk_copy_g2s(b_hi_s, src, kRowBytes, op_full(s));
+        bulk_copy_g2s(b_lo_s, src + 16384, kRowBytes, op_full(s));
+        ++ib; advance(cb);
+      };
+      for (int i = 0; i < kLead && ca.nkb > 0; ++i) issue_a();
+      while (cb.nkb > 0) {
+        issue_b();
+        if (ca.nkb > 0) issue_a();
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * BN));
+  }
+}
+
 // C = epilogue(sum_z partial[z]) in a fixed order; one thread per 4 consecutive columns (N % 4 == 0)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, Params p) {
   pdl_wait();
@@ -668,6 +976,33 @@ static int launch_tma(const Params& p, int zdim, cudaStream_t st) {
   return GR_OK;
 }
 
+// > 0: the persistent path cannot serve this call
+template <int BN>
+static int launch_persist(const Params& p, int zdim, cudaStream_t st) {
+  using C = CfgPersist<BN>;
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return 1;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.lda * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_tf32x3_persist_kernel<BN>), C::kSmemBytes));
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const long long total = (long long)tiles_m * tiles_n * zdim;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(total < sms ? total : sms);
+  GR_CHECK_CUDA(launch_pdl(gemm_tf32x3_persist_kernel<BN>, dim3(grid), dim3(kThreadsPersist), (size_t)C::kSmemBytes, st, tm, p, tiles_m,
+                           tiles_n, zdim));
+  GR_CHECK_LAUNCH("gemm_tf32x3_persist_kernel");
+  return GR_OK;
+}
+
 static bool use_tma() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GAUSSREG_GEMM_TMA"); v = e ? atoi(e) : 1; }
@@ -677,6 +1012,18 @@ static bool use_tma() {
 // one launch of the tile kernel: TMA-fed when B is pre-packed, ld.global producers otherwise
 static int launch_any(int bn, const Params& p, int zdim, cudaStream_t st) {
   if (p.B_packed && use_tma() && p.K >= 2 * BK) {
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("GAUSSREG_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
+    // The persistent kernel overlaps one tile's epilogue with the next tile's MMAs, which pays when a CTA gets
+    // several short tiles (narrow N or small K: 49 vs 61 us on 60000x32x480, 30 vs 34 us on 41907x256x64).  Wide
+    // products with a long K loop stay on the 128x256 tiles (twice the flops per A byte read from shared memory),
+    // and grids of at most ~one tile per SM have nothing to overlap.  persist=2 forces it for every shape.
+    const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + (bn > 128 ? 128 : bn) - 1) / (bn > 128 ? 128 : bn)) * zdim;
+    const bool pays = tiles > 222 && (p.N <= 128 || p.K <= 128);
+    if (persist > 1 || (persist == 1 && pays)) {
+      const int rcp = bn == 64 ? launch_persist<64>(p, zdim, st) : launch_persist<128>(p, zdim, st);
+      if (rcp <= 0) return rcp;
+    }
     const int rc = bn == 256 ? launch_tma<256>(p, zdim, st) : (bn == 128 ? launch_tma<128>(p, zdim, st) : launch_tma<64>(p, zdim, st));
     if (rc <= 0) return rc;
   }
