@@ -20,13 +20,13 @@ __device__ __noinline__ void kabsch_from_H(const double H[9], const double sc[3]
   double A[9], V[9];
   for (int i = 0; i < 9; ++i) { A[i] = H[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
+    bool rotated = false;  // a sweep that rotates nothing leaves A and V as they are: so would every later one
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
         double al = 0, be = 0, ga = 0;
         for (int r = 0; r < 3; ++r) { al += A[3 * r + p] * A[3 * r + p]; be += A[3 * r + q] * A[3 * r + q]; ga += A[3 * r + p] * A[3 * r + q]; }
-        off += fabs(ga);
         if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        rotated = true;
         const double zeta = (be - al) / (2.0 * ga);
         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
@@ -37,7 +37,7 @@ __device__ __noinline__ void kabsch_from_H(const double H[9], const double sc[3]
           V[3 * r + p] = c * vp - s * vq; V[3 * r + q] = s * vp + c * vq;
         }
       }
-    if (off == 0.0) break;
+    if (!rotated) break;
   }
   double sg[3];
   int ord[3] = {0, 1, 2};
@@ -85,31 +85,45 @@ __device__ __noinline__ void kabsch_from_H(const double H[9], const double sc[3]
   }
 }
 
-__device__ __forceinline__ double block_sum_double(double v, double* sh /* >= 32 */) {
+constexpr int kLgrShFloats = 32 * 9 + 16;  // scratch of block_sum_n: 32 warp partials per value, then the totals
+
+// Sums N per-thread values over the CTA (every thread receives all N totals): one shuffle butterfly per value, the warp
+// partials through shared memory, a second butterfly by warp 0.  Three barriers whatever N is.
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float* sh /* kLgrShFloats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
   __syncthreads();
-  if (lane == 0) sh[warp] = v;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < N; ++k) sh[k * 32 + warp] = v[k];
   __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < nw; ++w) t += sh[w];
-  return t;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float t = lane < nw ? sh[k * 32 + lane] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sh[32 * N + k] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = sh[32 * N + k];
 }
 
-__device__ __forceinline__ float block_sum_float(float v, float* sh /* >= 32 */) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int w = 0; w < nw; ++w) t += sh[w];
-  return t;
-}
+// A run of correspondences; the pointers may address shared or global memory.
+struct CorrSeg {
+  const float* src;
+  const float* ref;
+  const float* w;
+  int n;
+};
 
-// Weighted Procrustes over n correspondences, executed by a whole CTA.  Weights w_i >= 0.
+// Weighted Procrustes over the correspondences of segments a then b, executed by a whole CTA.  Weights w_i >= 0.
 // procrustes.py:41-70: w <- w / (sum w + eps); centroids; H; SVD.  Result T (3x4 row-major) in shared memory.
 //
 // All sums are accumulated in fp32, as the reference does (torch.sum / bmm on float tensors).  This matters for
@@ -118,35 +132,48 @@ __device__ __forceinline__ float block_sum_float(float v, float* sh /* >= 32 */)
 // would instead return a clean near-identity rotation for H ~ 0, and such a hypothesis can collect spuriously many
 // inliers whenever the true motion is small -- a systematic deviation from the reference's hypothesis selection
 // (observed on the textured3k golden).  Only the 3x3 factorisation itself runs in fp64.
-__device__ void block_procrustes(const float* __restrict__ src, const float* __restrict__ ref, const float* __restrict__ w, int n,
-                                 float eps, double* sh, float* T_out /* shared, 12 */) {
-  float* shf = reinterpret_cast<float*>(sh);
-  float sw = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sw += w[i];
-  sw = block_sum_float(sw, shf);
-  const float denom = sw + eps;
-  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float wi = w[i] / denom;
-    a[0] += src[3 * i] * wi; a[1] += src[3 * i + 1] * wi; a[2] += src[3 * i + 2] * wi;
-    a[3] += ref[3 * i] * wi; a[4] += ref[3 * i + 1] * wi; a[5] += ref[3 * i + 2] * wi;
+__device__ void block_procrustes(const CorrSeg a, const CorrSeg b, float eps, float* sh, float* T_out /* shared, 12 */) {
+  const CorrSeg segs[2] = {a, b};
+  float sw[1] = {0.f};
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+    for (int i = threadIdx.x; i < segs[g].n; i += blockDim.x) sw[0] += segs[g].w[i];
+  block_sum_n<1>(sw, sh);
+  const float denom = sw[0] + eps;
+  float cen[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const float* __restrict__ src = segs[g].src;
+    const float* __restrict__ ref = segs[g].ref;
+    const float* __restrict__ w = segs[g].w;
+    for (int i = threadIdx.x; i < segs[g].n; i += blockDim.x) {
+      const float wi = w[i] / denom;
+      cen[0] += src[3 * i] * wi; cen[1] += src[3 * i + 1] * wi; cen[2] += src[3 * i + 2] * wi;
+      cen[3] += ref[3 * i] * wi; cen[4] += ref[3 * i + 1] * wi; cen[5] += ref[3 * i + 2] * wi;
+    }
   }
-  float cen[6];
-  for (int k = 0; k < 6; ++k) cen[k] = block_sum_float(a[k], shf);
+  block_sum_n<6>(cen, sh);
   const float scx = cen[0], scy = cen[1], scz = cen[2];
   const float rcx = cen[3], rcy = cen[4], rcz = cen[5];
   float h[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float wi = w[i] / denom;
-    const float sx = src[3 * i] - scx, sy = src[3 * i + 1] - scy, sz = src[3 * i + 2] - scz;
-    const float rx = wi * (ref[3 * i] - rcx), ry = wi * (ref[3 * i + 1] - rcy), rz = wi * (ref[3 * i + 2] - rcz);
-    h[0] += sx * rx; h[1] += sx * ry; h[2] += sx * rz;
-    h[3] += sy * rx; h[4] += sy * ry; h[5] += sy * rz;
-    h[6] += sz * rx; h[7] += sz * ry; h[8] += sz * rz;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const float* __restrict__ src = segs[g].src;
+    const float* __restrict__ ref = segs[g].ref;
+    const float* __restrict__ w = segs[g].w;
+    for (int i = threadIdx.x; i < segs[g].n; i += blockDim.x) {
+      const float wi = w[i] / denom;
+      const float sx = src[3 * i] - scx, sy = src[3 * i + 1] - scy, sz = src[3 * i + 2] - scz;
+      const float rx = wi * (ref[3 * i] - rcx), ry = wi * (ref[3 * i + 1] - rcy), rz = wi * (ref[3 * i + 2] - rcz);
+      h[0] += sx * rx; h[1] += sx * ry; h[2] += sx * rz;
+      h[3] += sy * rx; h[4] += sy * ry; h[5] += sy * rz;
+      h[6] += sz * rx; h[7] += sz * ry; h[8] += sz * rz;
+    }
   }
-  double H[9];
-  for (int k = 0; k < 9; ++k) H[k] = (double)block_sum_float(h[k], shf);
+  block_sum_n<9>(h, sh);
   if (threadIdx.x == 0) {
+    double H[9];
+    for (int k = 0; k < 9; ++k) H[k] = (double)h[k];
     const double sc[3] = {(double)scx, (double)scy, (double)scz}, rc[3] = {(double)rcx, (double)rcy, (double)rcz};
     kabsch_from_H(H, sc, rc, T_out);
   }
@@ -158,63 +185,79 @@ struct PatchCorr {  // per patch: up to K*topk candidates in (row, col) order
   int count;
 };
 
-// One CTA (K threads, K <= 128) per patch.  score = exp(log score) on the K x K block without dustbin.
-__global__ void __launch_bounds__(kLgrThreads) lgr_correspondence_kernel(
+// One CTA per patch.  score = exp(log score) on the K x K block without dustbin.  Threads 0..K-1 find the top-k of
+// their row and threads 128..128+K-1 the top-k of their column, each in ONE scan with a sorted insertion (value
+// descending, index ascending on ties: what repeated torch.topk / argmax yields).  Mutual selection then only has to
+// test the <= topk row winners of a row against the column winners (local_global_registration.py:71-93).
+constexpr int kCorrThreads = 256;
+constexpr int kCorrTop = kLgrMaxPerRow / 2;  // >= topk
+__global__ void __launch_bounds__(kCorrThreads) lgr_correspondence_kernel(
     const float* __restrict__ ms, int K, int ld /* K or K+1 */, const unsigned char* __restrict__ ref_masks,
-    const unsigned char* __restrict__ src_masks, int topk, float conf, int mutual, int* __restrict__ counts,
+    const unsigned char* __restrict__ src_masks, int topk, float conf, int* __restrict__ counts,
     int* __restrict__ cand_rc /* (P, K*topk) packed row<<16|col */, float* __restrict__ cand_score) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float e[];  // K x (K+1) exp scores (padded rows: conflict-free row and column walks)
   const int KP = K + 1;
-  __shared__ int row_top[kLgrThreads][kLgrMaxPerRow];
-  __shared__ int col_top[kLgrThreads][kLgrMaxPerRow];
-  __shared__ int row_cnt[kLgrThreads + 1];
+  __shared__ int row_top[kLgrThreads][kCorrTop];
+  __shared__ int col_top[kLgrThreads][kCorrTop];
+  __shared__ int warp_tot[kLgrThreads / 32];
   const int b = blockIdx.x, t = threadIdx.x;
   const float* src = ms + (long long)b * ld * ld;
   for (int i = t; i < K * K; i += blockDim.x) e[(i / K) * KP + (i % K)] = expf(src[(i / K) * ld + (i % K)]);
   __syncthreads();
-  if (t < K) {
-    // row top-k and column top-k by (value desc, index asc)
-    for (int pass = 0; pass < 2; ++pass) {
-      int sel[kLgrMaxPerRow];
-      for (int r = 0; r < topk; ++r) {
-        float bv = -INFINITY; int bi = -1;
-        for (int j = 0; j < K; ++j) {
-          bool used = false;
-          for (int q = 0; q < r; ++q) used |= sel[q] == j;
-          if (used) continue;
-          const float v = pass == 0 ? e[t * KP + j] : e[j * KP + t];
-          if (v > bv) { bv = v; bi = j; }
-        }
-        sel[r] = bi;
+  {
+    const int line = t & (kLgrThreads - 1);
+    const bool rows = t < kLgrThreads;
+    if (line < K) {
+      float bv[kCorrTop];
+      int bi[kCorrTop];
+#pragma unroll
+      for (int q = 0; q < kCorrTop; ++q) { bv[q] = -INFINITY; bi[q] = -1; }
+      const float* walk = rows ? e + line * KP : e + line;
+      const int step = rows ? 1 : KP;
+      for (int j = 0; j < K; ++j) {
+        const float v = walk[j * step];
+#pragma unroll
+        for (int q = kCorrTop - 1; q >= 0; --q)
+          if (v > bv[q]) {
+            if (q < kCorrTop - 1) { bv[q + 1] = bv[q]; bi[q + 1] = bi[q]; }
+            bv[q] = v; bi[q] = j;
+          }
       }
-      for (int r = 0; r < topk; ++r) (pass == 0 ? row_top : col_top)[t][r] = sel[r];
+#pragma unroll
+      for (int q = 0; q < kCorrTop; ++q) (rows ? row_top : col_top)[line][q] = bi[q];
     }
   }
   __syncthreads();
-  int mine[kLgrMaxPerRow];
+  int mine[kCorrTop];
   int nm = 0;
   if (t < K && ref_masks[(long long)b * K + t]) {
-    for (int j = 0; j < K; ++j) {
-      bool in_row = false, in_col = false;
-      for (int r = 0; r < topk; ++r) { in_row |= row_top[t][r] == j; in_col |= col_top[j][r] == t; }
-      const bool ok_v = e[t * KP + j] > conf;
-      const bool c = mutual ? (in_row && in_col && ok_v) : ((in_row || in_col) && ok_v);
-      if (c && src_masks[(long long)b * K + j] && nm < kLgrMaxPerRow) mine[nm++] = j;
+    for (int r = 0; r < topk; ++r) {
+      const int j = row_top[t][r];
+      if (j < 0) continue;
+      bool in_col = false;
+      for (int q = 0; q < topk; ++q) in_col |= col_top[j][q] == t;
+      if (in_col && e[t * KP + j] > conf && src_masks[(long long)b * K + j]) mine[nm++] = j;
     }
+    // torch.nonzero order: ascending column within the row
+    for (int x = 1; x < nm; ++x)
+      for (int y = x; y > 0 && mine[y - 1] > mine[y]; --y) { const int tmp = mine[y]; mine[y] = mine[y - 1]; mine[y - 1] = tmp; }
   }
-  row_cnt[t] = nm;
-  __syncthreads();
-  if (t == 0) {
-    int acc = 0;
-    for (int i = 0; i < K; ++i) { const int c = row_cnt[i]; row_cnt[i] = acc; acc += c; }
-    row_cnt[K] = acc;
-    counts[b] = acc;
-  }
-  __syncthreads();
-  if (t < K) {
-    const long long base = (long long)b * K * topk * (mutual ? 1 : 2) + row_cnt[t];
+  if (t < kLgrThreads) {  // exclusive scan of the row counts over the first four warps
+    const int lane = t & 31, warp = t >> 5;
+    int inc = nm;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (t == kLgrThreads - 1) counts[b] = before + inc;
+    const long long base = (long long)b * K * topk + before + inc - nm;
     for (int q = 0; q < nm; ++q) {
       cand_rc[base + q] = (t << 16) | mine[q];
       cand_score[base + q] = e[t * KP + mine[q]];
@@ -261,7 +304,7 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
                                                                      int* __restrict__ inliers) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double sh[32];
+  __shared__ float sh[kLgrShFloats];
   __shared__ float T[12];
   __shared__ int s_cnt;
   const int b = blockIdx.x;
@@ -270,7 +313,7 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
     if (threadIdx.x == 0) inliers[b] = -1;
     return;
   }
-  block_procrustes(src_corr + 3ll * off, ref_corr + 3ll * off, corr_scores + off, n, eps, sh, T);
+  block_procrustes(CorrSeg{src_corr + 3ll * off, ref_corr + 3ll * off, corr_scores + off, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, sh, T);
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   int c = 0;
@@ -290,18 +333,30 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
   if (threadIdx.x < 12) T_local[b * 12 + threadIdx.x] = T[threadIdx.x];
 }
 
-// single CTA: pick the best hypothesis (first maximum), then `steps` rounds of global refinement
-__global__ void __launch_bounds__(1024) lgr_refine_kernel(const float* __restrict__ ref_corr, const float* __restrict__ src_corr,
-                                                          const float* __restrict__ corr_scores, const int* __restrict__ offsets, int P,
-                                                          const float* __restrict__ T_local, const int* __restrict__ inliers, float radius,
-                                                          float eps, int steps, float* __restrict__ w /* scratch, C */,
-                                                          float* __restrict__ T_out /* 16 */, int* __restrict__ best_out) {
+// single CTA: pick the best hypothesis (first maximum), then `steps` rounds of global refinement.  The first `cap`
+// correspondences (all of them, normally) are staged in shared memory once -- the 4 * steps passes over them then cost
+// shared-memory latency instead of a dependent L2 round trip per pass; whatever exceeds `cap` is read in place.
+constexpr int kRefineThreads = 1024;
+constexpr int kRefineCap = 6400;  // x 32 B = 200 KB of dynamic shared memory
+__global__ void __launch_bounds__(kRefineThreads) lgr_refine_kernel(const float* __restrict__ ref_corr, const float* __restrict__ src_corr,
+                                                                    const float* __restrict__ corr_scores, const int* __restrict__ offsets, int P,
+                                                                    const float* __restrict__ T_local, const int* __restrict__ inliers, float radius,
+                                                                    float eps, int steps, int cap, float* __restrict__ w /* scratch, C */,
+                                                                    float* __restrict__ T_out /* 16 */, int* __restrict__ best_out) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double sh[32];
+  extern __shared__ float stage[];  // src (3 cap) | ref (3 cap) | score (cap) | w (cap)
+  __shared__ float sh[kLgrShFloats];
   __shared__ float T[12];
   __shared__ int s_best;
   const int C = offsets[P];
+  const int n0 = C < cap ? C : cap, n1 = C - n0;
+  float* s_src = stage;
+  float* s_ref = s_src + 3 * (size_t)cap;
+  float* s_score = s_ref + 3 * (size_t)cap;
+  float* s_w = s_score + cap;
+  for (int i = threadIdx.x; i < 3 * n0; i += blockDim.x) { s_src[i] = src_corr[i]; s_ref[i] = ref_corr[i]; }
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) s_score[i] = corr_scores[i];
   if (threadIdx.x == 0) {
     int best = -1, bc = -1;
     for (int b = 0; b < P; ++b)
@@ -310,14 +365,21 @@ __global__ void __launch_bounds__(1024) lgr_refine_kernel(const float* __restric
     *best_out = best;
   }
   __syncthreads();
+  const CorrSeg near_scores{s_src, s_ref, s_score, n0}, far_scores{src_corr + 3ll * n0, ref_corr + 3ll * n0, corr_scores + n0, n1};
+  const CorrSeg near_w{s_src, s_ref, s_w, n0}, far_w{src_corr + 3ll * n0, ref_corr + 3ll * n0, w + n0, n1};
   auto rescore = [&]() {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-      const float sx = src_corr[3 * i], sy = src_corr[3 * i + 1], sz = src_corr[3 * i + 2];
-      const float ax = (sx * T[0] + sy * T[1] + sz * T[2]) + T[3];
-      const float ay = (sx * T[4] + sy * T[5] + sz * T[6]) + T[7];
-      const float az = (sx * T[8] + sy * T[9] + sz * T[10]) + T[11];
-      const float dx = ref_corr[3 * i] - ax, dy = ref_corr[3 * i + 1] - ay, dz = ref_corr[3 * i + 2] - az;
-      w[i] = sqrtf(dx * dx + dy * dy + dz * dz) < radius ? corr_scores[i] : 0.f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const CorrSeg& sg = g == 0 ? near_scores : far_scores;
+      float* wout = g == 0 ? s_w : w + n0;
+      for (int i = threadIdx.x; i < sg.n; i += blockDim.x) {
+        const float sx = sg.src[3 * i], sy = sg.src[3 * i + 1], sz = sg.src[3 * i + 2];
+        const float ax = (sx * T[0] + sy * T[1] + sz * T[2]) + T[3];
+        const float ay = (sx * T[4] + sy * T[5] + sz * T[6]) + T[7];
+        const float az = (sx * T[8] + sy * T[9] + sz * T[10]) + T[11];
+        const float dx = sg.ref[3 * i] - ax, dy = sg.ref[3 * i + 1] - ay, dz = sg.ref[3 * i + 2] - az;
+        wout[i] = sqrtf(dx * dx + dy * dy + dz * dz) < radius ? sg.w[i] : 0.f;
+      }
     }
     __syncthreads();
   };
@@ -327,13 +389,13 @@ __global__ void __launch_bounds__(1024) lgr_refine_kernel(const float* __restric
     rescore();
   } else {
     // degenerate: initialise with all correspondences (local_global_registration.py:180-185)
-    block_procrustes(src_corr, ref_corr, corr_scores, C, eps, sh, T);
+    block_procrustes(near_scores, far_scores, eps, sh, T);
     rescore();
   }
-  block_procrustes(src_corr, ref_corr, w, C, eps, sh, T);
+  block_procrustes(near_w, far_w, eps, sh, T);
   for (int s = 0; s < steps - 1; ++s) {
     rescore();
-    block_procrustes(src_corr, ref_corr, w, C, eps, sh, T);
+    block_procrustes(near_w, far_w, eps, sh, T);
   }
   if (threadIdx.x < 12) T_out[threadIdx.x] = T[threadIdx.x];
   if (threadIdx.x >= 12 && threadIdx.x < 16) T_out[threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
@@ -345,10 +407,10 @@ __global__ void __launch_bounds__(kLgrThreads) procrustes_batched_kernel(const f
                                                                          float* __restrict__ T_out /* (B,4,4) */) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double sh[32];
+  __shared__ float sh[kLgrShFloats];
   __shared__ float T[12];
   const long long b = blockIdx.x;
-  block_procrustes(src + b * n * 3, ref + b * n * 3, w + b * n, n, eps, sh, T);
+  block_procrustes(CorrSeg{src + b * n * 3, ref + b * n * 3, w + b * n, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, sh, T);
   if (threadIdx.x < 12) T_out[b * 16 + threadIdx.x] = T[threadIdx.x];
   if (threadIdx.x >= 12 && threadIdx.x < 16) T_out[b * 16 + threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
 }
@@ -399,8 +461,8 @@ extern "C" int gr_local_global_registration(const float* matching_scores, int P,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)K * (K + 1) * sizeof(float);
   if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(lgr_correspondence_kernel), (int)smem));
-  GR_CHECK_CUDA(launch_pdl(lgr_correspondence_kernel, dim3(P), dim3(kLgrThreads), (size_t)(smem), st, matching_scores, K, ld, ref_knn_masks, src_knn_masks, topk,
-                                                           confidence_threshold, mutual, counts, cand_rc, cand_score));
+  GR_CHECK_CUDA(launch_pdl(lgr_correspondence_kernel, dim3(P), dim3(kCorrThreads), (size_t)(smem), st, matching_scores, K, ld, ref_knn_masks, src_knn_masks, topk,
+                                                           confidence_threshold, counts, cand_rc, cand_score));
   GR_CHECK_LAUNCH("lgr_correspondence_kernel");
   GR_CHECK_CUDA(launch_pdl(lgr_compact_kernel, dim3(P), dim3(128), (size_t)(0), st, counts, P, cap_pp, cand_rc, cand_score, ref_knn_points, src_knn_points, K, ref_corr_points,
                                         src_corr_points, corr_scores, offsets, num_corr));
@@ -408,8 +470,10 @@ extern "C" int gr_local_global_registration(const float* matching_scores, int P,
   GR_CHECK_CUDA(launch_pdl(lgr_hypothesis_kernel, dim3(P), dim3(kLgrThreads), (size_t)(0), st, ref_corr_points, src_corr_points, corr_scores, offsets, P, correspondence_threshold,
                                                    acceptance_radius, 1e-5f, T_local, inliers));
   GR_CHECK_LAUNCH("lgr_hypothesis_kernel");
-  GR_CHECK_CUDA(launch_pdl(lgr_refine_kernel, dim3(1), dim3(1024), (size_t)(0), st, ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers, acceptance_radius,
-                                        1e-5f, num_refinement_steps, w, transform, counts + P));
+  const size_t refine_smem = (size_t)kRefineCap * 8 * sizeof(float);
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(lgr_refine_kernel), (int)refine_smem));
+  GR_CHECK_CUDA(launch_pdl(lgr_refine_kernel, dim3(1), dim3(kRefineThreads), refine_smem, st, ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers,
+                           acceptance_radius, 1e-5f, num_refinement_steps, kRefineCap, w, transform, counts + P));
   GR_CHECK_LAUNCH("lgr_refine_kernel");
   return GR_OK;
 }

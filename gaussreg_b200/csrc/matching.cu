@@ -305,6 +305,108 @@ __device__ __forceinline__ void sinkhorn_lse_pass128(const float* __restrict__ p
   }
 }
 
+// Steady-state form of the K = 128 pass (every iteration but the first).  Same arithmetic per term as
+// sinkhorn_lse_pass128<false>, restructured for throughput: no branch inside the term loops (masked lines are computed and
+// discarded; a branch per line serialised the eight exp chains), compile-time strides so that every shared-memory
+// address is base + immediate, the dustbin-column terms of the warp's eight lines evaluated by eight lanes at once, and
+// the eight line totals reduced with a transposing butterfly (9 shuffles instead of 40).  The summation tree differs
+// from the generic pass in the last bits; it is fixed, so results are reproducible run to run.
+template <bool EXP2, bool ROWPASS>
+__device__ __forceinline__ void sinkhorn_lse_steady128(const float* __restrict__ ps, const float* __restrict__ add,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       float masked_below, int warp, int lane) {
+  constexpr int K = 128, K1 = K + 1;
+  constexpr int si = ROWPASS ? K1 : 1, sj = ROWPASS ? 1 : K1;
+  if (warp > 16) return;
+  const bool reg = warp < 16;              // warps 0-15: lines warp + 16 r; warp 16: the dustbin line (eight copies of it)
+  const int nl = reg ? 8 : 1;
+  const int ibase = reg ? warp : K;
+  const int ls = reg ? 16 * si : 0;        // stride between the warp's lines
+  const float* base = ps + ibase * si + lane * sj;
+  float a[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) a[t] = add[lane + 32 * t];
+  const float ad = add[K];
+  float shift[8], sm[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = ibase + (reg ? 16 * r : 0);
+    shift[r] = bias[i] - out[i];
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float arg = base[r * ls + 32 * t * sj] + a[t] - shift[r];
+      s += EXP2 ? ex2_approx(arg) : __expf(arg);
+    }
+    sm[r] = s;
+  }
+  // line L = (lane >> 2) & 7 ends up on lanes 4L .. 4L+3
+  const int L = (lane >> 2) & 7;
+  const int iL = ibase + (reg ? 16 * L : 0);
+  const float my_bias = bias[iL];
+  const float my_shift = my_bias - out[iL];
+  const bool my_live = L < nl && my_bias > masked_below;
+  const float dust_arg = ps[iL * si + K * sj] + ad - my_shift;
+  const float dust = EXP2 ? ex2_approx(dust_arg) : __expf(dust_arg);
+  float v4[4], v2[2], my_sum;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = hi ? sm[k] : sm[k + 4], keep = hi ? sm[k + 4] : sm[k];
+      v4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = hi ? v4[k] : v4[k + 2], keep = hi ? v4[k + 2] : v4[k];
+      v2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+    my_sum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  my_sum += __shfl_xor_sync(0xffffffffu, my_sum, 2);
+  my_sum += __shfl_xor_sync(0xffffffffu, my_sum, 1);
+  my_sum += dust;
+  float fin_shift = my_shift;
+  // Underflow / overflow repair, as in sinkhorn_lse_pass128: redo the line with its true maximum (whole warp).
+  unsigned bad = __ballot_sync(0xffffffffu, (lane & 3) == 0 && my_live && !(my_sum > 1e-30f && my_sum < 1e30f));
+  while (bad) {
+    const int src = __ffs(bad) - 1;
+    bad &= bad - 1;
+    const int r = src >> 2;
+    const int i = ibase + (reg ? 16 * r : 0);
+    float m = lane == 0 ? ps[i * si + K * sj] + ad : -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) m = fmaxf(m, ps[i * si + (lane + 32 * t) * sj] + a[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float arg = ps[i * si + (lane + 32 * t) * sj] + a[t] - m;
+      s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+    }
+    if (lane == 0) {
+      const float arg = ps[i * si + K * sj] + ad - m;
+      s2 += EXP2 ? ex2_approx(arg) : __expf(arg);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == src) { my_sum = s2; fin_shift = m; }
+  }
+  if ((lane & 3) == 0 && L < nl)
+    out[iL] = my_live ? my_bias - ((EXP2 ? log2f(my_sum) : logf(my_sum)) + fin_shift) : 0.f;
+}
+
 constexpr int kSink128Threads = 17 * 32;
 
 template <bool FAST128, bool EXP2 = false>
@@ -358,10 +460,10 @@ __global__ void __launch_bounds__(FAST128 ? kSink128Threads : kSinkThreads, FAST
     // u_i = log_mu_i - logsumexp_j(ps_ij + v_j) ; v_j = log_nu_j - logsumexp_i(ps_ij + u_i)
     if (FAST128) {
       if (it == 0) sinkhorn_lse_pass128<true, EXP2>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
-      else sinkhorn_lse_pass128<false, EXP2>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
+      else sinkhorn_lse_steady128<EXP2, true>(ps, v, lmu, u, masked_below, warp, lane);
       __syncthreads();
       if (it == 0) sinkhorn_lse_pass128<true, EXP2>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
-      else sinkhorn_lse_pass128<false, EXP2>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
+      else sinkhorn_lse_steady128<EXP2, false>(ps, u, lnu, v, masked_below, warp, lane);
       __syncthreads();
       continue;
     }
@@ -384,6 +486,220 @@ __global__ void __launch_bounds__(FAST128 ? kSink128Threads : kSinkThreads, FAST
     } else {
       o[t] = (ps[t] + u[i] + v[j]) - norm;
     }
+  }
+}
+
+// ---- S1, K = 128: scaling form ---------------------------------------------------------------------------------
+// The log-domain iteration u_i = log mu_i - LSE_j(ps_ij + v_j), v_j = log nu_j - LSE_i(ps_ij + u_i) spends one exp per
+// matrix entry per half step: 2 * 100 * 129^2 exps per patch, SFU-bound (0.47 ms for 256 patches even with both
+// passes branch-free).  With the potentials split as u = U + log2 a, v = V + log2 b and Kt_ij = 2^(ps_ij + U_i + V_j)
+// held fixed for a block of iterations, the same recurrence is
+//     a_i = mu_i / sum_j Kt_ij b_j ,   b_j = nu_j / sum_i Kt_ij a_i          (one FMA per entry per half step)
+// and every kScaleBlock iterations a, b are absorbed into U, V and Kt is rebuilt from ps (so rounding does not
+// accumulate in Kt and its entries stay <= ~1).  The first iteration runs in the log domain with the true row/column
+// maxima, which is what bounds Kt.  Kt lives in registers: warp w < 16 owns rows w + 16 r (r < 8), lane l the columns
+// l + 32 t (t < 4); warp 16 owns the dustbin row; the dustbin column entry of row L sits on lane 4 L.  Row sums are
+// reduced inside the warp (transposing butterfly), column sums through 17 per-warp partial vectors in shared memory,
+// added in a fixed order.  Should any sum leave [1e-30, 1e30] (scores far outside the trained range), the CTA starts
+// over with the plain log-domain kernel body, so the result is always the robust one.
+constexpr int kScaleBlock = 11;
+
+__global__ void __launch_bounds__(kSink128Threads, 2) sinkhorn_scaling128_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+                                                                                 const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
+                                                                                 int iters, float inf, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int K = 128, K1 = K + 1;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  extern __shared__ float sm[];
+  float* ps = sm;               // K1*K1, log2 units
+  float* u = ps + K1 * K1;      // potentials, log2 units
+  float* v = u + K1;
+  float* lmu = v + K1;          // log2 marginals
+  float* lnu = lmu + K1;
+  float* mu = lnu + K1;         // marginals
+  float* nu = mu + K1;
+  float* a_s = nu + K1;         // scalings of the current block
+  float* b_s = a_s + K1;
+  float* part = b_s + K1;       // 17 x K1 column partials
+  __shared__ int s_cnt[2];
+  __shared__ int s_trouble;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned char* rm = row_masks + (long long)b * K;
+  const unsigned char* cm = col_masks + (long long)b * K;
+  const float alpha = *alpha_p;
+  if (tid < 2) s_cnt[tid] = 0;
+  if (tid == 2) s_trouble = 0;
+  __syncthreads();
+  {
+    int a = 0, c = 0;
+    for (int i = tid; i < K; i += blockDim.x) { a += rm[i] != 0; c += cm[i] != 0; }
+    a = warp_sum(a); c = warp_sum(c);
+    if (lane == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], c); }
+  }
+  for (int t = tid; t < K1 * K1; t += blockDim.x) {
+    const int i = t / K1, j = t % K1;
+    const bool masked = (i < K && !rm[i]) || (j < K && !cm[j]);
+    float val = (i < K && j < K) ? scores[((long long)b * K + i) * K + j] : alpha;
+    val = masked ? -inf : val;
+    ps[t] = val * kLog2e;
+  }
+  __syncthreads();
+  const float nvr = (float)s_cnt[0], nvc = (float)s_cnt[1];
+  const float norm = -logf(nvr + nvc);
+  const float masked_below = -0.5f * inf;
+  for (int i = tid; i < K1; i += blockDim.x) {
+    float m = i < K ? norm : logf(nvc) + norm;
+    float n = i < K ? norm : logf(nvr) + norm;
+    if (i < K && !rm[i]) m = -inf;
+    if (i < K && !cm[i]) n = -inf;
+    m *= kLog2e; n *= kLog2e;
+    lmu[i] = m; lnu[i] = n; u[i] = 0.f; v[i] = 0.f;
+    mu[i] = m > masked_below ? ex2_approx(m) : 0.f;
+    nu[i] = n > masked_below ? ex2_approx(n) : 0.f;
+  }
+  __syncthreads();
+  int done = 0;
+  if (iters > 0) {
+    sinkhorn_lse_pass128<true, true>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
+    __syncthreads();
+    sinkhorn_lse_pass128<true, true>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
+    __syncthreads();
+    done = 1;
+  }
+  // roles
+  const bool reg = warp < 16;
+  const int nl = reg ? 8 : 1;
+  const int ibase = reg ? warp : K;
+  const int L = (lane >> 2) & 7;
+  const int iL = ibase + (reg ? 16 * L : 0);
+  const bool fin = (lane & 3) == 0 && L < nl;        // this lane finishes row iL
+  const bool live_row = fin && lmu[iL] > masked_below;
+  const float my_mu = fin ? mu[iL] : 0.f;
+  const bool col_owner = tid < K1;
+  const bool live_col = col_owner && lnu[col_owner ? tid : 0] > masked_below;
+  const float my_nu = col_owner ? nu[tid] : 0.f;
+  bool trouble = false;
+  while (done < iters) {
+    const int m = iters - done < kScaleBlock ? iters - done : kScaleBlock;
+    float k[8][4];
+    {
+      float vj[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) vj[t] = v[lane + 32 * t];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = ibase + (reg ? 16 * r : 0);
+        const float ui = u[i];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) k[r][t] = r < nl ? ex2_approx(ps[i * K1 + lane + 32 * t] + ui + vj[t]) : 0.f;
+      }
+    }
+    const float kd = fin ? ex2_approx(ps[iL * K1 + K] + u[iL] + v[K]) : 0.f;
+    if (col_owner) b_s[tid] = 1.f;
+    __syncthreads();
+    float my_a = 0.f, my_b = 0.f;
+    for (int it = 0; it < m; ++it) {
+      // ---- a_i = mu_i / sum_j Kt_ij b_j
+      float sr[8];
+      {
+        float bj[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bj[t] = b_s[lane + 32 * t];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          float acc = k[r][0] * bj[0];
+#pragma unroll
+          for (int t = 1; t < 4; ++t) acc = fmaf(k[r][t], bj[t], acc);
+          sr[r] = acc;
+        }
+      }
+      float v4[4], v2[2], my_s;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float send = hi ? sr[q] : sr[q + 4], keep = hi ? sr[q + 4] : sr[q];
+          v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float send = hi ? v4[q] : v4[q + 2], keep = hi ? v4[q + 2] : v4[q];
+          v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool hi = lane & 4;
+        const float send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+        my_s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      my_s += __shfl_xor_sync(0xffffffffu, my_s, 2);
+      my_s += __shfl_xor_sync(0xffffffffu, my_s, 1);
+      my_s = fmaf(kd, b_s[K], my_s);
+      if (fin) {
+        my_a = live_row ? my_mu / my_s : 0.f;
+        if (live_row && !(my_s > 1e-30f && my_s < 1e30f)) s_trouble = 1;
+        a_s[iL] = my_a;
+      }
+      __syncthreads();
+      // ---- b_j = nu_j / sum_i Kt_ij a_i
+      {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float ar = a_s[ibase + (reg ? 16 * r : 0)];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] = fmaf(k[r][t], ar, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) part[warp * K1 + lane + 32 * t] = acc[t];
+        float d = kd * my_a;  // zero off the finishing lanes
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 8);
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        if (lane == 0) part[warp * K1 + K] = d;
+      }
+      __syncthreads();
+      if (col_owner) {
+        float tj = part[tid];
+#pragma unroll
+        for (int w = 1; w < 17; ++w) tj += part[w * K1 + tid];
+        my_b = live_col ? my_nu / tj : 0.f;
+        if (live_col && !(tj > 1e-30f && tj < 1e30f)) s_trouble = 1;
+        b_s[tid] = my_b;
+      }
+      __syncthreads();
+    }
+    if (live_row) u[iL] += log2f(my_a);
+    if (live_col) v[tid] += log2f(my_b);
+    done += m;
+    __syncthreads();
+    trouble = s_trouble != 0;
+    if (trouble) break;
+  }
+  if (trouble) {  // out-of-range sums: redo the patch with the log-domain recurrence
+    for (int i = tid; i < K1; i += blockDim.x) { u[i] = 0.f; v[i] = 0.f; }
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+      if (it == 0) sinkhorn_lse_pass128<true, true>(ps, K1, 1, v, lmu, u, masked_below, warp, lane);
+      else sinkhorn_lse_steady128<true, true>(ps, v, lmu, u, masked_below, warp, lane);
+      __syncthreads();
+      if (it == 0) sinkhorn_lse_pass128<true, true>(ps, 1, K1, u, lnu, v, masked_below, warp, lane);
+      else sinkhorn_lse_steady128<true, false>(ps, u, lnu, v, masked_below, warp, lane);
+      __syncthreads();
+    }
+  }
+  float* o = out + (long long)b * K1 * K1;
+  for (int t = tid; t < K1 * K1; t += blockDim.x) {
+    const int i = t / K1, j = t % K1;
+    const bool masked = (i < K && !rm[i]) || (j < K && !cm[j]);
+    float val = (i < K && j < K) ? scores[((long long)b * K + i) * K + j] : alpha;
+    val = masked ? -inf : val;
+    o[t] = (val + u[i] * kLn2 + v[j] * kLn2) - norm;
   }
 }
 
@@ -457,7 +773,14 @@ extern "C" int gr_sinkhorn(const float* scores, const uint8_t* row_masks, const 
   if (fast_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN128"); fast_knob = e ? atoi(e) : 1; }
   static int exp2_knob = -1;
   if (exp2_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN_EXP2"); exp2_knob = e ? atoi(e) : 1; }  // measured: 0.63 -> 0.52 ms
-  if (K == 128 && fast_knob && exp2_knob) {
+  static int scaling_knob = -1;
+  if (scaling_knob < 0) { const char* e = getenv("GAUSSREG_SINKHORN_SCALING"); scaling_knob = e ? atoi(e) : 1; }
+  if (K == 128 && fast_knob && exp2_knob && scaling_knob) {
+    const size_t smem_sc = ((size_t)(K + 1) * (K + 1) + (8 + 17) * (size_t)(K + 1)) * sizeof(float);
+    GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_scaling128_kernel), (int)smem_sc));
+    GR_CHECK_CUDA(launch_pdl(sinkhorn_scaling128_kernel, dim3(P), dim3(kSink128Threads), smem_sc, static_cast<cudaStream_t>(stream), scores, row_masks, col_masks, alpha,
+                             num_iterations, inf, out));
+  } else if (K == 128 && fast_knob && exp2_knob) {
     GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(sinkhorn_kernel<true, true>), (int)smem));
     GR_CHECK_CUDA(launch_pdl(sinkhorn_kernel<true, true>, dim3(P), dim3(kSink128Threads), (size_t)(smem), static_cast<cudaStream_t>(stream), scores, row_masks, col_masks, alpha,
                                                                                                 K, num_iterations, inf, out));
