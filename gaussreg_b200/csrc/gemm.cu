@@ -394,15 +394,20 @@ __device__ __forceinline__ void sm_cp_async4(void* dst, const void* src, int src
 
 // A_VEC = false: A rows are not 16-byte addressable (odd pitch or K, e.g. the (N,N) attention probabilities with odd N):
 // its panel is fetched with 4-byte cp.async instead
-template <bool TRANSB, bool A_VEC>
-__global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq) {
+template <bool TRANSB, bool A_VEC, int KQ>
+__global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) float tiny_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int PA = kq + 4;                     // A panel [32][kq + 4] (and the (N,K) B panel)
-  const int PBn = 40;                        // (K,N) B panel [kq][40]
-  const int a_elems = 32 * PA, b_elems = TRANSB ? 32 * PA : kq * PBn;
+  // KQ (the K range of one warp per pass) is a template parameter: every panel index below is then a compile-time
+  // constant and the load loops unroll into plain cp.async sequences -- with a run-time kq the index arithmetic
+  // (divisions by the chunk count) was two thirds of the instructions of this latency-bound kernel.
+  constexpr int PA = KQ + 4;                 // A panel [32][KQ + 4] (and the (N,K) B panel)
+  constexpr int PBn = 40;                    // (K,N) B panel [KQ][40]
+  constexpr int a_elems = 32 * PA, b_elems = TRANSB ? 32 * PA : KQ * PBn;
+  constexpr int HALF = KQ / 2;               // first commit group covers [0, HALF), the second [HALF, KQ)
+  constexpr int C4 = HALF / 4;               // 16-byte chunks per row and part: 2, 4 or 8
   float* As = tiny_smem + warp * (a_elems + b_elems);
   float* Bs = As + a_elems;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -418,39 +423,47 @@ __global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  const int half = (kq / 2 + 7) & ~7;        // first commit group covers [0, half), the second [half, kq)
-  for (int kpass = 0; kpass < p.K; kpass += 4 * kq) {
-    const int kw = kpass + warp * kq;         // this warp's K range [kw, kw + kq)
+  for (int kpass = 0; kpass < p.K; kpass += 4 * KQ) {
+    const int kw = kpass + warp * KQ;         // this warp's K range [kw, kw + KQ)
     if (kpass > 0) __syncwarp();
     // ---- issue this warp's loads: two groups
+#pragma unroll
     for (int part = 0; part < 2; ++part) {
-      const int kb = part == 0 ? 0 : half, ke = part == 0 ? half : kq;
-      const int c4 = (ke - kb) >> 2;           // 16-byte chunks per row in this part
+      constexpr int kb0 = 0;
+      const int kb = part == 0 ? kb0 : HALF;
       if (A_VEC) {
-        for (int e = lane; e < 32 * c4; e += 32) {
-          const int r = e / c4, c = e % c4;
+#pragma unroll
+        for (int i = 0; i < C4; ++i) {
+          const int e = lane + 32 * i;
+          const int r = e / C4, c = e % C4;
           const int gm = m0 + r, gk = kw + kb + 4 * c;
           const bool ok = gm < p.M && gk < p.K;
-          sm_cp_async16(As + r * PA + kb + 4 * c, A + (ok ? (long long)gm * p.lda + gk : 0), ok ? 16 : 0);
+          const int rest = (p.K - gk) * 4;  // a row may end inside the chunk (K % 4 != 0 on a padded pitch): zero fill
+          sm_cp_async16(As + r * PA + kb + 4 * c, A + (ok ? (long long)gm * p.lda + gk : 0), ok ? (rest < 16 ? rest : 16) : 0);
         }
       } else {
-        const int c1 = ke - kb;
-        for (int e = lane; e < 32 * c1; e += 32) {
-          const int r = e / c1, c = e % c1;
+#pragma unroll 4
+        for (int i = 0; i < HALF; ++i) {
+          const int e = lane + 32 * i;
+          const int r = e / HALF, c = e % HALF;
           const int gm = m0 + r, gk = kw + kb + c;
           const bool ok = gm < p.M && gk < p.K;
           sm_cp_async4(As + r * PA + kb + c, A + (ok ? (long long)gm * p.lda + gk : 0), ok ? 4 : 0);
         }
       }
       if (TRANSB) {
-        for (int e = lane; e < 32 * c4; e += 32) {
-          const int r = e / c4, c = e % c4;
+#pragma unroll
+        for (int i = 0; i < C4; ++i) {
+          const int e = lane + 32 * i;
+          const int r = e / C4, c = e % C4;
           const int gn = n0 + r, gk = kw + kb + 4 * c;
           const bool ok = gn < p.N && gk < p.K;
           sm_cp_async16(Bs + r * PA + kb + 4 * c, B + (ok ? (long long)gn * p.ldb + gk : 0), ok ? 16 : 0);
         }
       } else {
-        for (int e = lane; e < (ke - kb) * 8; e += 32) {
+#pragma unroll
+        for (int i = 0; i < HALF / 4; ++i) {  // HALF rows of eight 16-byte chunks
+          const int e = lane + 32 * i;
           const int r = kb + (e >> 3), c = e & 7;
           const int gk = kw + r, gn = n0 + 4 * c;
           const bool ok = gk < p.K && gn < p.N;
@@ -460,17 +473,19 @@ __global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // ---- multiply: first half while the second is still in flight
+#pragma unroll
     for (int part = 0; part < 2; ++part) {
       if (part == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      const int kb = part == 0 ? 0 : half, ke = part == 0 ? half : kq;
-      for (int k8 = kb; k8 < ke; k8 += 8) {
-        if (kw + k8 >= p.K) break;             // zero-filled tail
+      const int kb = part == 0 ? 0 : HALF;
+#pragma unroll
+      for (int k8 = 0; k8 < HALF; k8 += 8) {
+        if (kw + kb + k8 >= p.K) break;        // zero-filled tail
         unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const float* ap = As + (16 * i + g) * PA + k8 + t;
+          const float* ap = As + (16 * i + g) * PA + kb + k8 + t;
           const float a0 = ap[0], a1 = ap[8 * PA], a2 = ap[4], a3 = ap[8 * PA + 4];
           ah[i][0] = __float_as_uint(a0); ah[i][1] = __float_as_uint(a1); ah[i][2] = __float_as_uint(a2); ah[i][3] = __float_as_uint(a3);
           al[i][0] = sm_lo_bits(a0); al[i][1] = sm_lo_bits(a1); al[i][2] = sm_lo_bits(a2); al[i][3] = sm_lo_bits(a3);
@@ -478,8 +493,8 @@ __global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float b0, b1;
-          if (TRANSB) { const float* bp = Bs + (8 * j + g) * PA + k8 + t; b0 = bp[0]; b1 = bp[4]; }
-          else { const float* bp = Bs + (k8 + t) * PBn + 8 * j + g; b0 = bp[0]; b1 = bp[4 * PBn]; }
+          if (TRANSB) { const float* bp = Bs + (8 * j + g) * PA + kb + k8 + t; b0 = bp[0]; b1 = bp[4]; }
+          else { const float* bp = Bs + (kb + k8 + t) * PBn + 8 * j + g; b0 = bp[0]; b1 = bp[4 * PBn]; }
           bh[j][0] = __float_as_uint(b0); bh[j][1] = __float_as_uint(b1);
           bl[j][0] = sm_lo_bits(b0); bl[j][1] = sm_lo_bits(b1);
         }
@@ -526,27 +541,31 @@ __global__ void __launch_bounds__(128) gemm_mma_tiny_kernel(GemmParams p, int kq
   }
 }
 
-static int launch_tiny(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
-  int kq = ((p.K + 3) / 4 + 7) & ~7;
-  if (kq > kTinyKq) kq = kTinyKq;
-  if (kq < 16) kq = 16;
-  const int PA = kq + 4;
-  const size_t per_warp = (size_t)32 * PA + (transb ? (size_t)32 * PA : (size_t)kq * 40);
-  size_t smem = 4 * per_warp * sizeof(float);
-  const size_t red = 4 * 32 * 33 * sizeof(float);
-  if (smem < red) smem = red;
+template <bool TB, bool AV, int KQ>
+static int launch_tiny_kq(const GemmParams& p, int batch, cudaStream_t st) {
+  constexpr int PA = KQ + 4;
+  constexpr size_t per_warp = (size_t)32 * PA + (TB ? (size_t)32 * PA : (size_t)KQ * 40);
+  constexpr size_t red = 4 * 32 * 33 * sizeof(float);
+  constexpr size_t smem = 4 * per_warp * sizeof(float) > red ? 4 * per_warp * sizeof(float) : red;
   dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, batch);
-  const bool a_vec = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && p.lda % 4 == 0 && p.sA % 4 == 0 && p.K % 4 == 0;
-#define GR_TINY(TB, AV)                                                                                                  \
-  do {                                                                                                                   \
-    if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_mma_tiny_kernel<TB, AV>), (int)smem)); \
-    GR_CHECK_CUDA(launch_pdl(gemm_mma_tiny_kernel<TB, AV>, grid, dim3(128), smem, st, p, kq));                                                        \
-  } while (0)
-  if (transb) { if (a_vec) GR_TINY(true, true); else GR_TINY(true, false); }
-  else { if (a_vec) GR_TINY(false, true); else GR_TINY(false, false); }
-#undef GR_TINY
+  if (smem > 48 * 1024) GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_mma_tiny_kernel<TB, AV, KQ>), (int)smem));
+  GR_CHECK_CUDA(launch_pdl(gemm_mma_tiny_kernel<TB, AV, KQ>, grid, dim3(128), smem, st, p));
   GR_CHECK_LAUNCH("gemm_mma_tiny_kernel");
   return GR_OK;
+}
+
+template <bool TB, bool AV>
+static int launch_tiny_av(const GemmParams& p, int batch, cudaStream_t st) {
+  // K range per warp and pass: a quarter of K, rounded up to 16 / 32 / 64 (K <= 256 runs in one pass)
+  if (p.K <= 64) return launch_tiny_kq<TB, AV, 16>(p, batch, st);
+  if (p.K <= 128) return launch_tiny_kq<TB, AV, 32>(p, batch, st);
+  return launch_tiny_kq<TB, AV, kTinyKq>(p, batch, st);
+}
+
+static int launch_tiny(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
+  const bool a_vec = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && p.lda % 4 == 0 && p.sA % 4 == 0;
+  if (transb) return a_vec ? launch_tiny_av<true, true>(p, batch, st) : launch_tiny_av<true, false>(p, batch, st);
+  return a_vec ? launch_tiny_av<false, true>(p, batch, st) : launch_tiny_av<false, false>(p, batch, st);
 }
 
 static bool mma_knob() {

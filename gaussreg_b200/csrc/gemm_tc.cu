@@ -530,7 +530,7 @@ struct CfgPersist {
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kOpBytes = kABytes + 2 * kBBytes;
   static constexpr int kOps = BN == 128 ? 2 : 3;
-  static constexpr int kRaw = BN == 128 ? 5 : 4;
+  static constexpr int kRaw = BN == 128 ? 5 : 4;  // (a 7-deep raw ring with 2 operand stages measured the same: not load-latency bound)
   static constexpr int kEpiBytes = 8 * 32 * 36 * 4 + 4 * BN * 8 + BN * 16;  // 8 transposition tiles | gn_col | gn_cold
   static constexpr int kSmemBytes = kRaw * kABytes + kOps * kOpBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
 };

@@ -23,6 +23,14 @@ int gr_softmax_rows(float* x, int64_t rows, int cols, void* stream);
 }
 
 namespace gr {
+int rpe_attention_probs_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* U, int64_t u_head, const float* qb,
+                           const float* bp, const float* emb, int N, float* P, int64_t ldp, void* stream);
+int cross_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, int N, int M, float* out,
+                    int64_t ldo, void* stream);
+bool cross_attention_fits(int M);
+}
+
+namespace gr {
 
 // ---- fused AttentionOutput (output_layer.py:14-21): y = LayerNorm(x + squeeze(relu(expand(x)))) -----------------
 // Three superpoint-sized launches (two GEMMs of ~0.1 GFLOP and a LayerNorm) are pure latency; here a CTA owns 8 rows,
@@ -136,9 +144,9 @@ static size_t carve_tf(void* ws, size_t ws_bytes, int N, int Nt, int C, int H, T
   TfWs w;
   w.x = c.take<float>((size_t)Nt * C);
   w.qkv = c.take<float>((size_t)Nt * 3 * C);
-  w.U = c.take<float>((size_t)H * N * C);
+  w.U = c.take<float>((size_t)H * Nt * C);
   w.qb = c.take<float>((size_t)H * N);
-  w.P = c.take<float>((size_t)H * N * N);
+  w.P = c.take<float>((size_t)H * N * ((N + 3) & ~3));
   w.hid = c.take<float>((size_t)Nt * C);
   w.att = c.take<float>((size_t)Nt * C);
   w.ffn = c.take<float>((size_t)Nt * 2 * C);
@@ -175,27 +183,41 @@ static int post_attention(const gr_layer_weights& L, float* x, const float* hid,
   return GR_OK;
 }
 
+static bool tf_fused() {  // 0: round-2a sequence (per-cloud U / qb products, three-launch cross-attention)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_TF_FUSED"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 // RPE self-attention of BOTH clouds (rows [0,N0) and [N0,N0+N1) of the stacked x): every row-wise product (q|k|v,
-// out-projection, FFN) and both LayerNorms run once on the N0+N1 stacked rows; only the N x N attention itself is per
-// cloud.
+// U = q_h W_p,h, out-projection, FFN) and both LayerNorms run once on the N0+N1 stacked rows; only the N x N attention
+// itself is per cloud.  The q.b_p term is computed inside the score kernel.
 static int self_layer(const gr_layer_weights& L, float* x, int N0, int N1, const float* emb0, const float* emb1, int C, int H,
                       TfWs& w, void* st) {
   const int dh = C / H, Nt = N0 + N1;
   if (!(L.wqkv && L.bqkv)) return GR_ERR_BAD_ARG;
   GR_TRY(linear(x, Nt, C, L.wqkv, L.bqkv, 3 * C, w.qkv, 0, st));
   const int64_t ld = 3 * C;
+  const bool fused = tf_fused() && C == 256 && H == 4 && (size_t)H * (N0 > N1 ? N0 : N1) * sizeof(float) <= 100 * 1024;
+  if (fused)  // U[h] (Nt, C) = q_h (Nt, dh) @ W_p[h*dh:(h+1)*dh, :] for both clouds at once   (see attention.cu)
+    GR_TRY(gr_gemm(w.qkv, ld, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)Nt * C, Nt, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0,
+                   0, st));
   for (int c = 0; c < 2; ++c) {
     const int N = c == 0 ? N0 : N1, off = c == 0 ? 0 : N0;
     const float* q = w.qkv + (size_t)off * ld;
     const float *k = q + C, *v = q + 2 * C;
     const float* emb = c == 0 ? emb0 : emb1;
-    // U[h] = q_h (N,dh) @ W_p[h*dh:(h+1)*dh, :] ; qb[h] = q_h @ b_p[h*dh:(h+1)*dh]   (see attention.cu)
-    GR_TRY(gr_gemm(q, ld, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0,
-                   st));
-    GR_TRY(gr_gemm(q, ld, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
-    GR_TRY(gr_rpe_attention_probs_ld(q, ld, k, ld, w.U, w.qb, emb, N, C, H, w.P, st));
-    GR_TRY(gr_gemm(w.P, N, (int64_t)N * N, v, ld, dh, 0, w.hid + (size_t)off * C, C, dh, N, dh, N, H, 1.f, nullptr, nullptr, nullptr, 0,
-                   0, 0, st));
+    const int64_t ldp = fused ? ((N + 3) & ~3) : N;
+    if (fused) {
+      GR_TRY(rpe_attention_probs_ex(q, ld, k, ld, w.U + (size_t)off * C, (int64_t)Nt * C, nullptr, L.bp, emb, N, w.P, ldp, st));
+    } else {
+      GR_TRY(gr_gemm(q, ld, dh, L.wp, C, (int64_t)dh * C, 0, w.U, C, (int64_t)N * C, N, C, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0,
+                     0, st));
+      GR_TRY(gr_gemm(q, ld, dh, L.bp, dh, dh, 1, w.qb, 1, N, N, 1, dh, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
+      GR_TRY(gr_rpe_attention_probs_ld(q, ld, k, ld, w.U, w.qb, emb, N, C, H, w.P, st));
+    }
+    GR_TRY(gr_gemm(w.P, ldp, (int64_t)N * ldp, v, ld, dh, 0, w.hid + (size_t)off * C, C, dh, N, dh, N, H, 1.f, nullptr, nullptr, nullptr,
+                   0, 0, 0, st));
   }
   return post_attention(L, x, w.hid, Nt, C, w, st);
 }
@@ -225,6 +247,26 @@ static int cross_layer(const gr_layer_weights& L, float* x, int N, const float* 
   GR_TRY(gr_softmax_rows(w.P, (int64_t)H * N, M, st));
   GR_TRY(gr_gemm(w.P, M, (int64_t)N * M, v, ldv, dh, 0, w.hid, C, dh, N, dh, M, H, 1.f, nullptr, nullptr, nullptr, 0, 0, 0, st));
   return post_attention(L, x, w.hid, N, C, w, st);
+}
+
+// One cross layer of conditional_transformer.py:107-112 (cloud 0 attends cloud 1, then cloud 1 attends the UPDATED
+// cloud 0) on the stacked x.  Everything the pre-update state determines -- q of both clouds, k|v of cloud 1 -- comes
+// out of ONE product with the packed (3C, C) weight; only k|v of the updated cloud 0 needs a second one.  Each
+// attention is one fused kernel.
+static int cross_pair(const gr_layer_weights& L, float* x, int N0, int N1, int C, TfWs& w, void* st) {
+  const int Nt = N0 + N1;
+  const int64_t ld = 3 * C;
+  float* x0 = x;
+  float* x1 = x + (size_t)N0 * C;
+  float* qkv0 = w.qkv;
+  float* qkv1 = w.qkv + (size_t)N0 * ld;
+  GR_TRY(linear(x, Nt, C, L.wqkv, L.bqkv, 3 * C, w.qkv, 0, st));
+  GR_TRY(cross_attention(qkv0, ld, qkv1 + C, ld, qkv1 + 2 * C, ld, N0, N1, w.hid, C, st));
+  GR_TRY(post_attention(L, x0, w.hid, N0, C, w, st));
+  GR_TRY(gr_gemm(x0, C, 0, L.wqkv + (size_t)C * C, C, 0, 1, qkv0 + C, ld, 0, N0, 2 * C, C, 1, 1.f, L.bqkv + C, nullptr, nullptr, 0, 0, 0,
+                 st));
+  GR_TRY(cross_attention(qkv1, ld, qkv0 + C, ld, qkv0 + 2 * C, ld, N1, N0, w.hid + (size_t)N0 * C, C, st));
+  return post_attention(L, x1, w.hid + (size_t)N0 * C, N1, C, w, st);
 }
 
 }  // namespace gr
@@ -260,8 +302,12 @@ extern "C" int gr_conditional_transformer(const gr_layer_weights* layers, int n_
       if (!emb0 || !emb1 || !L.wp || !L.bp) return GR_ERR_BAD_ARG;
       GR_TRY(self_layer(L, w.x, N0, N1, emb0, emb1, C, num_heads, w, stream));
     } else {
-      GR_TRY(cross_layer(L, x0, N0, x1, N1, C, num_heads, w, stream));
-      GR_TRY(cross_layer(L, x1, N1, x0, N0, C, num_heads, w, stream));
+      if (tf_fused() && C == 256 && num_heads == 4 && L.wqkv && L.bqkv && cross_attention_fits(N0 > N1 ? N0 : N1)) {
+        GR_TRY(cross_pair(L, w.x, N0, N1, C, w, stream));
+      } else {
+        GR_TRY(cross_layer(L, x0, N0, x1, N1, C, num_heads, w, stream));
+        GR_TRY(cross_layer(L, x1, N1, x0, N0, C, num_heads, w, stream));
+      }
     }
   }
   GR_CHECK_CUDA(cudaMemcpyAsync(feats0, x0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
