@@ -190,8 +190,10 @@ class OpProfiler:
                 work = 2.0 * a[7] * a[8] * a[9]
                 shape = (a[7], a[8], a[9], 1, 1)
                 key = "gr_linear_packed[tcgen05]" if self._lib.gr_last_gemm_path() == 1 else "gr_linear_packed[ffma]"
-            elif name == "gr_structure_embedding_fused":  # (d_idx, a_idx, rows, angle_k, div, hidden, ...)
+            elif name in ("gr_structure_embedding_fused", "gr_structure_embedding_fused_f16"):  # (d_idx, a_idx, rows, angle_k, div, hidden, ...)
                 work = 2.0 * a[2] * (1 + a[3]) * a[5] * a[5]
+                key = "gr_structure_embedding_fused"
+                self.t1_kind = "f16" if name.endswith("_f16") else "tf32"
             # algorithmic HBM bytes of the HBM-class ops (SURVEY.md section 8(d) formulas)
             elif name in ("gr_radius_neighbors", "gr_radius_neighbors_cached"):  # (q, s, ql, sl, batch, nq, ns, radius, out, ld, ...)
                 work = 12.0 * (a[5] + a[6]) + 8.0 * a[5] * a[9]

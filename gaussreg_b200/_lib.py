@@ -95,6 +95,8 @@ _SIGNATURES = {
     "gr_embedding_combine": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gr_pack_weight_tf32x3": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "gr_structure_embedding_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gr_pack_weight_f16x2": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
+    "gr_structure_embedding_fused_f16": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_rpe_attention_probs_ld": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),

@@ -11,6 +11,8 @@
 // the epilogue applies the bias / max-over-k / sum directly on the accumulators.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace gr {
@@ -511,6 +513,256 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
   }
 }
 
+// sin / cos by a 128-entry table of the full period plus a tiny polynomial: a = k pi/64 + d, |d| <= pi/128,
+//     sin a = S_k cos d + C_k sin d,   cos a = C_k cos d - S_k sin d,
+// sin d = d - d^3/6 (truncation 7e-11), cos d = 1 - d^2/2 + d^4/24 (3e-13).  The reduction is two FMAs (the products
+// k * C1, k * C2 are not rounded inside an FMA; C1 + C2 = pi/64 to 1e-16) and the table covers all four quadrants, so
+// there is no fix-up: 17 instructions for the pair instead of ~30 for sincos_cw, same accuracy class (table entries and
+// two roundings: ~1e-7 absolute).  tab[k] = (sin, cos)(k pi / 64), correctly rounded.
+__device__ __forceinline__ void sincos_tab(float a, const float2* __restrict__ tab, float* s, float* c) {
+  const float kf = rintf(a * 20.371832715762602f);
+  float d = fmaf(kf, -0.049087386578321457f, a);
+  d = fmaf(kf, 1.3659809e-09f, d);  // fp32(pi/64) - pi/64 = +1.3659809e-9
+  const float2 t = tab[__float2int_rn(kf) & 127];
+  const float d2 = d * d;
+  const float sd = fmaf(d * d2, -0.16666667f, d);
+  const float cd = fmaf(d2, fmaf(d2, 0.041666668f, -0.5f), 1.0f);
+  *s = fmaf(t.x, cd, t.y * sd);
+  *c = fmaf(t.y, cd, -(t.x * sd));
+}
+
+// ---- T1 with fp16-split operands ("3xFP16") ------------------------------------------------------------------------
+// TF32 and fp16 carry the same 11 significant bits, so x = hi + lo with two fp16 parts is exactly as accurate as the
+// two-part TF32 split -- as long as the values sit in fp16's exponent range.  Here they do by construction: the A
+// operand is sin / cos in [-1, 1] and the B operand is a static weight matrix that is pre-scaled by a power of two at
+// packing time (so that its lo parts are fp16 normals); the scale is divided out in the epilogue, exactly.  What is
+// lost is bounded absolutely, not relatively: an fp16 subnormal lo part is good to 2^-25 (3e-8) of an O(1) value.
+// kind::f16 issues K = 16 per instruction at the rate kind::tf32 issues K = 8: the three products per k-step cost half
+// the tensor-pipe time, and a 64-wide k-block fills the same 128-byte swizzled row a 32-wide fp32 block did.
+constexpr int kF16BK = 64;                                 // K elements per k-block (128-byte rows of fp16)
+constexpr int kF16KB = kEmbC / kF16BK;                     // 4 k-blocks per projection
+constexpr int kF16ATile = kEmbBM * kF16BK * 2;             // 16 KB
+constexpr int kF16BTile = kE2BN * kF16BK * 2;              // 32 KB
+constexpr int kF16StageBytes = 2 * kF16ATile + 2 * kF16BTile;  // 96 KB
+constexpr int kF16Stages = 2;
+constexpr int kF16Smem = kF16Stages * kF16StageBytes + 1024 + 256;
+
+// W (256, 256) fp32 -> per 64-wide k-block [hi 32 KB][lo 32 KB] of fp16 in the K-major SWIZZLE_128B byte order, W
+// multiplied by `scale` (a power of two) first.
+__global__ void __launch_bounds__(256) pack_weight_f16x2_kernel(const float* __restrict__ W, int N, int K, float scale,
+                                                                unsigned char* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int kb = blockIdx.x;
+  unsigned char* base = out + (size_t)kb * 2 * kF16BTile;
+  for (int ch = threadIdx.x; ch < kE2BN * 8; ch += blockDim.x) {
+    const int r = ch >> 3, c = ch & 7;
+    const int gk = kb * kF16BK + c * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = 0.f, v1 = 0.f;  // rows / columns beyond (N, K) are zero padding
+      if (r < N && gk + 2 * e < K) v0 = W[(size_t)r * K + gk + 2 * e] * scale;
+      if (r < N && gk + 2 * e + 1 < K) v1 = W[(size_t)r * K + gk + 2 * e + 1] * scale;
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+      hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + kF16BTile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Same structure as structure_embedding_tc256_kernel<1> (16 producer / read-out warps + the MMA warp, four products in
+// the order a_0, a_1, a_2, d ping-ponging between two 256-column TMEM slots, running max in registers), with fp16
+// operand tiles: 4 k-blocks of 64 per product.
+__global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel(
+    const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
+    const float* __restrict__ div_term, const unsigned char* __restrict__ wd_packed, const unsigned char* __restrict__ wa_packed,
+    float inv_scale_d, float inv_scale_a, const float* __restrict__ bias_d, const float* __restrict__ bias_a,
+    float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kF16Stages * kF16StageBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kF16Stages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kF16Stages);
+  auto slot_free = [&](int s) { return bar_base + 8u * (2 * kF16Stages + 1 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kF16Stages + 3);
+  __shared__ float s_div[kEmbC / 2];
+  __shared__ float2 s_tab[128];  // (sin, cos)(k pi / 64)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long r0 = (long long)blockIdx.x * kEmbBM;
+  const int n_gemm = 1 + angle_k;  // a_0 .. a_{k-1}, then d
+  const int n_iter = n_gemm * kF16KB;
+
+  if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
+  if (tid >= 128 && tid < 256) {
+    double sd, cd;
+    sincospi((double)(tid - 128) / 64.0, &sd, &cd);
+    s_tab[tid - 128] = make_float2((float)sd, (float)cd);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kF16Stages; ++s) { mbar_init(full_bar(s), kEmbProducers / 32); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    mbar_init(slot_free(0), kEmbProducers / 32);
+    mbar_init(slot_free(1), kEmbProducers / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr int kMmaWarp = kEmbProducers / 32;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < kMmaWarp) {
+    const int row = tid >> 2, h8 = tid & 3;
+    const long long r = r0 + row;
+    const bool valid = r < rows;
+    float xg[4] = {0.f, 0.f, 0.f, 0.f};  // indices in GEMM order: a_0 .. a_{k-1}, d
+    if (valid) {
+      const float dv = d_idx[r];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xg[k] = k < angle_k ? a_idx[r * angle_k + k] : (k == angle_k ? dv : 0.f);
+      if (angle_k == 3) xg[3] = dv;
+    }
+    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter / 64-column group read by this warp
+    const uint32_t my_tmem = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+    float mx[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) mx[j] = -INFINITY;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kF16Stages;
+      const int g = it / kF16KB, kb = it % kF16KB;
+      if (it >= kF16Stages) mbar_wait(empty_bar(s), ((it / kF16Stages) - 1) & 1);
+      if (kb == 2 && g >= 1) {
+        // the commit just waited for (iteration it - 2 = k-block 0 of this product) was issued after every MMA of
+        // product g-1: fold that accumulator into the running max and return the TMEM slot
+        tc_fence_after();
+        const uint32_t src = my_tmem + (uint32_t)(((g - 1) & 1) * kE2BN);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t t[16];
+          tmem_ld16_nowait(src + c16 * 16, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx[c16 * 16 + j] = fmaxf(mx[c16 * 16 + j], __uint_as_float(t[j]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(slot_free((g - 1) & 1));
+      }
+      unsigned char* st = smem + s * kF16StageBytes;
+      if (tid == 0) {
+        const unsigned char* wsrc = (g == angle_k ? wd_packed : wa_packed) + (size_t)kb * 2 * kF16BTile;
+        mbar_expect_tx(full_bar(s), 2 * kF16BTile);
+        const uint32_t b_hi = smem_u32(st + 2 * kF16ATile);
+#pragma unroll
+        for (int part = 0; part < 4; ++part)  // [hi 32 KB][lo 32 KB], source and destination both contiguous
+          bulk_copy_g2s(b_hi + part * (kF16BTile / 2), wsrc + (size_t)part * (kF16BTile / 2), kF16BTile / 2, full_bar(s));
+      }
+      const float x = g == 0 ? xg[0] : (g == 1 ? xg[1] : (g == 2 ? xg[2] : xg[3]));
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c = h8 * 2 + jj;           // 16-byte chunk of the 128-byte row: K elements 8c .. 8c+7 of the k-block
+        const int i0 = kb * 32 + c * 4;      // = four (sin, cos) pairs of frequencies i0 .. i0+3
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float sv, cv;
+          sincos_tab(__fmul_rn(x, s_div[i0 + e]), s_tab, &sv, &cv);   // rows beyond `rows` carry x = 0 and are never stored
+          const __half2 h = __floats2half2_rn(sv, cv);               // one cvt.rn.f16x2.f32: sin in the low half
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(sv - hf.x, cv - hf.y);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(st + kF16ATile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+    }
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t dsrc = my_tmem + (uint32_t)((angle_k & 1) * kE2BN);
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+#pragma unroll
+    for (int c32 = 0; c32 < 2; ++c32) {
+      uint32_t t[32];
+      tmem_ld32(dsrc + c32 * 32, t);
+      const int nbase = cq * 64 + c32 * 32;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = (__uint_as_float(t[j]) * inv_scale_d + bias_d[nbase + j]) + (mx[c32 * 32 + j] * inv_scale_a + bias_a[nbase + j]);
+        o.y = (__uint_as_float(t[j + 1]) * inv_scale_d + bias_d[nbase + j + 1]) + (mx[c32 * 32 + j + 1] * inv_scale_a + bias_a[nbase + j + 1]);
+        o.z = (__uint_as_float(t[j + 2]) * inv_scale_d + bias_d[nbase + j + 2]) + (mx[c32 * 32 + j + 2] * inv_scale_a + bias_a[nbase + j + 2]);
+        o.w = (__uint_as_float(t[j + 3]) * inv_scale_d + bias_d[nbase + j + 3]) + (mx[c32 * 32 + j + 3] * inv_scale_a + bias_a[nbase + j + 3]);
+        *reinterpret_cast<float4*>(stage + lane * 36 + j) = o;
+      }
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+      for (int r4 = 0; r4 < 32; r4 += 4) {
+        const int rw = r4 + rsub;
+        const long long rr = r0 + q * 32 + rw;
+        if (rr < rows)
+          *reinterpret_cast<float4*>(out + rr * kEmbC + nbase + c4) = *reinterpret_cast<const float4*>(stage + rw * 36 + c4);
+      }
+    }
+    tc_fence_before();
+  } else {
+    if (lane == 0) {
+      // kind::f16: c_format F32 (1 << 4), a/b_format F16 (0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kE2BN >> 3) << 17) | ((uint32_t)(kEmbBM >> 4) << 24);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kF16Stages;
+        const int g = it / kF16KB, kb = it % kF16KB;
+        if (kb == 0 && g >= 2) {  // the slot still holds GEMM g-2 until the producers have read it out
+          mbar_wait(slot_free(g & 1), ((g >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(full_bar(s), (it / kF16Stages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kF16StageBytes);
+        const uint32_t a_lo = a_hi + kF16ATile, b_hi = a_hi + 2 * kF16ATile, b_lo = b_hi + kF16BTile;
+        const uint32_t acc = tmem_acc + (uint32_t)((g & 1) * kE2BN);
+#pragma unroll
+        for (int k16 = 0; k16 < kF16BK / 16; ++k16) {
+          const uint32_t ko = k16 * 32;  // 16 fp16 = 32 bytes along the swizzled row
+          umma_f16(acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, (kb | k16) != 0 ? 1u : 0u);
+          umma_f16(acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1u);
+          umma_f16(acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(512));
+  }
+}
+
 }  // namespace tc
 }  // namespace gr
 
@@ -579,5 +831,33 @@ extern "C" int gr_structure_embedding_fused(const float* d_idx, const float* a_i
   else
     GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_tc_kernel<false>, dim3(grid), dim3(tc::kEmbThreads), (size_t)(tc::kEmbSmem), static_cast<cudaStream_t>(stream), d_idx, a_idx, rows, angle_k, div_term, wd_packed, wa_packed, bias_d, bias_a, out));
   GR_CHECK_LAUNCH("structure_embedding_tc_kernel");
+  return GR_OK;
+}
+
+/* fp16-split form of the packed (256,256) projection weight: 4 k-blocks x [hi 32 KB][lo 32 KB] = 256 KB.  `scale` must be
+ * a power of two chosen so that scale * max|W| stays far below 65504 (the caller passes 1 / scale to the fused kernel). */
+extern "C" int gr_pack_weight_f16x2(const float* W, int N, int K, float scale, void* out, void* stream) {
+  if (N <= 0 || N > tc::kE2BN || K <= 0 || K > tc::kEmbC || !W || !out || !(scale > 0.f)) return GR_ERR_BAD_ARG;
+  GR_CHECK_CUDA(launch_pdl(tc::pack_weight_f16x2_kernel, dim3(tc::kF16KB), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), W, N, K, scale,
+                           reinterpret_cast<unsigned char*>(out)));
+  GR_CHECK_LAUNCH("pack_weight_f16x2_kernel");
+  return GR_OK;
+}
+
+/* T1 fused with fp16-split operands (same result contract as gr_structure_embedding_fused; weights from
+ * gr_pack_weight_f16x2 with scales 1 / inv_scale_d, 1 / inv_scale_a). */
+extern "C" int gr_structure_embedding_fused_f16(const float* d_idx, const float* a_idx, int64_t rows, int angle_k,
+                                                const float* div_term, int hidden_dim, const void* wd_packed, const void* wa_packed,
+                                                float inv_scale_d, float inv_scale_a, const float* bias_d, const float* bias_a,
+                                                float* out, void* stream) {
+  if (rows < 0 || angle_k < 1 || angle_k > 3 || hidden_dim != tc::kEmbC) return GR_ERR_BAD_ARG;
+  if (rows == 0) return GR_OK;
+  if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_f16_kernel), tc::kF16Smem));
+  const unsigned tiles = (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM);
+  GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_f16_kernel, dim3(tiles), dim3(tc::kEmbThreads), (size_t)(tc::kF16Smem), static_cast<cudaStream_t>(stream),
+                           d_idx, a_idx, (long long)rows, angle_k, div_term, reinterpret_cast<const unsigned char*>(wd_packed),
+                           reinterpret_cast<const unsigned char*>(wa_packed), inv_scale_d, inv_scale_a, bias_d, bias_a, out));
+  GR_CHECK_LAUNCH("structure_embedding_f16_kernel");
   return GR_OK;
 }

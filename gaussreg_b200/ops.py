@@ -4,6 +4,9 @@ PyTorch is used for device memory and the current stream only; every function be
 library's own sm_100a kernels and raises RuntimeError if the call fails.  Mirrors
 geotransformer/modules/ops/*.py where the reference has an equivalent.
 """
+import math
+import os
+
 import torch
 
 from . import _lib
@@ -179,7 +182,7 @@ def invalidate_weight_caches(module):
     for m in module.modules():
         m.__dict__.pop("_gr_native", None)
     for p in list(module.parameters()) + list(module.buffers()):
-        for attr in ("_gr_packed", "_gr_kmajor", "_gr_qkv", "_gr_t"):
+        for attr in ("_gr_packed", "_gr_packed16", "_gr_kmajor", "_gr_qkv", "_gr_t"):
             if hasattr(p, attr):
                 try:
                     delattr(p, attr)
@@ -440,12 +443,46 @@ def packed_weight_tf32x3(weight):
     return cached[1]
 
 
+def packed_weight_f16x2(weight):
+    """(256,256) projection weight -> fp16 hi/lo tiles for the fp16-split structure-embedding kernel, pre-scaled by a
+    power of two so that the largest |w| lands in [4, 8) (lo parts stay fp16 normals; fp16 tops out at 65504).
+    Returns (buffer, 1/scale); cached on the parameter."""
+    cached = getattr(weight, "_gr_packed16", None)
+    if cached is None or cached[0] != weight._version or cached[1].device != weight.device:
+        N, K = weight.shape
+        wmax = float(weight.detach().abs().max())
+        exp = 0 if not (wmax > 0.0 and math.isfinite(wmax)) else max(-14, min(14, math.floor(math.log2(8.0 / wmax))))
+        scale = 2.0 ** exp
+        out = torch.empty((4 * 2 * 256 * 64 * 2,), dtype=torch.uint8, device=weight.device)
+        st = _lib.lib().gr_pack_weight_f16x2(weight.detach().contiguous().data_ptr(), N, K, scale, out.data_ptr(), _stream())
+        _lib.check(st, "pack_weight_f16x2")
+        cached = (weight._version, out, 1.0 / scale)
+        try:
+            weight._gr_packed16 = cached
+        except AttributeError:
+            pass
+    return cached[1], cached[2]
+
+
+def _t1_f16():
+    v = os.environ.get("GAUSSREG_T1_F16")
+    return True if v is None else v not in ("0", "")
+
+
 def structure_embedding_fused(d_idx, a_idx, div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b):
     """geotransformer.py:57-72 in one tensor-core kernel: (N,N), (N,N,k) indices -> (N,N,C)."""
     N = d_idx.shape[0]
     k = a_idx.shape[-1]
     C = proj_d_w.shape[0]
     out = torch.empty((N, N, C), dtype=_F32, device=d_idx.device)
+    if _t1_f16() and C == 256 and proj_d_w.shape[1] == 256:
+        wd, isd = packed_weight_f16x2(proj_d_w)
+        wa, isa = packed_weight_f16x2(proj_a_w)
+        st = _lib.lib().gr_structure_embedding_fused_f16(d_idx.data_ptr(), a_idx.data_ptr(), N * N, k, div_term.data_ptr(), C,
+                                                         wd.data_ptr(), wa.data_ptr(), isd, isa, proj_d_b.data_ptr(),
+                                                         proj_a_b.data_ptr(), out.data_ptr(), _stream())
+        _lib.check(st, "structure_embedding_fused_f16")
+        return out
     st = _lib.lib().gr_structure_embedding_fused(d_idx.data_ptr(), a_idx.data_ptr(), N * N, k, div_term.data_ptr(), C,
                                                  packed_weight_tf32x3(proj_d_w).data_ptr(), packed_weight_tf32x3(proj_a_w).data_ptr(),
                                                  proj_d_b.data_ptr(), proj_a_b.data_ptr(), out.data_ptr(), _stream())

@@ -255,6 +255,17 @@ int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t
                                  int hidden_dim, const float* wd_packed, const float* wa_packed, const float* bias_d,
                                  const float* bias_a, float* out, void* stream);
 
+/* T1 with fp16-split operands: TF32 and fp16 carry the same 11 significant bits, so the two-part split is as accurate,
+ * and kind::f16 issues at twice the kind::tf32 rate.  Valid here because the generated operand is sin / cos in [-1, 1]
+ * and the static weights are pre-scaled by a power of two (divided out in the epilogue).
+ * gr_pack_weight_f16x2: W (N <= 256, K <= 256) fp32 -> 256 KB of fp16 hi/lo tiles; gr_structure_embedding_fused_f16:
+ * same contract as gr_structure_embedding_fused, inv_scale_* = 1 / the packing scales.
+ * Replaces geotransformer/modules/geotransformer/geotransformer.py:57-72. */
+int gr_pack_weight_f16x2(const float* W, int N, int K, float scale, void* out, void* stream);
+int gr_structure_embedding_fused_f16(const float* d_idx, const float* a_idx, int64_t rows, int angle_k, const float* div_term,
+                                     int hidden_dim, const void* wd_packed, const void* wa_packed, float inv_scale_d,
+                                     float inv_scale_a, const float* bias_d, const float* bias_a, float* out, void* stream);
+
 /* T2  RPE attention probabilities with the p-term reassociated (rpe_transformer.py:50-66), row softmax
  * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */
 int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,
