@@ -26,7 +26,8 @@ class LayerWeights(ctypes.Structure):
 class UnaryWeights(ctypes.Structure):
     """gr_unary_weights (include/gaussreg_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("weight", "weight_packed", "bias", "gn_weight", "gn_bias")] + \
-               [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "leaky_relu")]
+               [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "leaky_relu", "split_k")] + \
+               [(n, ctypes.c_void_p) for n in ("weight_packed_lo", "weight_packed_hi")]
 
 
 class KPConvWeights(ctypes.Structure):

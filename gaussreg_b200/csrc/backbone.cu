@@ -227,15 +227,40 @@ static int fpn(const gr_fpn_weights& W, const gr_pyramid& P, const float* feats,
   for (const Dec& d : decs) {
     const int f = d.fine, M = P.n_points[f], Nc = P.n_points[f + 1];
     const size_t mk = ar.mark();
-    float* cat = ar.take<float>((size_t)M * (coarse_ch + stage_ch[f]));
-    if (!ar.dry) {
-      if (!ar.ok()) return GR_ERR_WORKSPACE;
-      if (d.w->in_channels != coarse_ch + stage_ch[f]) return GR_ERR_BAD_ARG;
-      GR_TRY(gr_upsample_concat(coarse, Nc, coarse_ch, P.upsampling[f], P.upsampling_ld[f], stage_out[f], stage_ch[f], M, cat, st));
-    }
+    if (!ar.dry && d.w->in_channels != coarse_ch + stage_ch[f]) return GR_ERR_BAD_ARG;
+    const bool split = d.w->split_k == coarse_ch && d.w->weight_packed_lo && d.w->weight_packed_hi;
     float* y = d.out;
-    if (!y) y = ar.take<float>((size_t)M * d.w->out_channels);  // cannot persist past release: only used when dry / unwanted
-    GR_TRY(unary(*d.w, cat, M, G, eps, nullptr, 0, y, ar, st));
+    if (split) {
+      // cat[up(coarse), skip] W^T = up(coarse W_lo^T) + skip W_hi^T: the coarse half of the product runs on the Nc
+      // coarse rows, its result is gathered to the fine rows straight into the output buffer and rides in the second
+      // product's epilogue as the residual (in place), together with the bias and the GroupNorm statistics.
+      const int out = d.w->out_channels, in = d.w->in_channels, C2 = stage_ch[f];
+      float* yc = ar.take<float>((size_t)Nc * out);
+      float* tmp = ar.take<float>((size_t)M * out);
+      GnStatsOut gn{ar.take<double2>(gn_blocks_capacity(M) * G), gn_blocks_capacity(M), G, 0};
+      if (!y) y = ar.take<float>((size_t)M * out);
+      int rc = GR_OK;
+      if (!ar.dry) {
+        if (!ar.ok()) return GR_ERR_WORKSPACE;
+        float* dst = d.w->gn_weight ? tmp : y;
+        GR_TRY(gemm_ex(coarse, coarse_ch, d.w->weight, in, 1, yc, out, Nc, out, coarse_ch, 1.f, nullptr, nullptr, nullptr, 0, 0, st,
+                       d.w->weight_packed_lo, nullptr));
+        GR_TRY(gr_upsample_concat(yc, Nc, out, P.upsampling[f], P.upsampling_ld[f], nullptr, 0, M, dst, st));
+        rc = gemm_ex(stage_out[f], C2, d.w->weight + coarse_ch, in, 1, dst, out, M, out, C2, 1.f, d.w->bias, nullptr, dst, out, 0, st,
+                     d.w->weight_packed_hi, d.w->gn_weight ? &gn : nullptr);
+      }
+      if (rc == GR_OK && d.w->gn_weight)
+        rc = norm_after_product(tmp, M, out, G, eps, gn, d.w->gn_weight, d.w->gn_bias, nullptr, d.w->leaky_relu ? 2 : 0, y, ar, st);
+      GR_TRY(rc);
+    } else {
+      float* cat = ar.take<float>((size_t)M * (coarse_ch + stage_ch[f]));
+      if (!ar.dry) {
+        if (!ar.ok()) return GR_ERR_WORKSPACE;
+        GR_TRY(gr_upsample_concat(coarse, Nc, coarse_ch, P.upsampling[f], P.upsampling_ld[f], stage_out[f], stage_ch[f], M, cat, st));
+      }
+      if (!y) y = ar.take<float>((size_t)M * d.w->out_channels);  // cannot persist past release: only used when dry / unwanted
+      GR_TRY(unary(*d.w, cat, M, G, eps, nullptr, 0, y, ar, st));
+    }
     if (d.out) ar.release(mk);
     coarse = y;
     coarse_ch = d.w->out_channels;

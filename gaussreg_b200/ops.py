@@ -127,10 +127,17 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_
 # ------------------------------------------------------------------------------------------------
 # native KPConv blocks / FPN: parameter structs for the C ABI (include/gaussreg_b200.h, csrc/backbone.cu)
 # ------------------------------------------------------------------------------------------------
-def _fill_unary(dst, mlp, norm, leaky, keep):
-    """gr_unary_weights from an nn.Linear (+ optional GroupNorm wrapper)."""
+def _fill_unary(dst, mlp, norm, leaky, keep, split_k=0):
+    """gr_unary_weights from an nn.Linear (+ optional GroupNorm wrapper).  split_k > 0 (decoder blocks): also pack the
+    two column slices of the weight, see gr_unary_weights.split_k."""
     w = mlp.weight
     dst.weight = w.data_ptr()
+    dst.split_k, dst.weight_packed_lo, dst.weight_packed_hi = 0, None, None
+    if 0 < split_k < w.shape[1] and split_k % 32 == 0 and (w.shape[1] - split_k) % 32 == 0 and os.environ.get("GAUSSREG_DECODER_SPLIT", "1") != "0":
+        lo, hi = w.detach()[:, :split_k].contiguous(), w.detach()[:, split_k:].contiguous()
+        plo, phi = packed_weight_tf32x3(lo), packed_weight_tf32x3(hi)
+        keep.extend([lo, hi, plo, phi])
+        dst.split_k, dst.weight_packed_lo, dst.weight_packed_hi = split_k, plo.data_ptr(), phi.data_ptr()
     if w.is_contiguous() and w.shape[1] % 4 == 0:
         pk = packed_weight_tf32x3(w)
         keep.append(pk)
@@ -278,9 +285,12 @@ def kpconv_fpn(backbone, feats, data_dict):
             else:                     # ConvBlock
                 b.kind, b.strided = 0, 0
                 b.gn_conv_weight, b.gn_conv_bias = m.norm.norm.weight.data_ptr(), m.norm.norm.bias.data_ptr()
-        _fill_unary(W.decoder4, backbone.decoder4.mlp, backbone.decoder4.norm, True, keep)
-        _fill_unary(W.decoder3, backbone.decoder3.mlp, backbone.decoder3.norm, True, keep)
-        _fill_unary(W.decoder2, backbone.decoder2.mlp, None, False, keep)
+        # decoder inputs are cat[upsampled coarser output, skip]: the coarse part has the previous decoder's (or the last
+        # encoder's) width
+        c5 = backbone.encoder5_3.unary2.mlp.weight.shape[0] if hasattr(backbone.encoder5_3, "unary2") else 0
+        _fill_unary(W.decoder4, backbone.decoder4.mlp, backbone.decoder4.norm, True, keep, split_k=c5)
+        _fill_unary(W.decoder3, backbone.decoder3.mlp, backbone.decoder3.norm, True, keep, split_k=backbone.decoder4.mlp.weight.shape[0])
+        _fill_unary(W.decoder2, backbone.decoder2.mlp, None, False, keep, split_k=backbone.decoder3.mlp.weight.shape[0])
         W.group_norm, W.eps = int(groups), float(eps)
         return W
 

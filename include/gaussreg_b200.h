@@ -155,6 +155,13 @@ typedef struct {
   const float* gn_bias;
   int in_channels, out_channels; /* in_channels == 0: the block is nn.Identity */
   int leaky_relu;             /* LeakyReLU(0.1) after the norm (UnaryBlock has_relu) */
+  /* Decoder blocks only (their input is cat[nearest_upsample(coarse), skip], backbone.py:195-208): with split_k = C_coarse
+   * and the packed images of weight[:, :split_k] / weight[:, split_k:], the product is evaluated as
+   * upsample(coarse W_lo^T) + skip W_hi^T -- a row gather commutes with the right-multiplication, so the coarse half
+   * runs on the 4x fewer coarse rows and no (M, C_coarse + C_skip) tensor is written.  split_k = 0: plain product. */
+  int split_k;
+  const float* weight_packed_lo;
+  const float* weight_packed_hi;
 } gr_unary_weights;
 
 typedef struct {

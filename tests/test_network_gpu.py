@@ -361,8 +361,16 @@ def _run_gpu_model(spec):
         h.remove()
     native = model.backbone(data["features"], data)
     torch.cuda.synchronize()
+    # The encoder is the same kernel sequence in both paths: bit-identical.  The decoders differ by ONE reassociation in the
+    # native call (cat[up(c), s] W^T evaluated as up(c W_lo^T) + s W_hi^T, gr_unary_weights.split_k): fp32 rounding only.
+    n_equal = 0
     for a, b in zip(native, by_module):
-        assert torch.equal(a, b)
+        if torch.equal(a, b):
+            n_equal += 1
+        else:
+            rel = float((a - b).norm() / b.norm())
+            assert rel < 3e-6, rel
+    assert n_equal >= 1
     return model, data, out, taps
 
 
