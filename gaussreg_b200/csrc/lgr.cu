@@ -5,6 +5,8 @@
 // The reference does six 3x3 SVDs on the CPU (procrustes.py:59) and one Python-list sync
 // (local_global_registration.py:159); here the weighted Kabsch solve is a one-sided Jacobi SVD in
 // double precision run by one thread, and the whole refinement chain is a single CTA.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace gr {
@@ -115,6 +117,41 @@ __device__ __forceinline__ void block_sum_n(float (&v)[N], float* sh /* kLgrShFl
   for (int k = 0; k < N; ++k) v[k] = sh[32 * N + k];
 }
 
+// Sum over one CTA / over the CTAs of a thread-block cluster (fixed rank order, every thread of every CTA receives the
+// same totals).  The cluster form exchanges the per-CTA totals through distributed shared memory, double-buffered so
+// that one cluster barrier per reduction suffices (a buffer is rewritten two reductions later, and a CTA only gets
+// there through the barrier of the reduction in between, which its peers reach after their reads).
+struct BlockReducer {
+  float* sh;
+  template <int N>
+  __device__ __forceinline__ void sum(float (&v)[N]) { block_sum_n<N>(v, sh); }
+};
+constexpr int kRefineCtas = 8;
+struct ClusterReducer {
+  float* sh;
+  float* xchg;  // [2][16] in every CTA's shared memory
+  int parity;
+  template <int N>
+  __device__ __forceinline__ void sum(float (&v)[N]) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    block_sum_n<N>(v, sh);
+    float* mine = xchg + parity * 16;
+    if (threadIdx.x < N) mine[threadIdx.x] = v[threadIdx.x < N ? threadIdx.x : 0];
+    cluster.sync();
+    if (threadIdx.x < N) {
+      float t = 0.f;
+      for (int r = 0; r < kRefineCtas; ++r) t += cluster.map_shared_rank(mine, r)[threadIdx.x];
+      sh[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = sh[k];
+    __syncthreads();
+    parity ^= 1;
+  }
+};
+
 // A run of correspondences; the pointers may address shared or global memory.
 struct CorrSeg {
   const float* src;
@@ -132,13 +169,14 @@ struct CorrSeg {
 // would instead return a clean near-identity rotation for H ~ 0, and such a hypothesis can collect spuriously many
 // inliers whenever the true motion is small -- a systematic deviation from the reference's hypothesis selection
 // (observed on the textured3k golden).  Only the 3x3 factorisation itself runs in fp64.
-__device__ void block_procrustes(const CorrSeg a, const CorrSeg b, float eps, float* sh, float* T_out /* shared, 12 */) {
+template <typename Reducer>
+__device__ void block_procrustes(const CorrSeg a, const CorrSeg b, float eps, Reducer& red, float* T_out /* shared, 12 */) {
   const CorrSeg segs[2] = {a, b};
   float sw[1] = {0.f};
 #pragma unroll
   for (int g = 0; g < 2; ++g)
     for (int i = threadIdx.x; i < segs[g].n; i += blockDim.x) sw[0] += segs[g].w[i];
-  block_sum_n<1>(sw, sh);
+  red.template sum<1>(sw);
   const float denom = sw[0] + eps;
   float cen[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -152,7 +190,7 @@ __device__ void block_procrustes(const CorrSeg a, const CorrSeg b, float eps, fl
       cen[3] += ref[3 * i] * wi; cen[4] += ref[3 * i + 1] * wi; cen[5] += ref[3 * i + 2] * wi;
     }
   }
-  block_sum_n<6>(cen, sh);
+  red.template sum<6>(cen);
   const float scx = cen[0], scy = cen[1], scz = cen[2];
   const float rcx = cen[3], rcy = cen[4], rcz = cen[5];
   float h[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -170,7 +208,7 @@ __device__ void block_procrustes(const CorrSeg a, const CorrSeg b, float eps, fl
       h[6] += sz * rx; h[7] += sz * ry; h[8] += sz * rz;
     }
   }
-  block_sum_n<9>(h, sh);
+  red.template sum<9>(h);
   if (threadIdx.x == 0) {
     double H[9];
     for (int k = 0; k < 9; ++k) H[k] = (double)h[k];
@@ -313,7 +351,8 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
     if (threadIdx.x == 0) inliers[b] = -1;
     return;
   }
-  block_procrustes(CorrSeg{src_corr + 3ll * off, ref_corr + 3ll * off, corr_scores + off, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, sh, T);
+  BlockReducer red{sh};
+  block_procrustes(CorrSeg{src_corr + 3ll * off, ref_corr + 3ll * off, corr_scores + off, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, red, T);
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   int c = 0;
@@ -333,45 +372,59 @@ __global__ void __launch_bounds__(kLgrThreads) lgr_hypothesis_kernel(const float
   if (threadIdx.x < 12) T_local[b * 12 + threadIdx.x] = T[threadIdx.x];
 }
 
-// single CTA: pick the best hypothesis (first maximum), then `steps` rounds of global refinement.  The first `cap`
-// correspondences (all of them, normally) are staged in shared memory once -- the 4 * steps passes over them then cost
-// shared-memory latency instead of a dependent L2 round trip per pass; whatever exceeds `cap` is read in place.
+// ONE thread-block cluster of kRefineCtas CTAs: pick the best hypothesis (first maximum), then `steps` rounds of global
+// refinement.  CTA r owns the r-th contiguous slice of the correspondences and stages up to `cap` of them in its shared
+// memory once (8 x 6400 covers every case seen; whatever exceeds it is read in place), so the 4 * steps passes cost
+// shared-memory latency; the three sums of each weighted Procrustes are exchanged through distributed shared memory
+// (ClusterReducer), every CTA then solves the same 3x3 problem redundantly and continues with the same transform.
+// (One CTA alone spent 0.21 ms here: its slice of the L2 bandwidth on ~25 k correspondences per pass.)
 constexpr int kRefineThreads = 1024;
 constexpr int kRefineCap = 6400;  // x 32 B = 200 KB of dynamic shared memory
-__global__ void __launch_bounds__(kRefineThreads) lgr_refine_kernel(const float* __restrict__ ref_corr, const float* __restrict__ src_corr,
-                                                                    const float* __restrict__ corr_scores, const int* __restrict__ offsets, int P,
-                                                                    const float* __restrict__ T_local, const int* __restrict__ inliers, float radius,
-                                                                    float eps, int steps, int cap, float* __restrict__ w /* scratch, C */,
-                                                                    float* __restrict__ T_out /* 16 */, int* __restrict__ best_out) {
+__global__ void __cluster_dims__(kRefineCtas, 1, 1) __launch_bounds__(kRefineThreads)
+    lgr_refine_kernel(const float* __restrict__ ref_corr, const float* __restrict__ src_corr, const float* __restrict__ corr_scores,
+                      const int* __restrict__ offsets, int P, const float* __restrict__ T_local, const int* __restrict__ inliers,
+                      float radius, float eps, int steps, int cap, float* __restrict__ w /* scratch, C */,
+                      float* __restrict__ T_out /* 16 */, int* __restrict__ best_out) {
   pdl_wait();
   pdl_trigger();
+  namespace cg = cooperative_groups;
+  const int rank = (int)cg::this_cluster().block_rank();
   extern __shared__ float stage[];  // src (3 cap) | ref (3 cap) | score (cap) | w (cap)
   __shared__ float sh[kLgrShFloats];
+  __shared__ float xchg[2 * 16];
   __shared__ float T[12];
   __shared__ int s_best;
   const int C = offsets[P];
-  const int n0 = C < cap ? C : cap, n1 = C - n0;
+  const int per = (C + kRefineCtas - 1) / kRefineCtas;
+  const int lo = rank * per < C ? rank * per : C;
+  const int n = C - lo < per ? C - lo : per;
+  const int n0 = n < cap ? n : cap, n1 = n - n0;
+  const float* g_src = src_corr + 3ll * lo;
+  const float* g_ref = ref_corr + 3ll * lo;
+  const float* g_score = corr_scores + lo;
+  float* g_w = w + lo;
   float* s_src = stage;
   float* s_ref = s_src + 3 * (size_t)cap;
   float* s_score = s_ref + 3 * (size_t)cap;
   float* s_w = s_score + cap;
-  for (int i = threadIdx.x; i < 3 * n0; i += blockDim.x) { s_src[i] = src_corr[i]; s_ref[i] = ref_corr[i]; }
-  for (int i = threadIdx.x; i < n0; i += blockDim.x) s_score[i] = corr_scores[i];
+  for (int i = threadIdx.x; i < 3 * n0; i += blockDim.x) { s_src[i] = g_src[i]; s_ref[i] = g_ref[i]; }
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) s_score[i] = g_score[i];
   if (threadIdx.x == 0) {
     int best = -1, bc = -1;
     for (int b = 0; b < P; ++b)
       if (inliers[b] > bc) { bc = inliers[b]; best = b; }
     s_best = best;
-    *best_out = best;
+    if (rank == 0) *best_out = best;
   }
   __syncthreads();
-  const CorrSeg near_scores{s_src, s_ref, s_score, n0}, far_scores{src_corr + 3ll * n0, ref_corr + 3ll * n0, corr_scores + n0, n1};
-  const CorrSeg near_w{s_src, s_ref, s_w, n0}, far_w{src_corr + 3ll * n0, ref_corr + 3ll * n0, w + n0, n1};
+  ClusterReducer red{sh, xchg, 0};
+  const CorrSeg near_scores{s_src, s_ref, s_score, n0}, far_scores{g_src + 3ll * n0, g_ref + 3ll * n0, g_score + n0, n1};
+  const CorrSeg near_w{s_src, s_ref, s_w, n0}, far_w{g_src + 3ll * n0, g_ref + 3ll * n0, g_w + n0, n1};
   auto rescore = [&]() {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const CorrSeg& sg = g == 0 ? near_scores : far_scores;
-      float* wout = g == 0 ? s_w : w + n0;
+      float* wout = g == 0 ? s_w : g_w + n0;
       for (int i = threadIdx.x; i < sg.n; i += blockDim.x) {
         const float sx = sg.src[3 * i], sy = sg.src[3 * i + 1], sz = sg.src[3 * i + 2];
         const float ax = (sx * T[0] + sy * T[1] + sz * T[2]) + T[3];
@@ -389,16 +442,19 @@ __global__ void __launch_bounds__(kRefineThreads) lgr_refine_kernel(const float*
     rescore();
   } else {
     // degenerate: initialise with all correspondences (local_global_registration.py:180-185)
-    block_procrustes(near_scores, far_scores, eps, sh, T);
+    block_procrustes(near_scores, far_scores, eps, red, T);
     rescore();
   }
-  block_procrustes(near_w, far_w, eps, sh, T);
+  block_procrustes(near_w, far_w, eps, red, T);
   for (int s = 0; s < steps - 1; ++s) {
     rescore();
-    block_procrustes(near_w, far_w, eps, sh, T);
+    block_procrustes(near_w, far_w, eps, red, T);
   }
-  if (threadIdx.x < 12) T_out[threadIdx.x] = T[threadIdx.x];
-  if (threadIdx.x >= 12 && threadIdx.x < 16) T_out[threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
+  if (rank == 0) {
+    if (threadIdx.x < 12) T_out[threadIdx.x] = T[threadIdx.x];
+    if (threadIdx.x >= 12 && threadIdx.x < 16) T_out[threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
+  }
+  cg::this_cluster().sync();  // no CTA may exit while a peer can still read its exchange buffer
 }
 
 // batched weighted Procrustes: one CTA per problem (drop-in for WeightedProcrustes.forward)
@@ -410,7 +466,8 @@ __global__ void __launch_bounds__(kLgrThreads) procrustes_batched_kernel(const f
   __shared__ float sh[kLgrShFloats];
   __shared__ float T[12];
   const long long b = blockIdx.x;
-  block_procrustes(CorrSeg{src + b * n * 3, ref + b * n * 3, w + b * n, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, sh, T);
+  BlockReducer red{sh};
+  block_procrustes(CorrSeg{src + b * n * 3, ref + b * n * 3, w + b * n, n}, CorrSeg{nullptr, nullptr, nullptr, 0}, eps, red, T);
   if (threadIdx.x < 12) T_out[b * 16 + threadIdx.x] = T[threadIdx.x];
   if (threadIdx.x >= 12 && threadIdx.x < 16) T_out[b * 16 + threadIdx.x] = threadIdx.x == 15 ? 1.f : 0.f;
 }
@@ -472,7 +529,7 @@ extern "C" int gr_local_global_registration(const float* matching_scores, int P,
   GR_CHECK_LAUNCH("lgr_hypothesis_kernel");
   const size_t refine_smem = (size_t)kRefineCap * 8 * sizeof(float);
   GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(lgr_refine_kernel), (int)refine_smem));
-  GR_CHECK_CUDA(launch_pdl(lgr_refine_kernel, dim3(1), dim3(kRefineThreads), refine_smem, st, ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers,
+  GR_CHECK_CUDA(launch_pdl(lgr_refine_kernel, dim3(kRefineCtas), dim3(kRefineThreads), refine_smem, st, ref_corr_points, src_corr_points, corr_scores, offsets, P, T_local, inliers,
                            acceptance_radius, 1e-5f, num_refinement_steps, kRefineCap, w, transform, counts + P));
   GR_CHECK_LAUNCH("lgr_refine_kernel");
   return GR_OK;
