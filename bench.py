@@ -536,12 +536,19 @@ def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microben
     n_t1 = max(1, sum(1 for r in lib.records if r[0] == "gr_structure_embedding_fused"))
     achieved = t1_flop / (t1_ms * 1e-3) / 1e12 if t1_ms > 0 else 0.0
     t1_rows = t1_flop / n_t1 / (2.0 * 4 * 256 * 256)  # (n, m) pairs per launch = N^2
+    f16 = getattr(lib, "t1_kind", "tf32") == "f16"
+    mma_peak = peaks["tf_sustained"] if f16 else peaks["tf_sustained"] / 2.0  # kind::f16 issues at the bf16 rate, kind::tf32 at half
     roofline = {
-        "kernel": "tc::structure_embedding_tc256_kernel (T1: in-kernel sinusoid -> tcgen05.mma kind::tf32 3xTF32 -> max_k -> sum; "
-                  "TMEM ping-pong accumulators)",
+        "kernel": ("tc::structure_embedding_f16_kernel (T1: in-kernel table sincos -> fp16 hi/lo split -> tcgen05.mma kind::f16, three "
+                   "MMAs per product -> max_k -> sum; TMEM ping-pong accumulators)") if f16 else
+                  ("tc::structure_embedding_tc256_kernel (T1: in-kernel sinusoid -> tcgen05.mma kind::tf32 3xTF32 -> max_k -> sum; "
+                   "TMEM ping-pong accumulators)"),
         "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-        "peak_source": peaks["source"] + " bf16 sustained (cuBLAS, MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate and "
-                       "every fp32-accurate product costs 3 MMAs, so the tensor-pipe occupancy is ~6 x frac",
+        "peak_source": peaks["source"] + " bf16 sustained (cuBLAS, MEASURED_PEAKS.json); achieved counts fp32-equivalent FLOPs "
+                       "(2 N^2 (1+k) 256^2): every fp32-accurate product costs 3 MMAs (hi.hi + hi.lo + lo.hi)" +
+                       (", issued as kind::f16 at the bf16 rate: tensor-pipe occupancy ~ 3 x frac" if f16 else
+                        ", and kind::tf32 issues at half the bf16 rate: tensor-pipe occupancy ~ 6 x frac"),
+        "mma_kind": "f16" if f16 else "tf32", "mma_tflops": 3.0 * achieved, "frac_of_mma_peak": 3.0 * achieved / mma_peak,
         "tf32_mma_tflops": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (peaks["tf_sustained"] / 2.0),
         "launches_per_step": n_t1, "avg_launch_ms": t1_ms / n_t1, "flop_per_launch_fp32_equiv": t1_flop / n_t1,
         "share_of_step": t1_ms / max(sum(per_op.values()), 1e-9),
@@ -550,12 +557,12 @@ def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microben
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        k = tj.get("kernels", {}).get("structure_embedding_tc256_kernel")
+        k = tj.get("kernels", {}).get("structure_embedding_f16_kernel" if f16 else "structure_embedding_tc256_kernel")
         if k:
             roofline["traffic"] = k["dram_bytes_per_launch"]
             roofline["traffic_source"] = tj.get("source")
         roofline["traffic_other_kernels"] = {n: v["dram_bytes_per_launch"] for n, v in tj.get("kernels", {}).items()
-                                             if n != "structure_embedding_tc256_kernel"}
+                                             if "structure_embedding" not in n and " grid=" not in n and "<" not in n}
     hbm = {}
     n_calls = {}
     for r in lib.records:

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, BN == 64 ? 2 : 1) gemm_tf32x3_kernel
   pdl_trigger();
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);  // full[st], empty[st], accum, tmem slot
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -376,7 +376,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreadsTma, BN == 64 ? 2 : 1) gemm_tf32x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p) {
   using C = CfgTma<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   unsigned char* raw_ring = smem;                                   // [kRaw][16 KB]
   unsigned char* op_ring = smem + C::kRaw * C::kABytes;             // [kOps][a_lo | b_hi | b_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(op_ring + C::kOps * C::kOpBytes);
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kThreadsPersist, 1) gemm_tf32x3_persist_kernel
                                                                                 int tiles_m, int tiles_n, int n_splits) {
   using C = CfgPersist<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   unsigned char* raw_ring = smem;
   unsigned char* op_ring = smem + C::kRaw * C::kABytes;
   unsigned char* epi = op_ring + C::kOps * C::kOpBytes;
