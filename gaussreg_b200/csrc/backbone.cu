@@ -177,6 +177,42 @@ static int block(const gr_block_weights& b, int groups, float eps, const float* 
     }
     sc = pooled;
   }
+  static int dual = -1;
+  if (dual < 0) { const char* e = getenv("GAUSSREG_GN_DUAL"); dual = e ? atoi(e) : 1; }
+  if (dual && b.shortcut.in_channels > 0 && b.shortcut.gn_weight && b.unary2.gn_weight && !b.shortcut.leaky_relu && !b.unary2.leaky_relu &&
+      b.shortcut.out_channels == b.unary2.out_channels && b.unary2.out_channels % 4 == 0) {
+    // both products leave their GroupNorm statistics; ONE apply pass then forms LeakyReLU(GN(unary2) + GN(shortcut))
+    const int out = b.unary2.out_channels;
+    float* ts = ar.take<float>((size_t)M * out);
+    float* tu = ar.take<float>((size_t)M * out);
+    GnStatsOut gs{ar.take<double2>(gn_blocks_capacity(M) * groups), gn_blocks_capacity(M), groups, 0};
+    GnStatsOut gu{ar.take<double2>(gn_blocks_capacity(M) * groups), gn_blocks_capacity(M), groups, 0};
+    float2* st_s = ar.take<float2>((size_t)groups);
+    float2* st_u = ar.take<float2>((size_t)groups);
+    if (!ar.dry) {
+      if (!ar.ok()) return GR_ERR_WORKSPACE;
+      GR_TRY(gemm_ex(sc, b.shortcut.in_channels, b.shortcut.weight, b.shortcut.in_channels, 1, ts, out, M, out, b.shortcut.in_channels, 1.f,
+                     b.shortcut.bias, nullptr, nullptr, 0, 0, st, b.shortcut.weight_packed, &gs));
+      GR_TRY(gemm_ex(c, b.unary2.in_channels, b.unary2.weight, b.unary2.in_channels, 1, tu, out, M, out, b.unary2.in_channels, 1.f,
+                     b.unary2.bias, nullptr, nullptr, 0, 0, st, b.unary2.weight_packed, &gu));
+      if (gs.nblk > 0 && gu.nblk > 0) {
+        GR_TRY(group_norm_finalize(gs.partial, gs.nblk, M, out, groups, eps, st_s, st));
+        GR_TRY(group_norm_finalize(gu.partial, gu.nblk, M, out, groups, eps, st_u, st));
+        GR_TRY(group_norm_apply2(tu, ts, M, out, groups, st_u, st_s, b.unary2.gn_weight, b.unary2.gn_bias, b.shortcut.gn_weight,
+                                 b.shortcut.gn_bias, 2, y, st));
+        ar.release(mk);
+        return GR_OK;
+      }
+      // a product ran on a path without epilogue statistics: normalise the two results the long way (ts -> ts, then tu + ts)
+      GR_TRY(norm_after_product(ts, M, out, groups, eps, gs, b.shortcut.gn_weight, b.shortcut.gn_bias, nullptr, 0, ts, ar, st));
+      GR_TRY(norm_after_product(tu, M, out, groups, eps, gu, b.unary2.gn_weight, b.unary2.gn_bias, ts, 2, y, ar, st));
+    } else {
+      norm_after_product(ts, M, out, groups, eps, gs, nullptr, nullptr, nullptr, 0, ts, ar, st);  // sizing of the fallback (two norms)
+      norm_after_product(tu, M, out, groups, eps, gu, nullptr, nullptr, nullptr, 0, y, ar, st);
+    }
+    ar.release(mk);
+    return GR_OK;
+  }
   if (b.shortcut.in_channels > 0) {
     float* s2 = ar.take<float>((size_t)M * b.shortcut.out_channels);
     GR_TRY(unary(b.shortcut, sc, M, groups, eps, nullptr, 0, s2, ar, st));

@@ -55,6 +55,10 @@ int gemm_ex(const float* A, long long lda, const float* B, long long ldb, int tr
 int group_norm_from_partial(const float* x, long long n_rows, int C, int groups, const double2* partial, int nblk,
                             const float* gamma, const float* beta, float eps, const float* add, int act, float* y,
                             float2* stats, void* stream);
+// the two halves of group_norm_from_partial, and the two-input apply y = act(GN(x) + GN2(x2))
+int group_norm_finalize(const double2* partial, int nblk, long long n_rows, int C, int groups, float eps, float2* stats, void* stream);
+int group_norm_apply2(const float* x, const float* x2, long long n_rows, int C, int groups, const float2* stats, const float2* stats2,
+                      const float* gamma, const float* beta, const float* gamma2, const float* beta2, int act, float* y, void* stream);
 // rows covered by one partial block of the split-K reduction (gemm_tc.cu)
 constexpr int kGnReduceRows = 32;
 

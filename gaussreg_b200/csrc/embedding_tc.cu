@@ -13,8 +13,6 @@
 
 #include <cuda_fp16.h>
 
-#include <mutex>
-
 #include "tc_common.cuh"
 
 namespace gr {
@@ -126,7 +124,7 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc_kernel(
   pdl_wait();
   pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEmbStages * kEmbStageBytes);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_tc256_kern
   pdl_wait();
   pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kE2Stages * kE2StageBytes);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -584,11 +582,13 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
     const float* __restrict__ d_idx, const float* __restrict__ a_idx, long long rows, int angle_k,
     const float* __restrict__ div_term, const unsigned char* __restrict__ wd_packed, const unsigned char* __restrict__ wa_packed,
     float inv_scale_d, float inv_scale_a, const float* __restrict__ bias_d, const float* __restrict__ bias_a,
-    const float2* __restrict__ sincos_table, float* __restrict__ out) {
+    float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
+  // (the rounded-up pointer is generic, so the tile stores below compile to generic ST.E rather than STS; keeping it in
+  // the shared window -- as gemm_tc.cu does -- measured 3 % SLOWER here: 0.82 vs 0.80 ms per pair)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kF16Stages * kF16StageBytes);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -600,14 +600,16 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
   __shared__ float2 s_tab[128];  // (sin, cos)(k pi / 64)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long r0 = (long long)blockIdx.x * kEmbBM;
   const int n_gemm = 1 + angle_k;  // a_0 .. a_{k-1}, then d
   const int n_iter = n_gemm * kF16KB;
-  const int n_tiles = (int)((rows + kEmbBM - 1) / kEmbBM);
-  // Persistent: the CTA walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; barriers, TMEM and the tables are set
-  // up once, stage / product counters (and with them every mbarrier parity) simply keep running across tiles.
 
   if (tid < kEmbC / 2) s_div[tid] = div_term[tid];
-  if (tid >= 128 && tid < 256) s_tab[tid - 128] = sincos_table[tid - 128];
+  if (tid >= 128 && tid < 256) {
+    double sd, cd;
+    sincospi((double)(tid - 128) / 64.0, &sd, &cd);
+    s_tab[tid - 128] = make_float2((float)sd, (float)cd);
+  }
   if (tid == 0) {
     for (int s = 0; s < kF16Stages; ++s) { mbar_init(full_bar(s), kEmbProducers / 32); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
@@ -627,11 +629,6 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
 
   if (warp < kMmaWarp) {
     const int row = tid >> 2, h8 = tid & 3;
-    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter / 64-column group read by this warp
-    const uint32_t my_tmem = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
-    int gi = 0, gp0 = 0, tile_iter = 0;  // stages / products issued before this tile, tiles done
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, gi += n_iter, gp0 += n_gemm, ++tile_iter) {
-    const long long r0 = (long long)tile * kEmbBM;
     const long long r = r0 + row;
     const bool valid = r < rows;
     float xg[4] = {0.f, 0.f, 0.f, 0.f};  // indices in GEMM order: a_0 .. a_{k-1}, d
@@ -641,20 +638,21 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
       for (int k = 0; k < 3; ++k) xg[k] = k < angle_k ? a_idx[r * angle_k + k] : (k == angle_k ? dv : 0.f);
       if (angle_k == 3) xg[3] = dv;
     }
+    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter / 64-column group read by this warp
+    const uint32_t my_tmem = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
     float mx[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) mx[j] = -INFINITY;
 
     for (int it = 0; it < n_iter; ++it) {
-      const int gs = gi + it;  // running stage counter
-      const int s = gs % kF16Stages;
+      const int s = it % kF16Stages;
       const int g = it / kF16KB, kb = it % kF16KB;
-      if (gs >= kF16Stages) mbar_wait(empty_bar(s), ((gs / kF16Stages) - 1) & 1);
+      if (it >= kF16Stages) mbar_wait(empty_bar(s), ((it / kF16Stages) - 1) & 1);
       if (kb == 2 && g >= 1) {
         // the commit just waited for (iteration it - 2 = k-block 0 of this product) was issued after every MMA of
         // product g-1: fold that accumulator into the running max and return the TMEM slot
         tc_fence_after();
-        const uint32_t src = my_tmem + (uint32_t)(((gp0 + g - 1) & 1) * kE2BN);
+        const uint32_t src = my_tmem + (uint32_t)(((g - 1) & 1) * kE2BN);
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
           uint32_t t[16];
@@ -665,10 +663,9 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(slot_free((gp0 + g - 1) & 1));
+        if (lane == 0) mbar_arrive(slot_free((g - 1) & 1));
       }
       unsigned char* st = smem + s * kF16StageBytes;
-      const uint32_t st_u32 = smem_u32(st);
       if (tid == 0) {
         const unsigned char* wsrc = (g == angle_k ? wd_packed : wa_packed) + (size_t)kb * 2 * kF16BTile;
         mbar_expect_tx(full_bar(s), 2 * kF16BTile);
@@ -693,32 +690,23 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
           hi[e] = *reinterpret_cast<const uint32_t*>(&h);
           lo[e] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        // explicit st.shared: through the rounded-up generic pointer the compiler emits generic stores (ST.E), which go
-        // down the global path and put every following shared load on the long scoreboard (ncu: top stall)
-        const uint32_t sa = st_u32 + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)kF16ATile), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(st + kF16ATile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(s));
     }
     // ---------------------------------------------------------------- epilogue
-    mbar_wait(accum_bar, tile_iter & 1);
+    mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int dslot = (gp0 + angle_k) & 1;
-    const uint32_t dsrc = my_tmem + (uint32_t)(dslot * kE2BN);
-
+    const uint32_t dsrc = my_tmem + (uint32_t)((angle_k & 1) * kE2BN);
     float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
 #pragma unroll
     for (int c32 = 0; c32 < 2; ++c32) {
       uint32_t t[32];
       tmem_ld32(dsrc + c32 * 32, t);
-      if (c32 == 1) {  // the d accumulator has left TMEM: the slot may take the next tile's product
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(slot_free(dslot));
-      }
       const int nbase = cq * 64 + c32 * 32;
       __syncwarp();
 #pragma unroll
@@ -740,31 +728,23 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
           *reinterpret_cast<float4*>(out + rr * kEmbC + nbase + c4) = *reinterpret_cast<const float4*>(stage + rw * 36 + c4);
       }
     }
-    // the transposition scratch above lives in the operand stages: nobody may start filling them for the next tile before
-    // every warp is done with it (all MMAs of this tile have completed: accum_bar)
-    asm volatile("bar.sync 1, %0;" ::"n"(kEmbProducers) : "memory");
-    }  // tile loop
     tc_fence_before();
   } else {
     if (lane == 0) {
       // kind::f16: c_format F32 (1 << 4), a/b_format F16 (0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(kE2BN >> 3) << 17) | ((uint32_t)(kEmbBM >> 4) << 24);
-      int gi = 0, gp0 = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, gi += n_iter, gp0 += n_gemm) {
       for (int it = 0; it < n_iter; ++it) {
-        const int gs = gi + it;
-        const int s = gs % kF16Stages;
+        const int s = it % kF16Stages;
         const int g = it / kF16KB, kb = it % kF16KB;
-        const int gp = gp0 + g;  // running product counter: slot gp & 1, last used by product gp - 2
-        if (kb == 0 && gp >= 2) {  // the slot still holds product gp-2 until the producers have read it out
-          mbar_wait(slot_free(gp & 1), ((gp >> 1) - 1) & 1);
+        if (kb == 0 && g >= 2) {  // the slot still holds GEMM g-2 until the producers have read it out
+          mbar_wait(slot_free(g & 1), ((g >> 1) - 1) & 1);
           tc_fence_after();
         }
-        mbar_wait(full_bar(s), (gs / kF16Stages) & 1);
+        mbar_wait(full_bar(s), (it / kF16Stages) & 1);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * kF16StageBytes);
         const uint32_t a_lo = a_hi + kF16ATile, b_hi = a_hi + 2 * kF16ATile, b_lo = b_hi + kF16BTile;
-        const uint32_t acc = tmem_acc + (uint32_t)((gp & 1) * kE2BN);
+        const uint32_t acc = tmem_acc + (uint32_t)((g & 1) * kE2BN);
 #pragma unroll
         for (int k16 = 0; k16 < kF16BK / 16; ++k16) {
           const uint32_t ko = k16 * 32;  // 16 fp16 = 32 bytes along the swizzled row
@@ -775,7 +755,6 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
         umma_commit(empty_bar(s));
       }
       umma_commit(accum_bar);
-      }  // tile loop
     }
     __syncwarp();
   }
@@ -786,38 +765,10 @@ __global__ void __launch_bounds__(kEmbThreads, 1) structure_embedding_f16_kernel
   }
 }
 
-// (sin, cos)(k pi / 64), k < 128, correctly rounded from double; one copy per device, filled on first use
-__global__ void sincos_table_kernel(float2* __restrict__ tab) {
-  double sd, cd;
-  sincospi((double)threadIdx.x / 64.0, &sd, &cd);
-  tab[threadIdx.x] = make_float2((float)sd, (float)cd);
-}
-
-static int sincos_table_for_device(cudaStream_t st, const float2** out) {
-  static std::mutex mu;
-  static float2* tabs[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return GR_ERR_CUDA;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!tabs[dev]) {
-    float2* t = nullptr;
-    if (cudaMalloc(&t, 128 * sizeof(float2)) != cudaSuccess) return GR_ERR_CUDA;
-    sincos_table_kernel<<<1, 128, 0, st>>>(t);
-    if (cudaGetLastError() != cudaSuccess) { cudaFree(t); return GR_ERR_CUDA; }
-    // other streams may use the table right away: make it complete before publishing the pointer
-    if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); return GR_ERR_CUDA; }
-    tabs[dev] = t;
-  }
-  *out = tabs[dev];
-  return GR_OK;
-}
-
 }  // namespace tc
 }  // namespace gr
 
 using namespace gr;
-
-#define GR_TRY_TABLE(expr) do { const int rc__ = (expr); if (rc__ != GR_OK) return rc__; } while (0)
 
 /* Packs a (N,K) fp32 weight into the tensor-core operand format, zero-padded to 256 rows x 32 columns:
  * out holds 2 * roundup(N,256) * roundup(K,32) floats. */
@@ -905,20 +856,10 @@ extern "C" int gr_structure_embedding_fused_f16(const float* d_idx, const float*
   if (rows == 0) return GR_OK;
   if (!d_idx || !a_idx || !div_term || !wd_packed || !wa_packed || !bias_d || !bias_a || !out) return GR_ERR_BAD_ARG;
   GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(tc::structure_embedding_f16_kernel), tc::kF16Smem));
-  const float2* table = nullptr;
-  GR_TRY_TABLE(tc::sincos_table_for_device(static_cast<cudaStream_t>(stream), &table));
   const unsigned tiles = (unsigned)((rows + tc::kEmbBM - 1) / tc::kEmbBM);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // The kernel walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ...  One CTA per tile (the hardware scheduler balances
-  // the tail) measured 0.80 ms per pair, one persistent CTA per SM 0.83 ms: the per-CTA set-up is not what costs.
-  static int persist = -1;
-  if (persist < 0) { const char* e = getenv("GAUSSREG_T1_PERSIST"); persist = e ? atoi(e) : 0; }
-  const unsigned grid = (persist && tiles > (unsigned)sms) ? (unsigned)sms : tiles;
-  GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_f16_kernel, dim3(grid), dim3(tc::kEmbThreads), (size_t)(tc::kF16Smem), static_cast<cudaStream_t>(stream),
+  GR_CHECK_CUDA(launch_pdl(tc::structure_embedding_f16_kernel, dim3(tiles), dim3(tc::kEmbThreads), (size_t)(tc::kF16Smem), static_cast<cudaStream_t>(stream),
                            d_idx, a_idx, (long long)rows, angle_k, div_term, reinterpret_cast<const unsigned char*>(wd_packed),
-                           reinterpret_cast<const unsigned char*>(wa_packed), inv_scale_d, inv_scale_a, bias_d, bias_a, table, out));
+                           reinterpret_cast<const unsigned char*>(wa_packed), inv_scale_d, inv_scale_a, bias_d, bias_a, out));
   GR_CHECK_LAUNCH("structure_embedding_f16_kernel");
   return GR_OK;
 }

@@ -345,6 +345,60 @@ extern "C" int gr_group_norm(const float* x, int64_t n_rows, int C, int groups, 
 }
 
 namespace gr {
+// y = act(GN_a(x) + GN_b(x2)): the ResidualBlock tail LeakyReLU(norm(unary2) + norm(shortcut)) in ONE pass over the two raw
+// products (kpconv/modules.py:205-224) -- the shortcut's own apply pass (a write and a re-read of (M, out)) disappears.
+__global__ void __launch_bounds__(256) groupnorm_apply2_kernel(const float* __restrict__ x, const float* __restrict__ x2, int n_rows, int C,
+                                                               int G, const float2* __restrict__ stats, const float2* __restrict__ stats2,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ gamma2, const float* __restrict__ beta2, int act,
+                                                               float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
+  const int c4 = C >> 2, cg = C / G;
+  const long long total4 = (long long)n_rows * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i], zv = reinterpret_cast<const float4*>(x2)[i];
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+    const float4 gm2 = *reinterpret_cast<const float4*>(gamma2 + c), bt2 = *reinterpret_cast<const float4*>(beta2 + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float z[4] = {zv.x, zv.y, zv.z, zv.w};
+    const float g4[4] = {gm.x, gm.y, gm.z, gm.w}, b4[4] = {bt.x, bt.y, bt.z, bt.w};
+    const float h4[4] = {gm2.x, gm2.y, gm2.z, gm2.w}, d4[4] = {bt2.x, bt2.y, bt2.z, bt2.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 st = stats[(c + k) / cg], st2 = stats2[(c + k) / cg];
+      float t = (v[k] - st.x) * st.y * g4[k] + b4[k];          // same expression order as groupnorm_apply_kernel ...
+      const float a = (z[k] - st2.x) * st2.y * h4[k] + d4[k];  // ... for both terms, so the result is bit-identical to
+      t += a;                                                  // apply(shortcut) followed by apply(unary2, add)
+      if (act == 2) t = t > 0.f ? t : 0.1f * t;
+      else if (act == 1) t = fmaxf(t, 0.f);
+      v[k] = t;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+int group_norm_finalize(const double2* partial, int nblk, long long n_rows, int C, int groups, float eps, float2* stats, void* stream) {
+  if (n_rows <= 0) return GR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_finalize_kernel, dim3(groups), dim3(256), 0, st, partial, nblk, groups, n_rows * (long long)(C / groups), eps, stats));
+  GR_CHECK_LAUNCH("groupnorm_finalize_kernel");
+  return GR_OK;
+}
+
+int group_norm_apply2(const float* x, const float* x2, long long n_rows, int C, int groups, const float2* stats, const float2* stats2,
+                      const float* gamma, const float* beta, const float* gamma2, const float* beta2, int act, float* y, void* stream) {
+  if (n_rows <= 0) return GR_OK;
+  if (C % 4 != 0) return GR_ERR_BAD_ARG;
+  const long long total4 = n_rows * (long long)(C / 4);
+  const int blocks = (int)min((long long)148 * 16, (total4 + 255) / 256);
+  GR_CHECK_CUDA(launch_pdl(groupnorm_apply2_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, x2, (int)n_rows, C, groups, stats,
+                           stats2, gamma, beta, gamma2, beta2, act, y));
+  GR_CHECK_LAUNCH("groupnorm_apply2_kernel");
+  return GR_OK;
+}
+
 int group_norm_from_partial(const float* x, long long n_rows, int C, int groups, const double2* partial, int nblk,
                             const float* gamma, const float* beta, float eps, const float* add, int act, float* y,
                             float2* stats, void* stream) {
