@@ -30,6 +30,12 @@ class UnaryWeights(ctypes.Structure):
                [(n, ctypes.c_void_p) for n in ("weight_packed_lo", "weight_packed_hi")]
 
 
+class PyramidSearch(ctypes.Structure):
+    """gr_pyramid_search."""
+    _fields_ = [("query_stage", ctypes.c_int), ("support_stage", ctypes.c_int), ("radius", ctypes.c_float),
+                ("limit", ctypes.c_int64), ("out_idx", ctypes.c_void_p), ("out_max_count", ctypes.c_void_p)]
+
+
 class KPConvWeights(ctypes.Structure):
     """gr_kpconv_weights."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("weights", "weights_kmajor", "weights_kmajor_packed", "bias", "kernel_points")] + \
@@ -96,6 +102,7 @@ _SIGNATURES = {
     "gr_embedding_combine": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gr_pack_weight_tf32x3": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "gr_structure_embedding_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gr_radius_pyramid": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, ctypes.c_size_t, _vp, _vp, _i32, _vp]),
     "gr_pack_weight_f16x2": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "gr_structure_embedding_fused_f16": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -920,3 +920,32 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
   GR_CHECK_LAUNCH("hash_order_replay_kernel");
   return GR_OK;
 }
+
+/* G3: the pyramid's searches in one call (see include/gaussreg_b200.h). */
+extern "C" int gr_radius_pyramid(const float* const* stage_points, const int64_t* const* stage_lengths, int n_stages, int batch,
+                                 int64_t capacity, void* const* stage_grid_ws, size_t grid_ws_bytes, void* const* stage_ready_events,
+                                 const gr_pyramid_search* searches, int n_searches, void* stream) {
+  if (!stage_points || !stage_lengths || !stage_grid_ws || !searches || n_stages <= 0 || n_stages > 16 || n_searches < 0 || batch <= 0 ||
+      capacity < 0)
+    return GR_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool built[16] = {};
+  int waited = 0;
+  for (int j = 0; j < n_searches; ++j) {
+    const gr_pyramid_search& q = searches[j];
+    if (q.query_stage < 0 || q.query_stage >= n_stages || q.support_stage < 0 || q.support_stage >= n_stages) return GR_ERR_BAD_ARG;
+    const int need = q.query_stage > q.support_stage ? q.query_stage : q.support_stage;
+    while (waited < need) {
+      ++waited;
+      if (stage_ready_events && stage_ready_events[waited])
+        GR_CHECK_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(stage_ready_events[waited]), 0));
+    }
+    const int rc = gr_radius_neighbors_cached(stage_points[q.query_stage], stage_points[q.support_stage], stage_lengths[q.query_stage],
+                                              stage_lengths[q.support_stage], batch, capacity, capacity, q.radius, q.out_idx, q.limit,
+                                              q.out_max_count, stage_grid_ws[q.support_stage], grid_ws_bytes,
+                                              built[q.support_stage] ? 1 : 0, stream);
+    if (rc != GR_OK) return rc;
+    built[q.support_stage] = true;
+  }
+  return GR_OK;
+}

@@ -12,6 +12,8 @@ Differences from the reference, by design:
     `torch.manual_seed(s); np.random.seed(s); create_model(cfg)` yields the reference's weights
     (checked against tests/golden/weights_checksum.npz).
 """
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -42,6 +44,7 @@ class GeoTransformer(nn.Module):
             correspondence_threshold=f.correspondence_threshold, correspondence_limit=f.correspondence_limit,
             num_refinement_steps=f.num_refinement_steps)
         self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+        self._count_slots = {}
 
     @torch.no_grad()
     def forward(self, data_dict):
@@ -89,8 +92,37 @@ class GeoTransformer(nn.Module):
         ref_feats_f, src_feats_f = feats_f[:ref_length_f], feats_f[ref_length_f:]
         out["ref_feats_f"], out["src_feats_f"] = ref_feats_f, src_feats_f
 
-        # 6. superpoint correspondences (model.py:156-163)
-        ref_ci, src_ci, node_corr_scores = self.coarse_matching(ref_feats_c_norm, src_feats_c_norm, ref_node_masks, src_node_masks)
+        # 6. superpoint correspondences (model.py:156-163).  The reference returns min(k, #valid pairs) of them -- a
+        # data-dependent length that costs a device->host round trip right where the GPU would run dry (0.2 ms of
+        # bubbles: the host can only queue the patch gathers, Sinkhorn and LGR after it).  Almost always the length is k:
+        # the tail is queued for k pairs at once, the count follows through pinned memory, and only if it turns out
+        # smaller is the tail redone on the shorter arrays.
+        ref_ci, src_ci, node_corr_scores, count = self.coarse_matching(ref_feats_c_norm, src_feats_c_norm, ref_node_masks,
+                                                                       src_node_masks, lazy=True)
+        count_host, count_ready = self._count_slot(feats.device)
+        count_host.copy_(count, non_blocking=True)
+        count_ready.record()
+        self._tail(out, ref_ci, src_ci, node_corr_scores, ref_node_knn_indices, src_node_knn_indices, ref_points_f, src_points_f,
+                   ref_feats_f, src_feats_f, feats_f.shape[1], feats.device)
+        count_ready.synchronize()  # completed long ago: the host has been queueing the tail meanwhile
+        c = int(count_host[0])
+        if c < ref_ci.shape[0]:
+            self._tail(out, ref_ci[:c], src_ci[:c], node_corr_scores[:c], ref_node_knn_indices, src_node_knn_indices, ref_points_f,
+                       src_points_f, ref_feats_f, src_feats_f, feats_f.shape[1], feats.device)
+        return out
+
+    def _count_slot(self, dev):
+        """A pinned int32 + event per (device, stream, thread): the asynchronous read-back of the correspondence count."""
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, threading.get_ident())
+        slot = self._count_slots.get(key)
+        if slot is None:
+            slot = (torch.empty((1,), dtype=torch.int32, pin_memory=True), torch.cuda.Event())
+            self._count_slots[key] = slot
+        return slot
+
+    def _tail(self, out, ref_ci, src_ci, node_corr_scores, ref_node_knn_indices, src_node_knn_indices, ref_points_f, src_points_f,
+              ref_feats_f, src_feats_f, C, dev):
+        K = self.num_points_in_patch
         out["ref_node_corr_indices"], out["src_node_corr_indices"] = ref_ci, src_ci
         out["node_corr_scores"] = node_corr_scores
 
@@ -108,8 +140,7 @@ class GeoTransformer(nn.Module):
         out["ref_node_corr_knn_masks"], out["src_node_corr_knn_masks"] = ref_knn_masks, src_knn_masks
 
         # 8. optimal transport (model.py:189-193)
-        C = feats_f.shape[1]
-        scores = torch.empty((P, K, K), dtype=torch.float32, device=feats.device)
+        scores = torch.empty((P, K, K), dtype=torch.float32, device=dev)
         ops.gemm_batched(ref_knn_feats.data_ptr(), C, K * C, src_knn_feats.data_ptr(), C, K * C, True, scores.data_ptr(), K,
                          K * K, K, K, C, P, alpha=1.0 / C ** 0.5)
         matching_scores = self.optimal_transport(scores, ref_knn_masks, src_knn_masks)
@@ -125,12 +156,11 @@ class GeoTransformer(nn.Module):
             c = int(num.item())  # the reference returns (C,3) tensors: data-dependent shape
             out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_pad[:c], src_pad[:c], sc_pad[:c]
             out["lgr_transform"], out["estimated_transform"], out["ransac_info"] = T, T_sim, info
-            return out
+            return
         ref_corr, src_corr, corr_scores, T = self.fine_matching(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks,
                                                                 matching_scores, node_corr_scores)
         out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_corr, src_corr, corr_scores
         out["estimated_transform"] = out["lgr_transform"] = T
-        return out
 
 
 def ops_gather_index(table, rows):

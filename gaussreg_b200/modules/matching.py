@@ -18,7 +18,9 @@ class SuperPointMatching(nn.Module):
         self.dual_normalization = dual_normalization
 
     @torch.no_grad()
-    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None):
+    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None, lazy=False):
+        """lazy=True (extension): no host sync -- returns the full-length (k) arrays plus the device scalar `count`; the caller
+        must check count == k before trusting entries beyond it (GeoTransformer.forward does, after queueing its tail)."""
         dev = ref_feats.device
         if ref_masks is None:
             ref_masks = torch.ones(ref_feats.shape[0], dtype=torch.bool, device=dev)
@@ -26,6 +28,8 @@ class SuperPointMatching(nn.Module):
             src_masks = torch.ones(src_feats.shape[0], dtype=torch.bool, device=dev)
         ref_idx, src_idx, scores, count = ops.superpoint_matching(
             ref_feats, src_feats, ref_masks, src_masks, self.num_correspondences, self.dual_normalization)
+        if lazy:
+            return ref_idx, src_idx, scores, count
         # the reference returns min(k, #valid pairs) entries (data-dependent length)
         c = int(count.item())
         if c < self.num_correspondences:

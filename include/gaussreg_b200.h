@@ -85,6 +85,25 @@ int gr_radius_neighbors_cached(const float* q_points, const float* s_points, con
                                int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
                                int reuse_grid, void* stream);
 
+/* All radius searches of a neighbour pyramid (utils/data.py:27-67: per stage `neighbors`, `subsampling`, `upsampling`) in
+ * ONE call: the host spends ~50 us here instead of ~0.6 ms on thirteen Python-issued calls, which is what delayed
+ * everything queued behind the pyramid.  Every stage's cloud lives in a capacity-sized buffer (`capacity` rows, true
+ * sizes in the device-side stage_lengths); searches[j] is gr_radius_neighbors_cached(query stage, support stage) into
+ * its own (capacity, limit) table, one cell grid per support stage (stage_grid_ws[s], each grid_ws_bytes >=
+ * gr_radius_neighbors_workspace_size(capacity, capacity, batch)) shared by the searches of that stage in call order.
+ * stage_ready_events[s] (cudaEvent_t, may be NULL) is waited on `stream` before the first search that touches stage s:
+ * the grid-subsampling chain may run on another stream. */
+typedef struct {
+  int query_stage, support_stage;
+  float radius;
+  int64_t limit;
+  int64_t* out_idx;
+  int32_t* out_max_count;
+} gr_pyramid_search;
+int gr_radius_pyramid(const float* const* stage_points, const int64_t* const* stage_lengths, int n_stages, int batch,
+                      int64_t capacity, void* const* stage_grid_ws, size_t grid_ws_bytes, void* const* stage_ready_events,
+                      const gr_pyramid_search* searches, int n_searches, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Dense fp32 product with fused epilogue (used by K1 contraction, K2 Linear, T1-T3 projections,
  * attention products, M1/M2 similarity).  Replaces the ATen/cuBLAS calls behind nn.Linear
