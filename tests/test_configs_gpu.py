@@ -192,3 +192,32 @@ def test_config2_full_size_pair_vs_oracle():
                       "num_corr_oracle": int(want["corr_scores"].shape[0])}) + "\n")
     assert err_tf < 1e-4, (err_tf, err)
     assert err < 1e-4 or int(out["corr_scores"].shape[0]) != int(want["corr_scores"].shape[0]), (err, err_tf)
+
+
+def test_fewer_superpoint_pairs_than_requested_takes_the_slow_path():
+    """GeoTransformer.forward queues its tail for k = 256 superpoint pairs before the true count is known on the host;
+    a pair with fewer valid superpoint pairs than k must come out exactly as if the count had been read first
+    (superpoint_matching.py:37-40 returns min(k, #valid) entries)."""
+    cfg = make_cfg()
+    model = seeded_model(0).cuda()
+    spec = dict(seed=11, n_points=700, room=(0.6, 0.55, 0.5))
+    d = make_pair_inputs(**spec)
+    args = (cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    data = registration_collate_fn_stack_mode([{k: d[k] for k in KEYS}], *args)
+    n_c = [int(x) for x in data["lengths"][-1].tolist()]
+    assert n_c[0] * n_c[1] < cfg.coarse_matching.num_correspondences, n_c  # the case this test is about
+    out = model(data)
+    c = out["ref_node_corr_indices"].shape[0]
+    assert 0 < c <= n_c[0] * n_c[1] and c < cfg.coarse_matching.num_correspondences
+    for key in ("src_node_corr_indices", "node_corr_scores", "matching_scores", "ref_node_corr_knn_points"):
+        assert out[key].shape[0] == c, key
+    T = out["estimated_transform"].cpu()
+    assert torch.isfinite(T).all()
+    with torch.no_grad():
+        want = onet.forward(seeded_model(0).state_dict(), oracle_data(spec))
+    assert want["ref_node_corr_indices"].shape[0] == c
+    assert torch.equal(out["ref_node_corr_indices"].cpu(), want["ref_node_corr_indices"])
+    assert torch.equal(out["src_node_corr_indices"].cpu(), want["src_node_corr_indices"])
+    # (the LGR transform of a 0.6 m toy cloud under random weights is ill-conditioned -- a handful of correspondences --
+    # so the comparison stops at the Sinkhorn output of the c patch pairs)
+    assert rel_l2(out["matching_scores"].cpu(), want["matching_scores"]) < 1e-4
