@@ -633,17 +633,22 @@ def run_ours(args, rank, world, local_rank):
     # (SURVEY.md section 8(e) / BASELINE configs[3]: the path has no per-pair exchange)
     local_T = torch.zeros((max(args.steps, warm_steps(args)), 4, 4), dtype=torch.float32, device=dev)
 
+    # GAUSSREG_EARLY=1: the two stage-0 backbone blocks are queued by the collate function right behind the subsampling
+    # chain (KPConvFPN.forward_early).  Bit-identical, but measured SLOWER (7.56 vs 7.35 ms): the window it was meant to
+    # fill is not idle -- the side stream runs the radius searches there -- so the blocks only contend with them.
+    early = model.backbone.forward_early if os.environ.get("GAUSSREG_EARLY", "0") == "1" else None
+
     def step_resident(i):
         pts, feats, lens = resident[i % pool]
         data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
-                                          cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+                                          cfg.backbone.init_radius, NEIGHBOR_LIMITS, early=early, features=feats)
         data["features"] = feats
         local_T[i] = model(data)["estimated_transform"]
 
     def step_e2e(i):
         h = host[i % pool]
         data = registration_collate_fn_stack_mode([dict(h)], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
-                                                  cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+                                                  cfg.backbone.init_radius, NEIGHBOR_LIMITS, early=early)
         T = model(data)["estimated_transform"]
         local_T[i] = T
         return T.cpu()  # the step's result is read back on the host every step (64 bytes)

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "gr_kpconv_block": (_i32, [_vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "gr_kpconv_fpn_workspace_size": (_sz, [_vp, _vp]),
     "gr_kpconv_fpn": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gr_kpconv_fpn_from": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_group_norm_workspace_size": (_sz, [_i64, _i32]),
     "gr_group_norm": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gr_layer_norm_add": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
@@ -102,7 +103,7 @@ _SIGNATURES = {
     "gr_embedding_combine": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gr_pack_weight_tf32x3": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "gr_structure_embedding_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gr_radius_pyramid": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, ctypes.c_size_t, _vp, _vp, _i32, _vp]),
+    "gr_radius_pyramid": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, ctypes.c_size_t, _vp, _vp, _i32, ctypes.c_uint32, _vp]),
     "gr_pack_weight_f16x2": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "gr_structure_embedding_fused_f16": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -230,14 +230,16 @@ static int block_out_channels(const gr_block_weights& b) { return b.kind == 0 ? 
 static const int kBlockStage[GR_FPN_BLOCKS] = {0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
 static const bool kBlockStrided[GR_FPN_BLOCKS] = {false, false, true, false, false, true, false, false, true, false, false, true, false, false};
 
+// start_block > 0: `feats` are the features AFTER block start_block - 1 (on the support points of block start_block): the
+// caller ran the first blocks itself, e.g. the two stage-0 blocks while the rest of the pyramid was still being built
 static int fpn(const gr_fpn_weights& W, const gr_pyramid& P, const float* feats, float* out_l2, float* out_l3, float* out_l4,
-               float* out_f5, Arena& ar, void* st) {
+               float* out_f5, Arena& ar, void* st, int start_block = 0) {
   const int G = W.group_norm;
   const float eps = W.eps;
   const float* cur = feats;      // features on the support points of the next block
   const float* stage_out[GR_FPN_STAGES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int stage_ch[GR_FPN_STAGES] = {0, 0, 0, 0, 0};
-  for (int i = 0; i < GR_FPN_BLOCKS; ++i) {
+  for (int i = start_block; i < GR_FPN_BLOCKS; ++i) {
     const gr_block_weights& b = W.blocks[i];
     const int qs = kBlockStage[i];
     const bool strided = kBlockStrided[i];
@@ -354,9 +356,21 @@ extern "C" size_t gr_kpconv_fpn_workspace_size(const gr_fpn_weights* w, const gr
   return ar.peak + 256;
 }
 
+extern "C" int gr_kpconv_fpn_from(const gr_fpn_weights* w, const gr_pyramid* pyr, int start_block, const float* feats, float* out_l2,
+                                  float* out_l3, float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream);
+
 extern "C" int gr_kpconv_fpn(const gr_fpn_weights* w, const gr_pyramid* pyr, const float* feats, float* out_l2, float* out_l3,
                              float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream) {
+  return gr_kpconv_fpn_from(w, pyr, 0, feats, out_l2, out_l3, out_l4, out_f5, ws, ws_bytes, stream);
+}
+
+/* Same, entering at block `start_block` (0, or 2 = after the two stage-0 blocks encoder1_1 / encoder1_2, whose output the
+ * caller passes as `feats`): stage 0 needs nothing but the input cloud and its own neighbour table, so those blocks can
+ * be queued before the rest of the pyramid is known. */
+extern "C" int gr_kpconv_fpn_from(const gr_fpn_weights* w, const gr_pyramid* pyr, int start_block, const float* feats, float* out_l2,
+                                  float* out_l3, float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream) {
   if (!w || !pyr || !feats || !out_l2 || !out_l3 || !out_l4 || !out_f5 || w->group_norm <= 0) return GR_ERR_BAD_ARG;
+  if (start_block != 0 && start_block != 2) return GR_ERR_BAD_ARG;
   for (int s = 0; s < GR_FPN_STAGES; ++s) {
     if (pyr->n_points[s] <= 0 || !pyr->points[s] || !pyr->neighbors[s] || pyr->neighbors_w[s] <= 0) return GR_ERR_BAD_ARG;
     if (s + 1 < GR_FPN_STAGES && (!pyr->subsampling[s] || !pyr->upsampling[s] || pyr->subsampling_w[s] <= 0 || pyr->upsampling_w[s] <= 0))
@@ -364,5 +378,5 @@ extern "C" int gr_kpconv_fpn(const gr_fpn_weights* w, const gr_pyramid* pyr, con
   }
   if (!ws) return GR_ERR_WORKSPACE;
   Arena ar(ws, ws_bytes, false);
-  return fpn(*w, *pyr, feats, out_l2, out_l3, out_l4, out_f5, ar, stream);
+  return fpn(*w, *pyr, feats, out_l2, out_l3, out_l4, out_f5, ar, stream, start_block);
 }

@@ -924,12 +924,13 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
 /* G3: the pyramid's searches in one call (see include/gaussreg_b200.h). */
 extern "C" int gr_radius_pyramid(const float* const* stage_points, const int64_t* const* stage_lengths, int n_stages, int batch,
                                  int64_t capacity, void* const* stage_grid_ws, size_t grid_ws_bytes, void* const* stage_ready_events,
-                                 const gr_pyramid_search* searches, int n_searches, void* stream) {
+                                 const gr_pyramid_search* searches, int n_searches, uint32_t built_mask, void* stream) {
   if (!stage_points || !stage_lengths || !stage_grid_ws || !searches || n_stages <= 0 || n_stages > 16 || n_searches < 0 || batch <= 0 ||
       capacity < 0)
     return GR_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool built[16] = {};
+  for (int i = 0; i < 16; ++i) built[i] = (built_mask >> i) & 1u;  // grids an earlier call already left in stage_grid_ws
   int waited = 0;
   for (int j = 0; j < n_searches; ++j) {
     const gr_pyramid_search& q = searches[j];

@@ -48,7 +48,8 @@ class LazyTables(list):
         return list.__repr__(self)
 
 
-def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, lazy=True):
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, lazy=True, early=None,
+                               features=None):
     """utils/data.py:13-77 on the GPU.  Returns the reference's dict plus `lengths_host` (python ints per stage and
     cloud, read in the same device->host transfer as the stage sizes, so that the model needs no sync of its own).
     With `lazy` (default) the three table lists are LazyTables: same contents, trimmed on first access.
@@ -104,12 +105,13 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     # stage serves all three (5 grids for 13 searches).
     built = [False] * num_stages
 
-    def searches_native(stream):
-        # one C-ABI call for the 13 searches (gr_radius_pyramid): ~50 us of host time instead of ~0.6 ms
+    def searches_native(stream, first=0, last=None, built_mask=0):
+        # one C-ABI call for the searches [first, last) (gr_radius_pyramid): ~50 us of host time instead of ~0.6 ms for 13
         L = _lib.lib()
-        arr = (_lib.PyramidSearch * len(specs))()
-        for j, (key, qs, ss, rad, limit) in enumerate(specs):
-            a = arr[j]
+        sel = specs[first:last]
+        arr = (_lib.PyramidSearch * len(sel))()
+        for j, (key, qs, ss, rad, limit) in enumerate(sel, start=first):
+            a = arr[j - first]
             a.query_stage, a.support_stage, a.radius, a.limit = qs, ss, float(rad), int(limit)
             a.out_idx, a.out_max_count = tables[j].data_ptr(), counts_dev[j:j + 1].data_ptr()
         vp = ctypes.c_void_p * num_stages
@@ -117,12 +119,28 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         len_arr = vp(*[l.data_ptr() for l in len_dev])
         ws_arr = vp(*[g.data_ptr() for g in grids])
         ev_arr = vp(*[(e.cuda_event if e is not None else None) for e in ready]) if side is not None else None
-        st = L.gr_radius_pyramid(pts_arr, len_arr, num_stages, nb, n0, ws_arr, min(g.numel() for g in grids), ev_arr, arr, len(specs),
-                                 stream.cuda_stream)
+        st = L.gr_radius_pyramid(pts_arr, len_arr, num_stages, nb, n0, ws_arr, min(g.numel() for g in grids), ev_arr, arr, len(sel),
+                                 built_mask, stream.cuda_stream)
         _lib.check(st, "radius_pyramid")
 
+    native = os.environ.get("GAUSSREG_PYRAMID_NATIVE", "1") != "0"
+    early_out = None
+    if early is not None and native and side is not None and features is not None and specs[0][:3] == ("neighbors", 0, 0):
+        # Stage 0 needs nothing from the subsampling chain: its neighbour table first, then the caller's stage-0 work
+        # (the first two backbone blocks) on the caller's stream, right behind the chain.  The GPU then stays busy while
+        # the host waits for the stage sizes below and prepares what depends on them.  The table is passed untrimmed
+        # (n0, limit): its padding entries are shadow neighbours.
+        with torch.cuda.stream(side):
+            searches_native(side, 0, 1)
+            ev0 = torch.cuda.Event()
+            ev0.record(side)
+        main.wait_event(ev0)
+        early_out = early(features, pts_cap[0], tables[0])
+
     def searches():
-        if os.environ.get("GAUSSREG_PYRAMID_NATIVE", "1") != "0":
+        if native:
+            if early_out is not None:
+                return searches_native(side, 1, None, built_mask=1)
             return searches_native(side if side is not None else main)
         waited = 0
         for j, (key, qs, ss, rad, limit) in enumerate(specs):
@@ -150,6 +168,8 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     sizes = [n0] + [int(t) for t in tot]
     points_list = [pts_cap[i][: sizes[i]] for i in range(num_stages)]
     out = {"points": points_list, "lengths": len_dev, "lengths_host": lengths_host}
+    if early_out is not None:
+        out["early_features"] = early_out
 
     def finalize():
         if done is not None:
@@ -178,8 +198,12 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
 
 
 def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, search_radius, neighbor_limits,
-                                       precompute_data=True):
-    """utils/data.py:139-189.  Points are organised [ref_1..ref_B, src_1..src_B]."""
+                                       precompute_data=True, early=None):
+    """utils/data.py:139-189.  Points are organised [ref_1..ref_B, src_1..src_B].
+
+    `early` (extension, e.g. ``model.backbone.forward_early``): a callable (features, points0, neighbors0) -> tensor that
+    is queued on the GPU as soon as stage 0 of the pyramid is known; its result is returned as ``early_features`` and
+    picked up by ``KPConvFPN.forward``."""
     batch_size = len(data_dicts)
     collated = {}
     for data_dict in data_dicts:
@@ -197,7 +221,8 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
             collated[key] = value[0]
     collated["features"] = feats
     if precompute_data:
-        collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits))
+        collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits,
+                                                   early=early if batch_size == 1 else None, features=feats))
     else:
         collated["points"] = points.to(dev)
         collated["lengths"] = lengths.to(dev)

@@ -53,9 +53,9 @@ def run(args):
     src_color = data_dict["src_feats"][:, 1:].cpu().numpy()
     host = {k: data_dict[k] for k in ("ref_adjust_scale", "src_adjust_scale", "ref_center", "src_center")}
     tensors = {k: v for k, v in data_dict.items() if k not in host}
+    model = load_model(cfg, args.weights)
     data = registration_collate_fn_stack_mode([tensors], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
                                               cfg.backbone.init_radius, NEIGHBOR_LIMITS)
-    model = load_model(cfg, args.weights)
     out = model(data)
     estimated_transform = out["estimated_transform"].cpu().numpy()
     ref_points, src_points = out["ref_points"].cpu().numpy(), out["src_points"].cpu().numpy()

@@ -35,8 +35,22 @@ class KPConvFPN(nn.Module):
         """One C-ABI call (csrc/backbone.cu issues every kernel of the 14 blocks and 3 decoders); the per-module
         Python path below is kept for teacher-forced tests (GAUSSREG_FPN_NATIVE=0)."""
         if os.environ.get("GAUSSREG_FPN_NATIVE", "1") != "0":
+            early = data_dict.get("early_features")
+            if early is not None:  # encoder1_1 / encoder1_2 already ran (forward_early, queued by the collate function)
+                return ops.kpconv_fpn(self, early, data_dict, start_block=2)
             return ops.kpconv_fpn(self, feats, data_dict)
         return self.forward_modules(feats, data_dict)
+
+    @torch.no_grad()
+    def forward_early(self, feats, points0, neighbors0):
+        """The two stage-0 blocks (backbone.py:166-167).  They need the input cloud and its own neighbour table only, so
+        `registration_collate_fn_stack_mode(..., early=model.backbone.forward_early)` queues them right behind the
+        grid-subsampling chain, BEFORE the host reads the stage sizes.  `neighbors0` may be the untrimmed (N, limit)
+        table: the padding entries are shadow neighbours and contribute exact zeros, the result is bit-identical
+        (tests/test_configs_gpu.py).  Opt-in: on a B200 it measured slower (7.56 vs 7.35 ms per pair) because the helper
+        stream is running the radius searches in exactly that window."""
+        f1 = self.encoder1_1(feats, points0, points0, neighbors0)
+        return self.encoder1_2(f1, points0, points0, neighbors0)
 
     @torch.no_grad()
     def forward_modules(self, feats, data_dict):

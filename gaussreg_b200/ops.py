@@ -256,7 +256,7 @@ _FPN_BLOCK_NAMES = ("encoder1_1", "encoder1_2", "encoder2_1", "encoder2_2", "enc
                     "encoder4_1", "encoder4_2", "encoder4_3", "encoder5_1", "encoder5_2", "encoder5_3")
 
 
-def kpconv_fpn(backbone, feats, data_dict):
+def kpconv_fpn(backbone, feats, data_dict, start_block=0):
     """KPConvFPN.forward (backbone.py:164-212) as ONE C-ABI call -> [l2, l3, l4, f5]."""
     import ctypes
     import torch.nn as nn
@@ -317,8 +317,8 @@ def kpconv_fpn(backbone, feats, data_dict):
             torch.empty((n[4], W.blocks[13].unary2.out_channels), dtype=_F32, device=dev)]
     L = _lib.lib()
     ws = _workspace(L.gr_kpconv_fpn_workspace_size(ctypes.byref(W), ctypes.byref(P)), dev)
-    st = L.gr_kpconv_fpn(ctypes.byref(W), ctypes.byref(P), feats.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
-                         outs[2].data_ptr(), outs[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    st = L.gr_kpconv_fpn_from(ctypes.byref(W), ctypes.byref(P), int(start_block), feats.data_ptr(), outs[0].data_ptr(),
+                              outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(st, "kpconv_fpn")
     return outs
 

@@ -92,7 +92,8 @@ int gr_radius_neighbors_cached(const float* q_points, const float* s_points, con
  * its own (capacity, limit) table, one cell grid per support stage (stage_grid_ws[s], each grid_ws_bytes >=
  * gr_radius_neighbors_workspace_size(capacity, capacity, batch)) shared by the searches of that stage in call order.
  * stage_ready_events[s] (cudaEvent_t, may be NULL) is waited on `stream` before the first search that touches stage s:
- * the grid-subsampling chain may run on another stream. */
+ * the grid-subsampling chain may run on another stream.  Bit s of built_mask: stage_grid_ws[s] already holds the grid of
+ * stage s (an earlier call of this function searched that stage). */
 typedef struct {
   int query_stage, support_stage;
   float radius;
@@ -102,7 +103,7 @@ typedef struct {
 } gr_pyramid_search;
 int gr_radius_pyramid(const float* const* stage_points, const int64_t* const* stage_lengths, int n_stages, int batch,
                       int64_t capacity, void* const* stage_grid_ws, size_t grid_ws_bytes, void* const* stage_ready_events,
-                      const gr_pyramid_search* searches, int n_searches, void* stream);
+                      const gr_pyramid_search* searches, int n_searches, uint32_t built_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense fp32 product with fused epilogue (used by K1 contraction, K2 Linear, T1-T3 projections,
@@ -236,6 +237,11 @@ int gr_kpconv_block(const gr_kpconv_weights* h_w, const float* gn_weight, const 
 size_t gr_kpconv_fpn_workspace_size(const gr_fpn_weights* h_w, const gr_pyramid* h_pyr);
 int gr_kpconv_fpn(const gr_fpn_weights* h_w, const gr_pyramid* h_pyr, const float* feats, float* out_l2, float* out_l3,
                   float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream);
+/* gr_kpconv_fpn entering at block `start_block` (0 or 2): with 2, `feats` is the output of encoder1_2 -- the two stage-0
+ * blocks (gr_kpconv_block) need only the input cloud and neighbors[0] and may have been queued while the rest of the
+ * pyramid was still being built (backbone.py:166-167 vs :168-212). */
+int gr_kpconv_fpn_from(const gr_fpn_weights* w, const gr_pyramid* pyr, int start_block, const float* feats, float* out_l2,
+                       float* out_l3, float* out_l4, float* out_f5, void* ws, size_t ws_bytes, void* stream);
 
 /* N1  farthest-point subsampling to `point_limit` (demo.py:44-47; restates exact FPS, the result the third-party
  * fpsample.bucket_fps_kdline_sampling accelerates).  points (n,3) -> out_idx (k) i64 in selection order. */

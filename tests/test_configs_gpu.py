@@ -221,3 +221,23 @@ def test_fewer_superpoint_pairs_than_requested_takes_the_slow_path():
     # (the LGR transform of a 0.6 m toy cloud under random weights is ill-conditioned -- a handful of correspondences --
     # so the comparison stops at the Sinkhorn output of the c patch pairs)
     assert rel_l2(out["matching_scores"].cpu(), want["matching_scores"]) < 1e-4
+
+
+def test_early_stage0_blocks_change_nothing():
+    """`registration_collate_fn_stack_mode(..., early=model.backbone.forward_early)` runs encoder1_1 / encoder1_2 on the
+    untrimmed stage-0 neighbour table before the rest of the pyramid exists: same bits as the plain order."""
+    cfg = make_cfg()
+    model = seeded_model(0).cuda()
+    d = make_pair_inputs(seed=3, n_points=6000)
+    args = (cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    plain = registration_collate_fn_stack_mode([{k: d[k] for k in KEYS}], *args)
+    assert "early_features" not in plain
+    out_plain = model(plain)
+    early = registration_collate_fn_stack_mode([{k: d[k] for k in KEYS}], *args, early=model.backbone.forward_early)
+    assert "early_features" in early
+    f1 = model.backbone.encoder1_2(model.backbone.encoder1_1(plain["features"], plain["points"][0], plain["points"][0], plain["neighbors"][0]),
+                                   plain["points"][0], plain["points"][0], plain["neighbors"][0])
+    assert torch.equal(early["early_features"], f1)
+    out_early = model(early)
+    for key in ("ref_feats_c", "src_feats_c", "ref_feats_f", "matching_scores", "estimated_transform"):
+        assert torch.equal(out_plain[key], out_early[key]), key

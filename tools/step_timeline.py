@@ -31,7 +31,8 @@ pts = torch.from_numpy(np.concatenate([d["ref_points"], d["src_points"]])).cuda(
 feats = torch.from_numpy(np.concatenate([d["ref_feats"], d["src_feats"]])).cuda()
 lens = torch.tensor([n, n], dtype=torch.int64, device="cuda")
 def step():
-    data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, NEIGHBOR_LIMITS)
+    data = precompute_data_stack_mode(pts, lens, cfg.backbone.num_stages, cfg.backbone.init_voxel_size, cfg.backbone.init_radius, NEIGHBOR_LIMITS,
+                                      early=model.backbone.forward_early if os.environ.get('GAUSSREG_EARLY', '0') == '1' else None, features=feats)
     data["features"] = feats
     return model(data)["estimated_transform"]
 for _ in range(5): step()
