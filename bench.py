@@ -403,8 +403,10 @@ def config5_large_pair(model, dev, steps=2):
            "pairs_per_s": 1e3 * len(times) / sum(times), "finite": bool(torch.isfinite(T).all())}
     if t1_ms > 0:
         tf = t1_flop / (t1_ms * 1e-3) / 1e12
+        f16 = getattr(lib, "t1_kind", "tf32") == "f16"  # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
         res["structure_embedding"] = {"ms": t1_ms, "achieved": tf, "unit": "TFLOP/s fp32-equivalent", "frac_of_bf16_sustained": tf / peaks["tf_sustained"],
-                                      "tf32_mma_tflops": 3.0 * tf, "frac_of_tf32_peak": 3.0 * tf / (peaks["tf_sustained"] / 2.0)}
+                                      "mma_kind": "f16" if f16 else "tf32", "mma_tflops": 3.0 * tf,
+                                      "frac_of_mma_peak": 3.0 * tf / (peaks["tf_sustained"] if f16 else peaks["tf_sustained"] / 2.0)}
     return res
 
 
@@ -549,7 +551,6 @@ def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microben
                        (", issued as kind::f16 at the bf16 rate: tensor-pipe occupancy ~ 3 x frac" if f16 else
                         ", and kind::tf32 issues at half the bf16 rate: tensor-pipe occupancy ~ 6 x frac"),
         "mma_kind": "f16" if f16 else "tf32", "mma_tflops": 3.0 * achieved, "frac_of_mma_peak": 3.0 * achieved / mma_peak,
-        "tf32_mma_tflops": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (peaks["tf_sustained"] / 2.0),
         "launches_per_step": n_t1, "avg_launch_ms": t1_ms / n_t1, "flop_per_launch_fp32_equiv": t1_flop / n_t1,
         "share_of_step": t1_ms / max(sum(per_op.values()), 1e-9),
         "algorithmic_bytes_per_launch": 4.0 * t1_rows * (256 + 4), "traffic": None,
