@@ -27,7 +27,9 @@ class UnaryWeights(ctypes.Structure):
     """gr_unary_weights (include/gaussreg_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("weight", "weight_packed", "bias", "gn_weight", "gn_bias")] + \
                [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "leaky_relu", "split_k")] + \
-               [(n, ctypes.c_void_p) for n in ("weight_packed_lo", "weight_packed_hi")]
+               [(n, ctypes.c_void_p) for n in ("weight_packed_lo", "weight_packed_hi", "weight_packed16", "weight_packed16_lo",
+                                               "weight_packed16_hi")] + \
+               [(n, ctypes.c_float) for n in ("inv_scale16", "inv_scale16_lo", "inv_scale16_hi")]
 
 
 class PyramidSearch(ctypes.Structure):
@@ -39,7 +41,8 @@ class PyramidSearch(ctypes.Structure):
 class KPConvWeights(ctypes.Structure):
     """gr_kpconv_weights."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("weights", "weights_kmajor", "weights_kmajor_packed", "bias", "kernel_points")] + \
-               [("sigma", ctypes.c_float), ("in_channels", ctypes.c_int), ("out_channels", ctypes.c_int)]
+               [("sigma", ctypes.c_float), ("in_channels", ctypes.c_int), ("out_channels", ctypes.c_int),
+                ("weights_kmajor_packed16", ctypes.c_void_p), ("inv_scale16", ctypes.c_float)]
 
 
 class BlockWeights(ctypes.Structure):
@@ -78,6 +81,7 @@ _SIGNATURES = {
     "gr_gemm": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                        _vp, _i64, _i64, _i32, _vp]),
     "gr_linear_packed": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "gr_linear_packed16": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _f32, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "gr_set_gemm_mode": (None, [_i32]),
     "gr_get_gemm_mode": (_i32, []),
     "gr_last_gemm_path": (_i32, []),
@@ -104,6 +108,9 @@ _SIGNATURES = {
     "gr_pack_weight_tf32x3": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "gr_structure_embedding_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gr_radius_pyramid": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, ctypes.c_size_t, _vp, _vp, _i32, ctypes.c_uint32, _vp]),
+    "gr_packed_weight_f16_bytes": (ctypes.c_size_t, [_i32, _i32]),
+    "gr_pack_weight_f16x3": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
+    "gr_gemm_f16_overflow_ptr": (_i32, [_vp]),
     "gr_pack_weight_f16x2": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "gr_structure_embedding_fused_f16": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

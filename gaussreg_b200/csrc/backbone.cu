@@ -76,13 +76,14 @@ static int unary(const gr_unary_weights& w, const float* x, long long rows, int 
   int rc = GR_OK;
   if (!w.gn_weight) {
     if (!ar.dry) rc = gemm_ex(x, in, w.weight, in, 1, y, out, (int)rows, out, in, 1.f, w.bias, nullptr, nullptr, 0, 0, st,
-                              w.weight_packed, nullptr);
+                              w.weight_packed, nullptr, w.weight_packed16, w.inv_scale16);
   } else {
     float* tmp = ar.take<float>((size_t)rows * out);
     GnStatsOut gn{ar.take<double2>(gn_blocks_capacity(rows) * groups), gn_blocks_capacity(rows), groups, 0};
     if (!ar.dry) {
       if (!ar.ok()) return GR_ERR_WORKSPACE;
-      rc = gemm_ex(x, in, w.weight, in, 1, tmp, out, (int)rows, out, in, 1.f, w.bias, nullptr, nullptr, 0, 0, st, w.weight_packed, &gn);
+      rc = gemm_ex(x, in, w.weight, in, 1, tmp, out, (int)rows, out, in, 1.f, w.bias, nullptr, nullptr, 0, 0, st, w.weight_packed, &gn,
+                   w.weight_packed16, w.inv_scale16);
     }
     if (rc == GR_OK)
       rc = norm_after_product(tmp, rows, out, groups, eps, gn, w.gn_weight, w.gn_bias, add, w.leaky_relu ? 2 : act_after_add, y, ar, st);
@@ -140,7 +141,7 @@ static int kpconv(const gr_kpconv_weights& w, const float* gn_w, const float* gn
       GnStatsOut* gp = (gn_w && stats_ok) ? &g : nullptr;
       if (w.weights_kmajor && KC % 4 == 0)
         rc = gemm_ex(A, KC, w.weights_kmajor, KC, 1, tmp + (size_t)r0 * Co, Co, rows, Co, KC, 1.f, w.bias, row_div + r0, nullptr, 0, 0, st,
-                     w.weights_kmajor_packed, gp);
+                     w.weights_kmajor_packed, gp, w.weights_kmajor_packed16, w.inv_scale16);
       else
         rc = gemm_ex(A, KC, w.weights, Co, 0, tmp + (size_t)r0 * Co, Co, rows, Co, KC, 1.f, w.bias, row_div + r0, nullptr, 0, 0, st, nullptr,
                      nullptr), gp = nullptr;
@@ -192,9 +193,11 @@ static int block(const gr_block_weights& b, int groups, float eps, const float* 
     if (!ar.dry) {
       if (!ar.ok()) return GR_ERR_WORKSPACE;
       GR_TRY(gemm_ex(sc, b.shortcut.in_channels, b.shortcut.weight, b.shortcut.in_channels, 1, ts, out, M, out, b.shortcut.in_channels, 1.f,
-                     b.shortcut.bias, nullptr, nullptr, 0, 0, st, b.shortcut.weight_packed, &gs));
+                     b.shortcut.bias, nullptr, nullptr, 0, 0, st, b.shortcut.weight_packed, &gs, b.shortcut.weight_packed16,
+                     b.shortcut.inv_scale16));
       GR_TRY(gemm_ex(c, b.unary2.in_channels, b.unary2.weight, b.unary2.in_channels, 1, tu, out, M, out, b.unary2.in_channels, 1.f,
-                     b.unary2.bias, nullptr, nullptr, 0, 0, st, b.unary2.weight_packed, &gu));
+                     b.unary2.bias, nullptr, nullptr, 0, 0, st, b.unary2.weight_packed, &gu, b.unary2.weight_packed16,
+                     b.unary2.inv_scale16));
       if (gs.nblk > 0 && gu.nblk > 0) {
         GR_TRY(group_norm_finalize(gs.partial, gs.nblk, M, out, groups, eps, st_s, st));
         GR_TRY(group_norm_finalize(gu.partial, gu.nblk, M, out, groups, eps, st_u, st));
@@ -282,10 +285,10 @@ static int fpn(const gr_fpn_weights& W, const gr_pyramid& P, const float* feats,
         if (!ar.ok()) return GR_ERR_WORKSPACE;
         float* dst = d.w->gn_weight ? tmp : y;
         GR_TRY(gemm_ex(coarse, coarse_ch, d.w->weight, in, 1, yc, out, Nc, out, coarse_ch, 1.f, nullptr, nullptr, nullptr, 0, 0, st,
-                       d.w->weight_packed_lo, nullptr));
+                       d.w->weight_packed_lo, nullptr, d.w->weight_packed16_lo, d.w->inv_scale16_lo));
         GR_TRY(gr_upsample_concat(yc, Nc, out, P.upsampling[f], P.upsampling_ld[f], nullptr, 0, M, dst, st));
         rc = gemm_ex(stage_out[f], C2, d.w->weight + coarse_ch, in, 1, dst, out, M, out, C2, 1.f, d.w->bias, nullptr, dst, out, 0, st,
-                     d.w->weight_packed_hi, d.w->gn_weight ? &gn : nullptr);
+                     d.w->weight_packed_hi, d.w->gn_weight ? &gn : nullptr, d.w->weight_packed16_hi, d.w->inv_scale16_hi);
       }
       if (rc == GR_OK && d.w->gn_weight)
         rc = norm_after_product(tmp, M, out, G, eps, gn, d.w->gn_weight, d.w->gn_bias, nullptr, d.w->leaky_relu ? 2 : 0, y, ar, st);

@@ -50,7 +50,7 @@ struct GnStatsOut {
 // gemm.cu: C = act(alpha A op(B) / row_div + bias + residual) with optional packed weights / GroupNorm statistics
 int gemm_ex(const float* A, long long lda, const float* B, long long ldb, int trans_b, float* C, long long ldc, int M, int N, int K,
             float alpha, const float* bias, const float* row_div, const float* residual, long long ldr, int act, void* stream,
-            const float* B_packed, GnStatsOut* gn);
+            const float* B_packed, GnStatsOut* gn, const void* B_packed16 = nullptr, float inv_scale16 = 1.f);
 // norm.cu: y = act(GroupNorm(x) [+ add]) from partial statistics (finalize + apply); ws holds `groups` float2
 int group_norm_from_partial(const float* x, long long n_rows, int C, int groups, const double2* partial, int nblk,
                             const float* gamma, const float* beta, float eps, const float* add, int act, float* y,

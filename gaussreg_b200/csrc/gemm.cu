@@ -634,7 +634,7 @@ int sgemm(const GemmParams& p, int batch, bool transb, cudaStream_t st) {
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
                 const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed,
-                GnStatsOut* gn);
+                GnStatsOut* gn, const void* B_packed16, float inv_scale16);
 
 static int g_gemm_mode = -1;  // 0: SIMT only, 1: tensor cores where the problem qualifies
 static thread_local int g_last_path = 0;
@@ -659,14 +659,15 @@ extern "C" int gr_last_gemm_path(void) { return g_last_path; }
 static int gemm_dispatch(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
                          int trans_b, float* C, int64_t ldc, int64_t strideC, int M, int N, int K, int batch, float alpha,
                          const float* bias, const float* row_div, const float* residual, int64_t ldr, int64_t strideR,
-                         int act, void* stream, const float* B_packed, GnStatsOut* gn = nullptr) {
+                         int act, void* stream, const float* B_packed, GnStatsOut* gn = nullptr, const void* B_packed16 = nullptr,
+                         float inv_scale16 = 1.f) {
   if (gn) gn->nblk = 0;
   if (M < 0 || N < 0 || K < 0 || batch < 0 || act < 0 || act > 2) return GR_ERR_BAD_ARG;
   if (M == 0 || N == 0 || batch == 0) return GR_OK;
   if (!A || !B || !C) return GR_ERR_BAD_ARG;
   if (trans_b && gr_get_gemm_mode() == 1) {
     const int rc = gemm_tf32x3(A, lda, strideA, B, ldb, strideB, C, ldc, strideC, M, N, K, batch, alpha, bias, row_div, residual,
-                               ldr, strideR, act, static_cast<cudaStream_t>(stream), B_packed, gn);
+                               ldr, strideR, act, static_cast<cudaStream_t>(stream), B_packed, gn, B_packed16, inv_scale16);
     if (rc <= 0) { g_last_path = 1; return rc; }
   }
   if (gn) gn->nblk = 0;
@@ -682,9 +683,9 @@ static int gemm_dispatch(const float* A, int64_t lda, int64_t strideA, const flo
 namespace gr {
 int gemm_ex(const float* A, long long lda, const float* B, long long ldb, int trans_b, float* C, long long ldc, int M, int N, int K,
             float alpha, const float* bias, const float* row_div, const float* residual, long long ldr, int act, void* stream,
-            const float* B_packed, GnStatsOut* gn) {
+            const float* B_packed, GnStatsOut* gn, const void* B_packed16, float inv_scale16) {
   return gemm_dispatch(A, lda, 0, B, ldb, 0, trans_b, C, ldc, 0, M, N, K, 1, alpha, bias, row_div, residual, ldr, 0, act, stream,
-                       B_packed, gn);
+                       B_packed, gn, B_packed16, inv_scale16);
 }
 }  // namespace gr
 
@@ -703,4 +704,13 @@ extern "C" int gr_linear_packed(const float* A, int64_t lda, const float* W, int
                                 int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* row_div,
                                 const float* residual, int64_t ldr, int act, void* stream) {
   return gemm_dispatch(A, lda, 0, W, ldw, 0, 1, C, ldc, 0, M, N, K, 1, alpha, bias, row_div, residual, ldr, 0, act, stream, W_packed);
+}
+
+/* gr_linear_packed with the fp16-split image of W as well (gr_pack_weight_f16x3, packing scale 1 / inv_scale16): products the
+ * tensor-core path accepts then run on kind::f16 (see gemm_tc.cu). */
+extern "C" int gr_linear_packed16(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_packed,
+                                  const void* W_packed16, float inv_scale16, float* C, int64_t ldc, int M, int N, int K, float alpha,
+                                  const float* bias, const float* row_div, const float* residual, int64_t ldr, int act, void* stream) {
+  return gemm_dispatch(A, lda, 0, W, ldw, 0, 1, C, ldc, 0, M, N, K, 1, alpha, bias, row_div, residual, ldr, 0, act, stream, W_packed,
+                       nullptr, W_packed16, inv_scale16);
 }

@@ -17,6 +17,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace gr {
@@ -47,6 +49,11 @@ struct Params {
   // (sum, sum of squares) of the final values, folded in a fixed order -> gn_partial[blockIdx.y * gn_groups + g]
   double2* gn_partial;
   int gn_groups;
+  // optional: B pre-split into fp16 hi/lo tiles (gr_pack_weight_f16x3: per 128-row tile and 64-wide k-block [hi 16 KB][lo 16 KB],
+  // B multiplied by a power of two whose inverse the launcher folds into alpha) for the kind::f16 persistent kernel
+  const unsigned char* B_packed16;
+  int packed_kblocks64;
+  float inv_scale16;
 };
 
 template <int BN>
@@ -819,6 +826,338 @@ __global__ void __launch_bounds__(kThreadsPersist, 1) gemm_tf32x3_persist_kernel
   }
 }
 
+// ---- the same persistent kernel with fp16-split operands ("3xFP16") ---------------------------------------------------
+// A tcgen05.mma dispatch costs ~80 cycles on these tiles whatever its kind (measured with GAUSSREG_GEMM_DEBUG: the
+// operand fetch from shared memory is 32 bytes per row either way), and kind::f16 covers K = 16 per dispatch where
+// kind::tf32 covers 8.  fp16 and TF32 carry the same 11 significant bits, so x = hi + lo in two fp16 parts is as
+// accurate as the TF32 split provided the values sit in fp16's range: weights are pre-scaled by a power of two at
+// packing time (divided out through alpha), activations are O(1..1e3) after GroupNorm / neighbourhood sums, and the
+// splitter raises a device flag (gr_gemm_f16_overflow_ptr) should it ever meet |x| > 6e4.
+// k-block = 64 K elements = two TMA boxes of 128 x 32 fp32 (raw ring of boxes) -> the splitter warps convert them into
+// one fp16 hi tile and one fp16 lo tile (128-byte rows, SWIZZLE_128B) -> 4 k-steps x 3 MMAs.  The raw boxes are released
+// by the splitters (the tensor core never reads them), the operand stages by the MMA commits.
+template <int BN>
+struct CfgPersist16 {
+  static constexpr int kBoxBytes = BM * BK * 4;          // one raw TMA box: 128 rows x 32 fp32 = 16 KB
+  static constexpr int kABytes = BM * 128;               // one fp16 operand tile of A: 128 rows x 64 halves = 16 KB
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kOpBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kOps = 2;
+  static constexpr int kRaw = BN == 128 ? 3 : 4;         // boxes; a k-block takes two consecutive ones
+  static constexpr int kEpiBytes = 8 * 32 * 36 * 4 + 4 * BN * 8 + BN * 16;
+  static constexpr int kSmemBytes = kRaw * kBoxBytes + kOps * kOpBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
+};
+__device__ int g_f16_overflow;  // set when a splitter met |x| > 6e4 (fp16 tops out at 65504)
+
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsPersist, 1) gemm_f16x3_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, Params p,
+                                                                                int tiles_m, int tiles_n, int n_splits) {
+  using C = CfgPersist16<BN>;
+  constexpr int BK16 = 64;  // K elements per k-block
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
+  unsigned char* raw_ring = smem;
+  unsigned char* op_ring = smem + C::kRaw * C::kBoxBytes;
+  unsigned char* epi = op_ring + C::kOps * C::kOpBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::kEpiBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  auto raw_full = [&](int r) { return bar_base + 8u * r; };
+  auto raw_empty = [&](int r) { return bar_base + 8u * (C::kRaw + r); };
+  auto op_full = [&](int s) { return bar_base + 8u * (2 * C::kRaw + s); };
+  auto op_empty = [&](int s) { return bar_base + 8u * (2 * C::kRaw + C::kOps + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * C::kRaw + 2 * C::kOps + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * C::kRaw + 2 * C::kOps + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kRaw + 2 * C::kOps + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = tiles_m * tiles_n * n_splits;
+  const bool split = p.k_split > 0;
+
+  if (tid == 0) {
+    for (int r = 0; r < C::kRaw; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), 4); }
+    for (int s = 0; s < C::kOps; ++s) { mbar_init(op_full(s), 4 + 1); mbar_init(op_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(4 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  // tile t -> (m tile, n tile, k slice): n fastest, so that the CTAs of one wave share their A rows through L2
+  auto tile_coords = [&](int t, int& mt, int& nt, int& z) { nt = t % tiles_n; mt = (t / tiles_n) % tiles_m; z = t / (tiles_n * tiles_m); };
+  auto k_range = [&](int z, int& kbeg, int& nkb) {
+    kbeg = split ? z * p.k_split : 0;
+    const int kend = split ? min(p.K, kbeg + p.k_split) : p.K;
+    nkb = (kend - kbeg + BK16 - 1) / BK16;
+  };
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps: TMEM lane quarter q = warp & 3,
+    // column half = warp >> 2 (a warp may only touch the 32 TMEM lanes of its quarter)
+    const int q = warp & 3, half = warp >> 2;
+    float* stage = reinterpret_cast<float*>(epi) + warp * (32 * 36);
+    float2* gn_col = reinterpret_cast<float2*>(epi + 8 * 32 * 36 * 4);   // [4][BN]
+    double2* gn_cold = reinterpret_cast<double2*>(epi + 8 * 32 * 36 * 4 + 4 * BN * 8);  // [BN]
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int mt, nt, z;
+      tile_coords(t, mt, nt, z);
+      const int m0 = mt * BM, n0 = nt * BN, b = it & 1;
+      mbar_wait(acc_full(b), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(b * 2 * BN);
+      float* __restrict__ Cp = p.C + (long long)z * p.sC;
+      const float* __restrict__ R = p.residual ? p.residual + (long long)z * p.sR : nullptr;
+      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) &&
+                          (!R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t r[32], rc[32];
+        tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), rc);
+        if (c0 + 32 >= (half + 1) * (BN / 2)) {  // last TMEM read of this warp: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          v.y = __uint_as_float(r[j + 1]) + __uint_as_float(rc[j + 1]);
+          v.z = __uint_as_float(r[j + 2]) + __uint_as_float(rc[j + 2]);
+          v.w = __uint_as_float(r[j + 3]) + __uint_as_float(rc[j + 3]);
+          *reinterpret_cast<float4*>(stage + lane * 36 + j) = v;
+        }
+        __syncwarp();
+        const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+        const int n = n0 + c0 + c4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (n + 3 < p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) bv = *reinterpret_cast<const float4*>(p.bias + n);
+          else { if (n < p.N) bv.x = p.bias[n]; if (n + 1 < p.N) bv.y = p.bias[n + 1]; if (n + 2 < p.N) bv.z = p.bias[n + 2]; if (n + 3 < p.N) bv.w = p.bias[n + 3]; }
+        }
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + rsub;
+          const int m = m0 + q * 32 + row;
+          if (m >= p.M) continue;
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+          float x[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+          if (p.row_div) { const float rd = p.row_div[m]; x[0] /= rd; x[1] /= rd; x[2] /= rd; x[3] /= rd; }
+          x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
+          if (R) {
+            const float* rp = R + (long long)m * p.ldr + n;
+            if (vec_ok && n + 3 < p.N) { const float4 tt = *reinterpret_cast<const float4*>(rp); x[0] += tt.x; x[1] += tt.y; x[2] += tt.z; x[3] += tt.w; }
+            else { for (int e = 0; e < 4; ++e) if (n + e < p.N) x[e] += rp[e]; }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.act == 1) x[e] = fmaxf(x[e], 0.f);
+            else if (p.act == 2) x[e] = x[e] > 0.f ? x[e] : 0.1f * x[e];
+          }
+          float* dst = Cp + (long long)m * p.ldc + n;
+          if (vec_ok && n + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          else { for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = x[e]; }
+          if (p.gn_partial) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) { cs[e] += x[e]; cq[e] = fmaf(x[e], x[e], cq[e]); }
+          }
+        }
+        if (p.gn_partial) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+          }
+          if (rsub == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gn_col[q * BN + c0 + c4 + e] = make_float2(cs[e], cq[e]);
+          }
+        }
+        __syncwarp();  // the transposition tile is rewritten by the next chunk
+      }
+      if (p.gn_partial) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (tid < BN) {
+          double a = 0.0, bsum = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { const float2 v = gn_col[qq * BN + tid]; a += (double)v.x; bsum += (double)v.y; }
+          gn_cold[tid] = make_double2(a, bsum);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int cg = p.N / p.gn_groups;
+        if (tid < BN / cg) {
+          const int gidx = n0 / cg + tid;
+          if (gidx < p.gn_groups) {
+            double a = 0.0, bsum = 0.0;
+            for (int c = tid * cg; c < (tid + 1) * cg; ++c) { a += gn_cold[c].x; bsum += gn_cold[c].y; }
+            p.gn_partial[(long long)mt * p.gn_groups + gidx] = make_double2(a, bsum);
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // gn_col / gn_cold are free for the next tile
+      }
+    }
+    tc_fence_before();
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ splitters: two fp32 boxes -> fp16 hi / lo tiles
+    const int stid = tid - 256;
+    int kit = 0;
+    bool bad = false;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt, z, kbeg, nkb;
+      tile_coords(t, mt, nt, z);
+      k_range(z, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        const int s = kit % C::kOps;
+        const int b0 = 2 * kit, b1 = 2 * kit + 1;  // box counters
+        const int r0 = b0 % C::kRaw, r1 = b1 % C::kRaw;
+        if (kit >= C::kOps) mbar_wait(op_empty(s), ((kit / C::kOps) - 1) & 1);
+        mbar_wait(raw_full(r0), (b0 / C::kRaw) & 1);
+        mbar_wait(raw_full(r1), (b1 / C::kRaw) & 1);
+        unsigned char* hi_tile = op_ring + s * C::kOpBytes;
+        unsigned char* lo_tile = hi_tile + C::kABytes;
+#pragma unroll
+        for (int i = 0; i < BM * 8 / 128; ++i) {
+          // task = (row, output chunk oc of 8 halves): K elements 8 oc .. 8 oc + 7 = fp32 chunks 2q, 2q+1 of box oc >> 2
+          const int e = stid + i * 128, row = e >> 3, oc = e & 7, q = oc & 3;
+          const unsigned char* box = raw_ring + ((oc >> 2) ? r1 : r0) * C::kBoxBytes + (row >> 3) * 1024 + (row & 7) * 128;
+          const float4 v0 = *reinterpret_cast<const float4*>(box + (((2 * q) ^ (row & 7)) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(box + (((2 * q + 1) ^ (row & 7)) << 4));
+          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __half2 h = __floats2half2_rn(x[2 * c], x[2 * c + 1]);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x[2 * c] - hf.x, x[2 * c + 1] - hf.y);
+            hi[c] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[c] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          bad |= fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))),
+                       fmaxf(fmaxf(fabsf(x[4]), fabsf(x[5])), fmaxf(fabsf(x[6]), fabsf(x[7])))) > 6.0e4f;
+          const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((oc ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(op_full(s)); mbar_arrive(raw_empty(r0)); mbar_arrive(raw_empty(r1)); }
+      }
+    }
+    if (bad) atomicExch(&g_f16_overflow, 1);
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ MMA issuer: the WHOLE warp walks the loop with
+    // warp-uniform values (descriptors live in uniform registers), one elected lane issues the tcgen05 instructions
+    {
+      // kind::f16: c_format F32 (1 << 4), a/b_format F16 (0), K-major both
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int kit = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int mt, nt, z, kbeg, nkb;
+        tile_coords(t, mt, nt, z);
+        k_range(z, kbeg, nkb);
+        const int b = it & 1;
+        if (it >= 2) mbar_wait(acc_empty(b), ((it >> 1) - 1) & 1);  // the epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(b * 2 * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % C::kOps;
+          mbar_wait(op_full(s), (kit / C::kOps) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(op_ring + s * C::kOpBytes);
+          const uint32_t a_lo = a_hi + C::kABytes, b_hi = a_lo + C::kABytes, b_lo = b_hi + C::kBBytes;
+          // the start-address field is the low 14 bits (address >> 4): a k-step of 16 halves = 32 bytes adds 2
+          const uint64_t d_ah = make_desc(a_hi), d_al = make_desc(a_lo), d_bh = make_desc(b_hi), d_bl = make_desc(b_lo);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k16 = 0; k16 < BK16 / 16; ++k16) {
+              const uint32_t first = (kb | k16) != 0 ? 1u : 0u;
+              umma_f16(tacc + BN, d_al + 2 * k16, d_bh + 2 * k16, idesc, first);
+              umma_f16(tacc + BN, d_ah + 2 * k16, d_bl + 2 * k16, idesc, 1u);
+              umma_f16(tacc, d_ah + 2 * k16, d_bh + 2 * k16, idesc, first);
+            }
+            umma_commit(op_empty(s));
+          }
+          __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(acc_full(b));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ loader
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      constexpr uint32_t kRowBytes = BN < 128 ? BN * 128 : 128 * 128;
+      // flattened k-block stream over this CTA's tiles; A runs kLead k-blocks ahead of B (see gemm_tf32x3_tma_kernel)
+      constexpr int kLead = 1;  // A (raw boxes, released early by the splitters) runs one k-block ahead of B
+      struct Cursor { int t, kb, nkb, kbeg, m0, n0, rot; };
+      auto open_tile = [&](Cursor& c) {
+        if (c.t >= total_tiles) { c.nkb = 0; return; }
+        int mt, nt, z;
+        tile_coords(c.t, mt, nt, z);
+        k_range(z, c.kbeg, c.nkb);
+        c.m0 = mt * BM; c.n0 = nt * BN; c.kb = 0;
+        c.rot = mt % c.nkb;
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.kb >= c.nkb) { c.t += gridDim.x; open_tile(c); }
+      };
+      auto kbr = [&](const Cursor& c) { int r = c.kb + c.rot; return r >= c.nkb ? r - c.nkb : r; };
+      Cursor ca, cb;
+      ca.t = cb.t = blockIdx.x;
+      open_tile(ca); open_tile(cb);
+      int ia = 0, ib = 0;  // issued k-blocks
+      auto issue_a = [&]() {  // one k-block = two boxes
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int bi = 2 * ia + j, r = bi % C::kRaw;
+          if (bi >= C::kRaw) mbar_wait(raw_empty(r), ((bi / C::kRaw) - 1) & 1);
+          mbar_arrive_expect_tx(raw_full(r), (uint32_t)C::kBoxBytes);
+          tma_load_2d(smem_u32(raw_ring + r * C::kBoxBytes), &tmap_a, ca.kbeg + kbr(ca) * BK16 + BK * j, ca.m0, raw_full(r));
+        }
+        ++ia; advance(ca);
+      };
+      auto issue_b = [&]() {
+        const int s = ib % C::kOps;
+        if (ib >= C::kOps) mbar_wait(op_empty(s), ((ib / C::kOps) - 1) & 1);
+        mbar_arrive_expect_tx(op_full(s), 2u * kRowBytes);
+        const int kblock = (cb.kbeg / BK16) + kbr(cb);
+        const uint32_t b_hi_s = smem_u32(op_ring + s * C::kOpBytes + 2 * C::kABytes), b_lo_s = b_hi_s + C::kBBytes;
+        const int nt = cb.n0 >> 7, rin = cb.n0 & 127;
+        const unsigned char* src = p.B_packed16 + ((size_t)nt * p.packed_kblocks64 + kblock) * (2 * 16384) + (size_t)rin * 128;
+        bulk_copy_g2s(b_hi_s, src, kRowBytes, op_full(s));
+        bulk_copy_g2s(b_lo_s, src + 16384, kRowBytes, op_full(s));
+        ++ib; advance(cb);
+      };
+      for (int i = 0; i < kLead && ca.nkb > 0; ++i) issue_a();
+      while (cb.nkb > 0) {
+        issue_b();
+        if (ca.nkb > 0) issue_a();
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * BN));
+  }
+}
+
+
 // C = epilogue(sum_z partial[z]) in a fixed order; one thread per 4 consecutive columns (N % 4 == 0)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, Params p) {
   pdl_wait();
@@ -1003,6 +1342,71 @@ static int launch_persist(const Params& p, int zdim, cudaStream_t st) {
   return GR_OK;
 }
 
+// B (N, K) row-major fp32 -> per (128-row tile, 64-wide k-block): [hi 16 KB][lo 16 KB] of fp16 (B * scale), rows of 128 bytes
+// in the K-major SWIZZLE_128B order; zero padding beyond (N, K).
+__global__ void __launch_bounds__(256) pack_weight_f16x3_kernel(const float* __restrict__ W, int N, int K, float scale,
+                                                                unsigned char* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int nt = blockIdx.y, kb = blockIdx.x;
+  const int kblocks = (K + 63) / 64;
+  unsigned char* base = out + ((size_t)nt * kblocks + kb) * (2 * 16384);
+  for (int ch = threadIdx.x; ch < 128 * 8; ch += blockDim.x) {
+    const int r = ch >> 3, c = ch & 7;
+    const int gn = nt * 128 + r, gk = kb * 64 + c * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = 0.f, v1 = 0.f;
+      if (gn < N && gk + 2 * e < K) v0 = W[(size_t)gn * K + gk + 2 * e] * scale;
+      if (gn < N && gk + 2 * e + 1 < K) v1 = W[(size_t)gn * K + gk + 2 * e + 1] * scale;
+      const __half2 h = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// > 0: the fp16 persistent path cannot serve this call
+template <int BN>
+static int launch_persist16(const Params& p, int zdim, cudaStream_t st) {
+  using C = CfgPersist16<BN>;
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return 1;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.lda * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(gemm_f16x3_persist_kernel<BN>), C::kSmemBytes));
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const long long total = (long long)tiles_m * tiles_n * zdim;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(total < sms ? total : sms);
+  Params pp = p;
+  pp.alpha = p.alpha * p.inv_scale16;  // a power of two: exact
+  GR_CHECK_CUDA(launch_pdl(gemm_f16x3_persist_kernel<BN>, dim3(grid), dim3(kThreadsPersist), (size_t)C::kSmemBytes, st, tm, pp, tiles_m,
+                           tiles_n, zdim));
+  GR_CHECK_LAUNCH("gemm_f16x3_persist_kernel");
+  return GR_OK;
+}
+
+static bool use_f16() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GAUSSREG_GEMM_F16"); v = e ? atoi(e) : 0; }  // opt-in, see ops._gemm_f16
+  return v != 0;
+}
+
 static bool use_tma() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GAUSSREG_GEMM_TMA"); v = e ? atoi(e) : 1; }
@@ -1011,6 +1415,10 @@ static bool use_tma() {
 
 // one launch of the tile kernel: TMA-fed when B is pre-packed, ld.global producers otherwise
 static int launch_any(int bn, const Params& p, int zdim, cudaStream_t st) {
+  if (p.B_packed16 && use_f16() && use_tma() && p.K >= 64 && (p.k_split == 0 || p.k_split % 64 == 0)) {
+    const int rc16 = p.N <= 64 ? launch_persist16<64>(p, zdim, st) : launch_persist16<128>(p, zdim, st);
+    if (rc16 <= 0) return rc16;
+  }
   if (p.B_packed && use_tma() && p.K >= 2 * BK) {
     static int persist = -1;
     if (persist < 0) { const char* e = getenv("GAUSSREG_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }
@@ -1071,7 +1479,7 @@ static bool use_bn256() {
 int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, long long ldb, long long sB, float* C, long long ldc,
                 long long sC, int M, int N, int K, int batch, float alpha, const float* bias, const float* row_div,
                 const float* residual, long long ldr, long long sR, int act, cudaStream_t st, const float* B_packed,
-                GnStatsOut* gn) {
+                GnStatsOut* gn, const void* B_packed16, float inv_scale16) {
   if (gn) gn->nblk = 0;
   const bool aligned = (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && (sA % 4 == 0) && (sB % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
@@ -1105,7 +1513,8 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
     int best_s = splits, best_slice = slice;
     const int s_max = K / 128 < 64 ? K / 128 : 64;
     for (int sc = 1; sc <= s_max; ++sc) {
-      int sl = ((K + sc - 1) / sc + 31) / 32 * 32;
+      const int gran = (B_packed16 && tc::use_f16()) ? 64 : 32;  // whole k-blocks (the fp16 kernel's are 64 wide)
+      int sl = ((K + sc - 1) / sc + gran - 1) / gran * gran;
       if (sl > kSlice + kSlice / 2) continue;  // rule (a)
       const int se = (K + sl - 1) / sl;
       const long long waves = (tiles * se + slots - 1) / slots;
@@ -1124,6 +1533,9 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act; p.k_split = 0;
   p.B_packed = (batch == 1) ? B_packed : nullptr;
   p.packed_kblocks = (K + 31) / 32;
+  p.B_packed16 = (batch == 1) ? static_cast<const unsigned char*>(B_packed16) : nullptr;
+  p.packed_kblocks64 = (K + 63) / 64;
+  p.inv_scale16 = inv_scale16;
   p.gn_partial = nullptr; p.gn_groups = 0;
   // GroupNorm statistics ride in the epilogue when every group lies inside one column tile
   const bool gn_ok = gn && gn->partial && batch == 1 && gn->groups > 0 && N % gn->groups == 0 && N % 4 == 0 &&
@@ -1168,3 +1580,26 @@ int gemm_tf32x3(const float* A, long long lda, long long sA, const float* B, lon
 }
 
 }  // namespace gr
+
+/* fp16-split image of a static (N, K) weight for the kind::f16 tensor-core kernels: `scale` must be a power of two with
+ * scale * max|W| far below 65504 (callers pass 1 / scale to the products).  out: gr_packed_weight_f16_bytes(N, K) bytes. */
+extern "C" size_t gr_packed_weight_f16_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return (size_t)((N + 127) / 128) * ((K + 63) / 64) * (2 * 16384);
+}
+extern "C" int gr_pack_weight_f16x3(const float* W, int N, int K, float scale, void* out, void* stream) {
+  if (N <= 0 || K <= 0 || !W || !out || !(scale > 0.f)) return GR_ERR_BAD_ARG;
+  dim3 grid((K + 63) / 64, (N + 127) / 128);
+  GR_CHECK_CUDA(gr::launch_pdl(gr::tc::pack_weight_f16x3_kernel, grid, dim3(256), (size_t)0, static_cast<cudaStream_t>(stream), W, N, K, scale,
+                           static_cast<unsigned char*>(out)));
+  GR_CHECK_LAUNCH("pack_weight_f16x3_kernel");
+  return GR_OK;
+}
+/* device address of the flag the fp16 kernels raise when an activation exceeded fp16's range (|x| > 6e4) */
+extern "C" int gr_gemm_f16_overflow_ptr(int** dev_ptr) {
+  if (!dev_ptr) return GR_ERR_BAD_ARG;
+  void* q = nullptr;
+  if (cudaGetSymbolAddress(&q, gr::tc::g_f16_overflow) != cudaSuccess) return GR_ERR_CUDA;
+  *dev_ptr = static_cast<int*>(q);
+  return GR_OK;
+}

@@ -73,6 +73,14 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, row_div=None
     assert x.stride(1) == 1 and weight.shape[1] == K
     if out is None:
         out = torch.empty((M, N), dtype=_F32, device=x.device)
+    if _gemm_f16():
+        pk16, inv16 = packed_weight_f16x3(weight)
+        st = _lib.lib().gr_linear_packed16(x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
+                                           packed_weight_tf32x3(weight).data_ptr(), pk16.data_ptr(), inv16, out.data_ptr(),
+                                           out.stride(0), M, N, K, 1.0, _ptr(bias), _ptr(row_div), _ptr(residual),
+                                           residual.stride(0) if residual is not None else 0, ACT[act], _stream())
+        _lib.check(st, "linear_packed16")
+        return out
     st = _lib.lib().gr_linear_packed(x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
                                      packed_weight_tf32x3(weight).data_ptr(), out.data_ptr(), out.stride(0), M, N, K, 1.0,
                                      _ptr(bias), _ptr(row_div), _ptr(residual),
@@ -127,21 +135,60 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, bias, kernel_
 # ------------------------------------------------------------------------------------------------
 # native KPConv blocks / FPN: parameter structs for the C ABI (include/gaussreg_b200.h, csrc/backbone.cu)
 # ------------------------------------------------------------------------------------------------
+def packed_weight_f16x3(weight):
+    """(N,K) static weight -> fp16 hi/lo tiles for the kind::f16 tensor-core GEMM, pre-scaled by a power of two so that the
+    largest |w| lands in [4, 8).  Returns (buffer, 1/scale); cached on the tensor."""
+    cached = getattr(weight, "_gr_packed16g", None)
+    if cached is None or cached[0] != weight._version or cached[1].device != weight.device:
+        N, K = weight.shape
+        wmax = float(weight.detach().abs().max())
+        exp = 0 if not (wmax > 0.0 and math.isfinite(wmax)) else max(-14, min(14, math.floor(math.log2(8.0 / wmax))))
+        scale = 2.0 ** exp
+        L = _lib.lib()
+        out = torch.empty((L.gr_packed_weight_f16_bytes(N, K),), dtype=torch.uint8, device=weight.device)
+        st = L.gr_pack_weight_f16x3(weight.detach().contiguous().data_ptr(), N, K, scale, out.data_ptr(), _stream())
+        _lib.check(st, "pack_weight_f16x3")
+        cached = (weight._version, out, 1.0 / scale)
+        try:
+            weight._gr_packed16g = cached
+        except AttributeError:
+            pass
+    return cached[1], cached[2]
+
+
+def _gemm_f16():
+    """GAUSSREG_GEMM_F16=1: backbone products on the kind::f16 persistent kernel (fp16-split operands).  Off by default: it
+    passes every parity test but buys only ~5 % on the GEMM shapes of the backbone (0.04 ms per pair) -- with 64-wide
+    k-blocks the operand rings that fit in shared memory are too shallow to hide the TMA latency -- and fp16's range is a
+    constraint the TF32 path does not have."""
+    return os.environ.get("GAUSSREG_GEMM_F16", "0") == "1"
+
+
 def _fill_unary(dst, mlp, norm, leaky, keep, split_k=0):
     """gr_unary_weights from an nn.Linear (+ optional GroupNorm wrapper).  split_k > 0 (decoder blocks): also pack the
     two column slices of the weight, see gr_unary_weights.split_k."""
     w = mlp.weight
     dst.weight = w.data_ptr()
     dst.split_k, dst.weight_packed_lo, dst.weight_packed_hi = 0, None, None
+    dst.weight_packed16, dst.weight_packed16_lo, dst.weight_packed16_hi = None, None, None
+    dst.inv_scale16 = dst.inv_scale16_lo = dst.inv_scale16_hi = 1.0
     if 0 < split_k < w.shape[1] and split_k % 32 == 0 and (w.shape[1] - split_k) % 32 == 0 and os.environ.get("GAUSSREG_DECODER_SPLIT", "1") != "0":
         lo, hi = w.detach()[:, :split_k].contiguous(), w.detach()[:, split_k:].contiguous()
         plo, phi = packed_weight_tf32x3(lo), packed_weight_tf32x3(hi)
         keep.extend([lo, hi, plo, phi])
         dst.split_k, dst.weight_packed_lo, dst.weight_packed_hi = split_k, plo.data_ptr(), phi.data_ptr()
+        if _gemm_f16():
+            (qlo, ilo), (qhi, ihi) = packed_weight_f16x3(lo), packed_weight_f16x3(hi)
+            keep.extend([qlo, qhi])
+            dst.weight_packed16_lo, dst.weight_packed16_hi, dst.inv_scale16_lo, dst.inv_scale16_hi = qlo.data_ptr(), qhi.data_ptr(), ilo, ihi
     if w.is_contiguous() and w.shape[1] % 4 == 0:
         pk = packed_weight_tf32x3(w)
         keep.append(pk)
         dst.weight_packed = pk.data_ptr()
+        if _gemm_f16():
+            pk16, inv16 = packed_weight_f16x3(w)
+            keep.append(pk16)
+            dst.weight_packed16, dst.inv_scale16 = pk16.data_ptr(), inv16
     else:
         dst.weight_packed = None
     dst.bias = mlp.bias.data_ptr() if mlp.bias is not None else None
@@ -160,8 +207,14 @@ def _fill_kpconv(dst, conv, keep):
         pk = packed_weight_tf32x3(wk)
         keep += [wk, pk]
         dst.weights_kmajor, dst.weights_kmajor_packed = wk.data_ptr(), pk.data_ptr()
+        dst.weights_kmajor_packed16, dst.inv_scale16 = None, 1.0
+        if _gemm_f16():
+            pk16, inv16 = packed_weight_f16x3(wk)
+            keep.append(pk16)
+            dst.weights_kmajor_packed16, dst.inv_scale16 = pk16.data_ptr(), inv16
     else:
         dst.weights_kmajor, dst.weights_kmajor_packed = None, None
+        dst.weights_kmajor_packed16, dst.inv_scale16 = None, 1.0
     dst.bias = conv.bias.data_ptr() if conv.bias is not None else None
     dst.kernel_points = conv.kernel_points.data_ptr()
     dst.sigma, dst.in_channels, dst.out_channels = float(conv.sigma), C, Co
@@ -189,7 +242,7 @@ def invalidate_weight_caches(module):
     for m in module.modules():
         m.__dict__.pop("_gr_native", None)
     for p in list(module.parameters()) + list(module.buffers()):
-        for attr in ("_gr_packed", "_gr_packed16", "_gr_kmajor", "_gr_qkv", "_gr_t"):
+        for attr in ("_gr_packed", "_gr_packed16", "_gr_packed16g", "_gr_kmajor", "_gr_qkv", "_gr_t"):
             if hasattr(p, attr):
                 try:
                     delattr(p, attr)

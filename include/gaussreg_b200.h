@@ -123,6 +123,9 @@ int gr_gemm(const float* A, int64_t lda, int64_t strideA, const float* B, int64_
 int gr_linear_packed(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_packed, float* C, int64_t ldc,
                      int M, int N, int K, float alpha, const float* bias, const float* row_div, const float* residual,
                      int64_t ldr, int act, void* stream);
+int gr_linear_packed16(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_packed, const void* W_packed16,
+                       float inv_scale16, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
+                       const float* row_div, const float* residual, int64_t ldr, int act, void* stream);
 void gr_set_gemm_mode(int mode);
 int gr_get_gemm_mode(void);
 /* 1 if the calling thread's last gr_gemm ran on the tensor cores, 0 if on the FFMA kernel (bench bookkeeping). */
@@ -182,6 +185,12 @@ typedef struct {
   int split_k;
   const float* weight_packed_lo;
   const float* weight_packed_hi;
+  /* Optional fp16-split images (gr_pack_weight_f16x3) of weight / weight[:, :split_k] / weight[:, split_k:] and the inverses
+   * of their packing scales: with them the products run on kind::f16 (K = 16 per tensor-core dispatch instead of 8). */
+  const void* weight_packed16;
+  const void* weight_packed16_lo;
+  const void* weight_packed16_hi;
+  float inv_scale16, inv_scale16_lo, inv_scale16_hi;
 } gr_unary_weights;
 
 typedef struct {
@@ -192,6 +201,8 @@ typedef struct {
   const float* kernel_points; /* (15, 3) */
   float sigma;
   int in_channels, out_channels;
+  const void* weights_kmajor_packed16; /* gr_pack_weight_f16x3 image of weights_kmajor (may be NULL) */
+  float inv_scale16;
 } gr_kpconv_weights;
 
 typedef struct {
@@ -293,6 +304,9 @@ int gr_structure_embedding_fused(const float* d_idx, const float* a_idx, int64_t
  * gr_pack_weight_f16x2: W (N <= 256, K <= 256) fp32 -> 256 KB of fp16 hi/lo tiles; gr_structure_embedding_fused_f16:
  * same contract as gr_structure_embedding_fused, inv_scale_* = 1 / the packing scales.
  * Replaces geotransformer/modules/geotransformer/geotransformer.py:57-72. */
+size_t gr_packed_weight_f16_bytes(int N, int K);
+int gr_pack_weight_f16x3(const float* W, int N, int K, float scale, void* out, void* stream);
+int gr_gemm_f16_overflow_ptr(int** dev_ptr);
 int gr_pack_weight_f16x2(const float* W, int N, int K, float scale, void* out, void* stream);
 int gr_structure_embedding_fused_f16(const float* d_idx, const float* a_idx, int64_t rows, int angle_k, const float* div_term,
                                      int hidden_dim, const void* wd_packed, const void* wa_packed, float inv_scale_d,
