@@ -67,18 +67,8 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     main = torch.cuda.current_stream(dev)
     side = ext.side_stream(dev) if os.environ.get("GAUSSREG_PYRAMID_STREAMS", "2") != "1" else None
 
-    # --- buffers first (all on the caller's stream / allocator pool): every stage is sized by the upper bound n0
-    specs = []  # (key, query stage, support stage, radius, limit)
-    r = radius
-    for i in range(num_stages):
-        specs.append(("neighbors", i, i, r, neighbor_limits[i]))
-        if i < num_stages - 1:
-            specs.append(("subsampling", i + 1, i, r, neighbor_limits[i]))
-            specs.append(("upsampling", i, i + 1, r * 2, neighbor_limits[i + 1]))
-        r *= 2
-    tables = [torch.empty((n0, limit), dtype=torch.int64, device=dev) for (_, _, _, _, limit) in specs]
-    counts_dev = torch.zeros((len(specs),), dtype=torch.int32, device=dev)
-    grids = [ext.radius_grid_workspace(points, lengths) for _ in range(num_stages)]  # sized by the upper bound n0
+    # the searches' row-count maxima accumulate into this (zero-filled BEFORE the helper stream forks off the caller's)
+    counts_dev = torch.zeros((3 * num_stages - 2,), dtype=torch.int32, device=dev)
     if side is not None:
         # the helper stream starts where the caller's stream is NOW: inputs are ready, and every kernel that may still
         # read a recycled buffer (the previous pair's forward) has been ordered before it
@@ -100,6 +90,19 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             ready.append(ev)
     sizes_dev = torch.cat(totals + len_dev) if totals else torch.cat(len_dev)
 
+    # --- buffers (all on the caller's stream / allocator pool, every stage sized by the upper bound n0): allocated AFTER the
+    # subsampling chain has been queued, so that the GPU is already working while the host does this (0.1 ms per pair)
+    specs = []  # (key, query stage, support stage, radius, limit)
+    r = radius
+    for i in range(num_stages):
+        specs.append(("neighbors", i, i, r, neighbor_limits[i]))
+        if i < num_stages - 1:
+            specs.append(("subsampling", i + 1, i, r, neighbor_limits[i]))
+            specs.append(("upsampling", i, i + 1, r * 2, neighbor_limits[i + 1]))
+        r *= 2
+    tables = [torch.empty((n0, limit), dtype=torch.int64, device=dev) for (_, _, _, _, limit) in specs]
+    assert len(specs) == counts_dev.shape[0]
+    grids = [ext.radius_grid_workspace(points, lengths) for _ in range(num_stages)]  # sized by the upper bound n0
     # --- radius searches (limit-wide tables, widths come back later).  Stage i's support cloud is searched with radius
     # r_i by "neighbors" and "subsampling" of stage i and (r_i = 2 r_{i-1}) by "upsampling" of stage i-1: one cell grid per
     # stage serves all three (5 grids for 13 searches).
