@@ -113,6 +113,9 @@ _SIGNATURES = {
     "gr_gemm_f16_overflow_ptr": (_i32, [_vp]),
     "gr_pack_weight_f16x2": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "gr_structure_embedding_fused_f16": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "gr_structure_embedding_table_floats": (_i64, [_i32, _f32]),
+    "gr_structure_embedding_build_table": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
+    "gr_structure_embedding_tabulated": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_rpe_attention_probs_ld": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),

@@ -61,6 +61,12 @@ class GeometricStructureEmbedding(nn.Module):
         C = self.embedding.d_model
         k = self.angle_k
         d_idx, a_idx = self.get_embedding_indices(pts)
+        if self.use_fused and C % 64 == 0 and k <= 3 and ops._t1_mode() == "table":
+            # proj(sinusoid(x)) tabulated per channel: no projection in the hot path (csrc/embedding_tab.cu)
+            out = ops.structure_embedding_tabulated(d_idx, a_idx, self.embedding.div_term, self.proj_d.weight, self.proj_d.bias,
+                                                    self.proj_a.weight, self.proj_a.bias, self.sigma_a)
+            if out is not None:
+                return out.unsqueeze(0) if batched else out
         if self.use_fused and C == 256 and k <= 3 and ops._lib.lib().gr_get_gemm_mode() == 1:
             out = ops.structure_embedding_fused(d_idx, a_idx, self.embedding.div_term, self.proj_d.weight, self.proj_d.bias,
                                                 self.proj_a.weight, self.proj_a.bias)

@@ -220,8 +220,22 @@ def _fill_kpconv(dst, conv, keep):
     dst.sigma, dst.in_channels, dst.out_channels = float(conv.sigma), C, Co
 
 
+def _drop_tensor_list(module, *_):
+    module.__dict__.pop("_gr_tensors", None)
+
+
 def _module_key(module):
-    return tuple((t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
+    """(version, storage) of every parameter / buffer under `module`.  Walking the module tree costs 0.5 ms for the
+    backbone (204 tensors) -- per step, on the host's critical path -- so the flat tensor list is kept on the module;
+    load_state_dict (which may re-assign Parameters) and invalidate_weight_caches drop it."""
+    ts = module.__dict__.get("_gr_tensors")
+    if ts is None:
+        ts = list(module.parameters()) + list(module.buffers())
+        if "_gr_tensors_hooked" not in module.__dict__:
+            module.__dict__["_gr_tensors_hooked"] = True
+            module.register_load_state_dict_post_hook(_drop_tensor_list)
+        module.__dict__["_gr_tensors"] = ts
+    return tuple([(t._version, t.data_ptr()) for t in ts])
 
 
 def _cached_struct(module, build):
@@ -241,8 +255,9 @@ def invalidate_weight_caches(module):
     caches are keyed on; load_state_dict / optimizer steps are detected automatically."""
     for m in module.modules():
         m.__dict__.pop("_gr_native", None)
+        m.__dict__.pop("_gr_tensors", None)
     for p in list(module.parameters()) + list(module.buffers()):
-        for attr in ("_gr_packed", "_gr_packed16", "_gr_packed16g", "_gr_kmajor", "_gr_qkv", "_gr_t"):
+        for attr in ("_gr_packed", "_gr_packed16", "_gr_packed16g", "_gr_kmajor", "_gr_qkv", "_gr_t", "_gr_t1_table"):
             if hasattr(p, attr):
                 try:
                     delattr(p, attr)
@@ -530,6 +545,53 @@ def packed_weight_f16x2(weight):
 def _t1_f16():
     v = os.environ.get("GAUSSREG_T1_F16")
     return True if v is None else v not in ("0", "")
+
+
+def _t1_mode():
+    """GAUSSREG_T1: 'table' (default: Hermite tables, no projection in the hot path) | 'tc' (tcgen05 projections)."""
+    return os.environ.get("GAUSSREG_T1", "table")
+
+
+def embedding_table(div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b, sigma_a):
+    """Exact node tables of proj_d(sinusoid(.)) / proj_a(sinusoid(.)), cached on proj_d.weight by parameter versions."""
+    key = (proj_d_w._version, proj_d_b._version, proj_a_w._version, proj_a_b._version, proj_a_w.data_ptr(), float(sigma_a),
+           proj_d_w.device)
+    cached = getattr(proj_d_w, "_gr_t1_table", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    C = proj_d_w.shape[0]
+    n = _lib.lib().gr_structure_embedding_table_floats(C, float(sigma_a))
+    if n <= 0:
+        return None
+    tab = torch.empty((n,), dtype=_F32, device=proj_d_w.device)
+    st = _lib.lib().gr_structure_embedding_build_table(div_term.data_ptr(), C, proj_d_w.detach().contiguous().data_ptr(),
+                                                       proj_d_b.data_ptr(), proj_a_w.detach().contiguous().data_ptr(),
+                                                       proj_a_b.data_ptr(), float(sigma_a), tab.data_ptr(), _stream())
+    _lib.check(st, "structure_embedding_build_table")
+    try:
+        proj_d_w._gr_t1_table = (key, tab)
+    except AttributeError:
+        pass
+    return tab
+
+
+def structure_embedding_tabulated(d_idx, a_idx, div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b, sigma_a):
+    """geotransformer.py:57-72 as f_d(d) + max_k f_a(a_k) from Hermite tables; None when the table cannot be used."""
+    N = d_idx.shape[0]
+    k = a_idx.shape[-1]
+    C = proj_d_w.shape[0]
+    tab = embedding_table(div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b, sigma_a)
+    if tab is None:
+        return None
+    out = torch.empty((N, N, C), dtype=_F32, device=d_idx.device)
+    st = _lib.lib().gr_structure_embedding_tabulated(d_idx.data_ptr(), a_idx.data_ptr(), N * N, k, tab.data_ptr(), float(sigma_a),
+                                                     div_term.data_ptr(), C, proj_d_w.detach().contiguous().data_ptr(),
+                                                     proj_d_b.data_ptr(), proj_a_w.detach().contiguous().data_ptr(),
+                                                     proj_a_b.data_ptr(), out.data_ptr(), _stream())
+    if st == -3:  # GR_ERR_CAPACITY: this sigma_a's table does not fit one SM's shared memory
+        return None
+    _lib.check(st, "structure_embedding_tabulated")
+    return out
 
 
 def structure_embedding_fused(d_idx, a_idx, div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b):

@@ -312,6 +312,21 @@ int gr_structure_embedding_fused_f16(const float* d_idx, const float* a_idx, int
                                      int hidden_dim, const void* wd_packed, const void* wa_packed, float inv_scale_d,
                                      float inv_scale_a, const float* bias_d, const float* bias_a, float* out, void* stream);
 
+/* T1 by tabulation.  proj(sinusoid(x)) is a band-limited function of ONE scalar per channel (highest angular frequency 1),
+ * so geotransformer.py:57-72 = f_d(d) + max_k f_a(a_k) with f_d, f_a interpolated from exact fp64 node tables (cubic
+ * Hermite, step 1/8 on the angle index range [0, 180/sigma_a]; quintic Hermite, step 1/2 on the distance index range
+ * [0, 64); an index outside its table is evaluated directly from the weights).  Error vs the exact function 7e-8
+ * relative (the fp32 reference itself: 3e-7).  gr_structure_embedding_table_floats: table size (0 on bad arguments);
+ * gr_structure_embedding_build_table: once per weight set; gr_structure_embedding_tabulated: same contract as
+ * gr_structure_embedding_fused with raw (hidden_dim, hidden_dim) weights; hidden_dim % 64 == 0.
+ * Replaces geotransformer/modules/geotransformer/geotransformer.py:57-72. */
+int64_t gr_structure_embedding_table_floats(int hidden_dim, float sigma_a);
+int gr_structure_embedding_build_table(const float* div_term, int hidden_dim, const float* W_d, const float* b_d,
+                                       const float* W_a, const float* b_a, float sigma_a, float* table, void* stream);
+int gr_structure_embedding_tabulated(const float* d_idx, const float* a_idx, int64_t rows, int angle_k, const float* table,
+                                     float sigma_a, const float* div_term, int hidden_dim, const float* W_d, const float* b_d,
+                                     const float* W_a, const float* b_a, float* out, void* stream);
+
 /* T2  RPE attention probabilities with the p-term reassociated (rpe_transformer.py:50-66), row softmax
  * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */
 int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,

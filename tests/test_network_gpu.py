@@ -206,7 +206,13 @@ def test_structure_embedding_vs_oracle():
     pts = (torch.rand(311, 3, generator=g) - 0.5) * torch.tensor([4.0, 3.0, 2.5])
     want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
     emb = m.transformer.embedding.cuda()
-    got = emb(pts.cuda()).cpu()  # fused tensor-core kernel
+    got = emb(pts.cuda()).cpu()  # default: Hermite tables of proj(sinusoid(.)) (csrc/embedding_tab.cu)
+    assert rel_l2(got, want) < 2e-6 and float((got - want).abs().max()) < 2e-5
+    os.environ["GAUSSREG_T1"] = "tc"
+    try:
+        got = emb(pts.cuda()).cpu()  # fused tensor-core kernel
+    finally:
+        del os.environ["GAUSSREG_T1"]
     assert rel_l2(got, want) < 1e-5
     emb.use_fused = False
     emb.CHUNK_ROWS = 20000  # unfused path, chunked
@@ -217,6 +223,49 @@ def test_structure_embedding_vs_oracle():
     gd, ga, gk = [t.cpu() for t in ops.embedding_indices(pts.cuda(), 0.2, 15, 3)]
     assert torch.equal(gk.long(), knn)
     assert rel_l2(gd, d_idx) < 1e-6 and float((ga - a_idx).abs().max()) < 1e-4
+
+
+def test_structure_embedding_table_edges():
+    """Table path: indices beyond the distance table (direct evaluation), angle_k 1..3, the exact fp64 function."""
+    m, sd = _transformer_pair()
+    emb = m.transformer.embedding.cuda()
+    g = torch.Generator().manual_seed(5)
+    # 40 m cloud: dist / sigma_d reaches ~200, far outside the [0, 64) table
+    pts = (torch.rand(97, 3, generator=g) - 0.5) * 40.0
+    want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
+    got = emb(pts.cuda()).cpu()
+    assert rel_l2(got, want) < 5e-6
+    # angle_k = 1, 2 through the C-ABI wrapper, against the exact function in fp64
+    pts = (torch.rand(150, 3, generator=g) - 0.5) * torch.tensor([4.0, 3.0, 2.5])
+    Wd, bd = emb.proj_d.weight.detach().double().cpu(), emb.proj_d.bias.detach().double().cpu()
+    Wa, ba = emb.proj_a.weight.detach().double().cpu(), emb.proj_a.bias.detach().double().cpu()
+    div = emb.embedding.div_term.detach().double().cpu()
+
+    def exact(x, W, b):
+        om = x.double().reshape(-1, 1) * div.reshape(1, -1)
+        E = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(x.numel(), -1)
+        return E @ W.T + b
+
+    for k in (1, 2, 3):
+        d_idx, a_idx, _ = ops.embedding_indices(pts.cuda(), 0.2, 15, k)
+        got = ops.structure_embedding_tabulated(d_idx, a_idx, emb.embedding.div_term, emb.proj_d.weight, emb.proj_d.bias,
+                                                emb.proj_a.weight, emb.proj_a.bias, 15).cpu()
+        fa = exact(a_idx.cpu(), Wa, ba).reshape(150, 150, k, -1).max(dim=2)[0]
+        ex = (exact(d_idx.cpu(), Wd, bd).reshape(150, 150, -1) + fa).float()
+        assert rel_l2(got, ex) < 5e-7, k
+    # NaN coordinates propagate as they do through torch.max
+    bad = pts.clone()
+    bad[3, 1] = float("nan")
+    got = emb(bad.cuda()).cpu()
+    assert torch.isnan(got[3]).all() and torch.isnan(got[:, 3]).all()
+    # a changed weight rebuilds the table
+    with torch.no_grad():
+        emb.proj_a.bias.add_(1.0)
+    got2 = emb(pts.cuda()).cpu()
+    with torch.no_grad():
+        emb.proj_a.bias.sub_(1.0)
+    got1 = emb(pts.cuda()).cpu()
+    assert float((got2 - got1 - 1.0).abs().max()) < 1e-5
 
 
 def test_transformer_layers_vs_oracle():
