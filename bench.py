@@ -194,6 +194,8 @@ class OpProfiler:
                 work = 2.0 * a[2] * (1 + a[3]) * a[5] * a[5]
                 key = "gr_structure_embedding_fused"
                 self.t1_kind = "f16" if name.endswith("_f16") else "tf32"
+            elif name == "gr_structure_embedding_tabulated":  # (d_idx, a_idx, rows, angle_k, table, sigma_a, div, hidden, ...)
+                work = 4.0 * a[2] * (a[7] + 1 + a[3])  # HBM bytes: the (rows, hidden) embedding written, the indices read
             # algorithmic HBM bytes of the HBM-class ops (SURVEY.md section 8(d) formulas)
             elif name in ("gr_radius_neighbors", "gr_radius_neighbors_cached"):  # (q, s, ql, sl, batch, nq, ns, radius, out, ld, ...)
                 work = 12.0 * (a[5] + a[6]) + 8.0 * a[5] * a[9]
@@ -375,6 +377,7 @@ def config5_large_pair(model, dev, steps=2):
     dd = {k: d[k] for k in ("ref_points", "src_points", "ref_feats", "src_feats")}
     lib = _lib._lib
     times, t1_ms, t1_flop, n_super = [], 0.0, 0.0, None
+    tab_ms = tab_bytes = 0.0
     for it in range(steps + 1):
         prof = it == steps and isinstance(lib, OpProfiler)
         if prof:
@@ -393,6 +396,9 @@ def config5_large_pair(model, dev, steps=2):
                 if name == "gr_structure_embedding_fused":
                     t1_ms += s1.elapsed_time(e1)
                     t1_flop += w
+                elif name == "gr_structure_embedding_tabulated":
+                    tab_ms += s1.elapsed_time(e1)
+                    tab_bytes += w
         if it > 0:
             times.append(s.elapsed_time(e))
         n_super = [int(x) for x in data["lengths"][-1].tolist()]
@@ -407,7 +413,22 @@ def config5_large_pair(model, dev, steps=2):
         res["structure_embedding"] = {"ms": t1_ms, "achieved": tf, "unit": "TFLOP/s fp32-equivalent", "frac_of_bf16_sustained": tf / peaks["tf_sustained"],
                                       "mma_kind": "f16" if f16 else "tf32", "mma_tflops": 3.0 * tf,
                                       "frac_of_mma_peak": 3.0 * tf / (peaks["tf_sustained"] if f16 else peaks["tf_sustained"] / 2.0)}
+    if tab_ms > 0:
+        res["structure_embedding"] = table_kernel_entry(tab_ms, tab_bytes, 2, peaks)
     return res
+
+
+def table_kernel_entry(ms, hbm_bytes, launches, peaks):
+    """The tabulated structure embedding (csrc/embedding_tab.cu): HBM bytes = the embedding it writes + the indices; its
+    own bound is shared-memory bandwidth (18 table floats = 72 B of LDS per output float against 148 SMs x 128 B/clk)."""
+    gbs = hbm_bytes / (ms * 1e-3) / 1e9
+    out_floats = hbm_bytes / 4.0 * 256.0 / 260.0
+    lds_tbs = out_floats * 72.0 / (ms * 1e-3) / 1e12
+    return {"kernel": "structure_embedding_table_kernel<3> (Hermite tables of proj(sinusoid(.)) in shared memory, no projection GEMM)",
+            "ms": ms, "launches": launches, "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+            "bound": "shared-memory bandwidth", "lds_TBps": lds_tbs, "lds_peak_TBps_nominal": 148 * 128 * 1.965e9 / 1e12,
+            "frac_of_lds_peak": lds_tbs / (148 * 128 * 1.965e9 / 1e12),
+            "replaces": "2 N^2 (1+k) 256^2 FLOPs of tcgen05 projections (structure_embedding_f16_kernel, GAUSSREG_T1=tc)"}
 
 
 def config4_sharded(model, rank, world, dev, pairs_per_rank=128, distinct=8):
@@ -564,10 +585,15 @@ def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microben
             roofline["traffic_source"] = tj.get("source")
         roofline["traffic_other_kernels"] = {n: v["dram_bytes_per_launch"] for n, v in tj.get("kernels", {}).items()
                                              if "structure_embedding" not in n and " grid=" not in n and "<" not in n}
+    tabulated = t1_ms <= 0.0
     hbm = {}
     n_calls = {}
     for r in lib.records:
         n_calls[r[0]] = n_calls.get(r[0], 0) + 1
+    k = "gr_structure_embedding_tabulated"
+    if per_op.get(k, 0.0) > 0:
+        hbm["structure_embedding_table_kernel"] = table_kernel_entry(per_op[k], work[k], n_calls.get(k, 0), peaks)
+        hbm["structure_embedding_table_kernel"]["share_of_step"] = per_op[k] / max(sum(per_op.values()), 1e-9)
     k = "gr_radius_neighbors"
     if per_op.get(k, 0.0) > 0:
         gbs = work[k] / (per_op[k] * 1e-3) / 1e9
@@ -584,6 +610,33 @@ def build_roofline(lib, per_op, work, peaks, model, resident_pair, dev, microben
         rpe["peak"] = peaks["hbm_gbs"]
         rpe["frac"] = rpe["achieved"] / peaks["hbm_gbs"]
         hbm["rpe_scores_softmax_v2_kernel"] = rpe
+    if tabulated:
+        # T1 no longer runs on the tensor cores (its projections are tabulated): the dominant kernel class of the step is
+        # now the backbone's tcgen05 products (KPConv contractions + unary Linears inside gr_kpconv_fpn_from).  They are
+        # timed live here on the step's own shapes, one call per shape with an L2 flush (CUDA events on the launch stream).
+        g = hbm.pop("tcgen05_gemm_backbone_shapes", None)
+        if g is not None:
+            bb_ms = per_op.get("gr_kpconv_fpn_from", 0.0) + per_op.get("gr_kpconv_fpn", 0.0)
+            roofline = {
+                "kernel": "tc::gemm_tf32x3_tma_kernel / gemm_tf32x3_persist_kernel (backbone products: tensor-map TMA A operand, "
+                          "tcgen05.mma kind::tf32 3xTF32, TMEM accumulators, GroupNorm statistics in the epilogue)",
+                "bound": "tensor", "achieved": g["achieved"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": g["frac"],
+                "peak_source": peaks["source"] + " bf16 sustained (cuBLAS, MEASURED_PEAKS.json); achieved counts fp32-equivalent "
+                               "FLOPs (2 M N K): every fp32-accurate product costs 3 kind::tf32 MMAs, which issue at half the bf16 rate: "
+                               "tensor-pipe occupancy ~ 6 x frac; the N <= 64 shapes are bound by the A stream (HBM), see shapes_MNK",
+                "mma_kind": "tf32", "mma_tflops": g["tf32_mma_tflops"], "frac_of_mma_peak": g["frac_of_tf32_peak"],
+                "ms_shapes_alone": g["ms"], "shapes_MNK": g["shapes_MNK"],
+                "share_of_step": "backbone call %.3f ms of %.3f ms; tcgen05 kernels ~ 1.85 ms of it (profiles/ launch list)" % (
+                    bb_ms, sum(per_op.values())),
+                "traffic": None,
+            }
+            if os.path.exists(tpath):
+                k = tj.get("kernels", {}).get("gemm_tf32x3_tma_kernel")
+                if k:
+                    roofline["traffic"] = k["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = tj.get("source")
+                roofline["traffic_other_kernels"] = {n: v["dram_bytes_per_launch"] for n, v in tj.get("kernels", {}).items()
+                                                     if n != "gemm_tf32x3_tma_kernel" and " grid=" not in n and "<" not in n}
     roofline["other_kernel_classes"] = hbm
     return roofline
 

@@ -6,10 +6,11 @@
 // i.e. band-limited with highest angular frequency 1.  Such a function is reproduced below fp32 rounding by Hermite
 // interpolation from a small table of exact node values: the angle index lives in [0, 180/sigma_a] (= [0, 12] for
 // sigma_a = 15) and takes a cubic Hermite table with step 1/8 (99 nodes); the distance index dist/sigma_d takes a
-// quintic Hermite table with step 1/2 over [0, 64) (129 nodes; 64 = 12.8 m at sigma_d = 0.2).  Interpolation error
+// quintic Hermite table with step 1/2 over [0, 1024] (204.8 m at sigma_d = 0.2), whose first 129 nodes ([0, 64],
+// 12.8 m) sit in shared memory and the rest (6 MB, L2-resident) is read from global memory.  Interpolation error
 // h^4/384 |f''''| resp. h^6/46080 |f^(6)|: measured 7e-8 relative to the exact function, where the reference's own
 // fp32 evaluation (sin of an fp32-rounded phase, fp32 GEMM) sits at 3e-7 — the table is the more accurate of the two.
-// An index outside its table (or NaN) is evaluated directly from W (slow, exact, warp-uniform branch).
+// An index outside its table (or NaN) is evaluated directly from W (slow, exact).
 //
 // The tables are built ONCE per weight set in fp64 (gr_structure_embedding_build_table), laid out per 64-channel slice.
 // The evaluation kernel is persistent: one CTA per SM, its slice of both tables (146 KB) in shared memory, one half-warp per
@@ -23,7 +24,8 @@ namespace gr {
 constexpr int kTabSlice = 64;      // channels per CTA
 constexpr int kTabInvHA = 8;       // 1 / step of the angle table
 constexpr int kTabInvHD = 2;       // 1 / step of the distance table
-constexpr int kTabND = 64 * kTabInvHD + 1;
+constexpr int kTabND = 64 * kTabInvHD + 1;     // distance nodes held in shared memory: [0, 64]
+constexpr int kTabNDG = 1024 * kTabInvHD + 1;  // distance nodes of the full table in global memory: [0, 1024]
 constexpr int kTabThreads = 1024;
 
 // nodes of the angle table: indices reach fl(pi_f32 * factor_a) (atan2f <= float(pi)); node n+1 must exist
@@ -32,7 +34,10 @@ static inline int tab_nodes_a(float sigma_a) {
   const float amax = 3.14159274101257324f * factor_a;
   return (int)(amax * (float)kTabInvHA) + 3;
 }
-__host__ __device__ static inline size_t tab_rows(int nA) { return (size_t)nA * 2 + (size_t)kTabND * 3; }
+// rows (of 64 channels) per slice: angle nodes (f, h f'), then distance nodes (f, h f', h^2 f''); the first
+// tab_rows_smem rows are the image every CTA copies into shared memory
+__host__ __device__ static inline size_t tab_rows(int nA) { return (size_t)nA * 2 + (size_t)kTabNDG * 3; }
+__host__ __device__ static inline size_t tab_rows_smem(int nA) { return (size_t)nA * 2 + (size_t)kTabND * 3; }
 
 // one thread per (table row group, channel): exact node values in fp64
 __global__ void __launch_bounds__(128) embedding_table_build_kernel(const float* __restrict__ div, int C, const float* __restrict__ Wd,
@@ -119,8 +124,7 @@ __device__ __forceinline__ float4 hermite3(const float* __restrict__ sA, int n, 
 }
 
 // quintic Hermite, node rows (f, h f', h^2 f'')
-__device__ __forceinline__ float4 hermite5(const float* __restrict__ sD, int n, float t) {
-  const float* p = sD + (size_t)n * (3 * kTabSlice);
+__device__ __forceinline__ float4 hermite5(const float* __restrict__ p, float t) {
   const float t2 = t * t, t3 = t2 * t;
   // H3 = t^3 (10 - 15 t + 6 t^2); H1 = t - t^3 (6 - 8 t + 3 t^2); H2 = t^2/2 - t^3 (3 - 3 t + t^2)/2
   // H4 = -t^3 (4 - 7 t + 3 t^2);  H5 = t^3 (1 - 2 t + t^2)/2
@@ -152,10 +156,11 @@ __global__ void __launch_bounds__(kTabThreads, 1) structure_embedding_table_kern
   const int slices = C / kTabSlice;
   const int slice = blockIdx.x % slices;
   const int cta = blockIdx.x / slices, ncta = gridDim.x / slices;
-  const int trows = nA * 2 + kTabND * 3;
+  const int trows = (int)tab_rows_smem(nA);
+  const float* gD = tab + ((size_t)slice * tab_rows(nA) + (size_t)nA * 2) * kTabSlice + 4 * (threadIdx.x & 15);
   {
     // the table is static data, complete long before this launch (build + fence kernel): safe ahead of pdl_wait
-    const float4* src = reinterpret_cast<const float4*>(tab + (size_t)slice * trows * kTabSlice);
+    const float4* src = reinterpret_cast<const float4*>(tab + (size_t)slice * tab_rows(nA) * kTabSlice);
     float4* dst = reinterpret_cast<float4*>(sm);
     const int n4 = trows * kTabSlice / 4;
     for (int i = threadIdx.x; i < n4; i += kTabThreads) dst[i] = __ldg(src + i);
@@ -194,7 +199,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) structure_embedding_table_kern
       const float u = x * (float)kTabInvHD;
       const int n = (int)u;
       float4 acc;
-      if (x >= 0.f && n < kTabND - 1) acc = hermite5(sD, n, u - (float)n);
+      if (x >= 0.f && n < kTabND - 1) acc = hermite5(sD + (size_t)n * (3 * kTabSlice), u - (float)n);
+      else if (x >= 0.f && n < kTabNDG - 1) acc = hermite5(gD + (size_t)n * (3 * kTabSlice), u - (float)n);  // L2-resident
       else acc = embedding_direct(x, Wd, bd, div, C, c0);
       float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -230,7 +236,7 @@ extern "C" int gr_structure_embedding_build_table(const float* div_term, int hid
   if (!div_term || !W_d || !b_d || !W_a || !b_a || !table) return GR_ERR_BAD_ARG;
   const int nA = tab_nodes_a(sigma_a);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GR_CHECK_CUDA(launch_pdl(embedding_table_build_kernel, dim3(nA + kTabND), dim3(128), (size_t)0, st, div_term, hidden_dim, W_d, b_d,
+  GR_CHECK_CUDA(launch_pdl(embedding_table_build_kernel, dim3(nA + kTabNDG), dim3(128), (size_t)0, st, div_term, hidden_dim, W_d, b_d,
                            W_a, b_a, nA, table));
   GR_CHECK_LAUNCH("embedding_table_build_kernel");
   GR_CHECK_CUDA(launch_pdl(embedding_table_fence_kernel, dim3(1), dim3(32), (size_t)0, st));
@@ -250,7 +256,7 @@ extern "C" int gr_structure_embedding_tabulated(const float* d_idx, const float*
   if (rows == 0) return GR_OK;
   if (!d_idx || !a_idx || !table || !div_term || !W_d || !b_d || !W_a || !b_a || !out) return GR_ERR_BAD_ARG;
   const int nA = tab_nodes_a(sigma_a);
-  const size_t smem = tab_rows(nA) * kTabSlice * sizeof(float);
+  const size_t smem = tab_rows_smem(nA) * kTabSlice * sizeof(float);
   if (smem > 227 * 1024) return GR_ERR_CAPACITY;
   int dev = 0, sms = 0;
   GR_CHECK_CUDA(cudaGetDevice(&dev));

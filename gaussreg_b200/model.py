@@ -67,11 +67,6 @@ class GeoTransformer(nn.Module):
         out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
         out["ref_points"], out["src_points"] = points[:ref_length], points[ref_length:]
 
-        # 1. point-to-node partition (model.py:99-109)
-        K = self.num_points_in_patch
-        _, ref_node_masks, ref_node_knn_indices, ref_node_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, K)
-        _, src_node_masks, src_node_knn_indices, src_node_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, K)
-
         # 3a. geometric structure embedding (geotransformer.py:57-72) depends on the superpoint coordinates only: it is
         # queued BEFORE the backbone, so that the GPU is busy while the host reads the neighbour-table widths
         # (data.LazyTables) and prepares the backbone call
@@ -81,6 +76,14 @@ class GeoTransformer(nn.Module):
         # 2. KPConv FPN (model.py:129-132)
         feats_list = self.backbone(feats, data_dict)
         feats_c, feats_f = feats_list[-1], feats_list[0]
+
+        # 1. point-to-node partition (model.py:99-109).  Its results are first needed by the superpoint matching, so it is
+        # issued AFTER the backbone: between the stage sizes and the backbone call the host is the bottleneck (the GPU
+        # finishes the embedding before the host has trimmed the tables and prepared the call), and every wrapper call
+        # issued there delays the backbone by its host time
+        K = self.num_points_in_patch
+        _, ref_node_masks, ref_node_knn_indices, ref_node_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, K)
+        _, src_node_masks, src_node_knn_indices, src_node_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, K)
 
         # 3b. geometric transformer (model.py:135-147)
         ref_feats_c, src_feats_c = self.transformer(ref_points_c, src_points_c, feats_c[:ref_length_c], feats_c[ref_length_c:],

@@ -315,7 +315,8 @@ int gr_structure_embedding_fused_f16(const float* d_idx, const float* a_idx, int
 /* T1 by tabulation.  proj(sinusoid(x)) is a band-limited function of ONE scalar per channel (highest angular frequency 1),
  * so geotransformer.py:57-72 = f_d(d) + max_k f_a(a_k) with f_d, f_a interpolated from exact fp64 node tables (cubic
  * Hermite, step 1/8 on the angle index range [0, 180/sigma_a]; quintic Hermite, step 1/2 on the distance index range
- * [0, 64); an index outside its table is evaluated directly from the weights).  Error vs the exact function 7e-8
+ * [0, 1024]: the first 129 nodes in shared memory, the rest read from L2; an index outside its table is evaluated
+ * directly from the weights).  Error vs the exact function 7e-8
  * relative (the fp32 reference itself: 3e-7).  gr_structure_embedding_table_floats: table size (0 on bad arguments);
  * gr_structure_embedding_build_table: once per weight set; gr_structure_embedding_tabulated: same contract as
  * gr_structure_embedding_fused with raw (hidden_dim, hidden_dim) weights; hidden_dim % 64 == 0.

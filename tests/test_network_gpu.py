@@ -230,11 +230,14 @@ def test_structure_embedding_table_edges():
     m, sd = _transformer_pair()
     emb = m.transformer.embedding.cuda()
     g = torch.Generator().manual_seed(5)
-    # 40 m cloud: dist / sigma_d reaches ~200, far outside the [0, 64) table
-    pts = (torch.rand(97, 3, generator=g) - 0.5) * 40.0
-    want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
-    got = emb(pts.cuda()).cpu()
-    assert rel_l2(got, want) < 5e-6
+    # 40 m cloud: dist / sigma_d reaches ~300, beyond the shared-memory nodes ([0, 64]) -> global-memory tier of the table;
+    # 400 m cloud: beyond the table ([0, 1024]) -> direct evaluation.  The oracle's own fp32 phase x * w carries an error
+    # of x * 2^-24, which is what the tolerance follows
+    for extent, tol in ((40.0, 5e-6), (400.0, 5e-5)):
+        pts = (torch.rand(97, 3, generator=g) - 0.5) * extent
+        want = onet.structure_embedding(sd, pts, 0.2, 15, 3)
+        got = emb(pts.cuda()).cpu()
+        assert rel_l2(got, want) < tol, extent
     # angle_k = 1, 2 through the C-ABI wrapper, against the exact function in fp64
     pts = (torch.rand(150, 3, generator=g) - 0.5) * torch.tensor([4.0, 3.0, 2.5])
     Wd, bd = emb.proj_d.weight.detach().double().cpu(), emb.proj_d.bias.detach().double().cpu()
