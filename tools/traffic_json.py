@@ -18,6 +18,11 @@ want = {
     "tensor_pipe_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "tensor_pipe_pct_alt": "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
     "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lds_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+    "lds_bank_conflicts": "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+    "lds_pipe_pct": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex_lsu_pct": "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "regs": "launch__registers_per_thread",
     "smem_dyn": "launch__shared_mem_per_block_dynamic",
     "grid": "launch__grid_size",
