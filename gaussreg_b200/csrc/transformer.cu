@@ -292,25 +292,32 @@ extern "C" int gr_conditional_transformer(const gr_layer_weights* layers, int n_
   carve_tf(ws, ws_bytes, N0 > N1 ? N0 : N1, N0 + N1, C, num_heads, &w, &ok);
   if (!ws || !ok) return GR_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* x0 = w.x;
-  float* x1 = w.x + (size_t)N0 * C;
-  GR_CHECK_CUDA(cudaMemcpyAsync(x0, feats0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  GR_CHECK_CUDA(cudaMemcpyAsync(x1, feats1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // feats1 directly behind feats0: the caller's buffer IS the stacked matrix, no staging copies
+  const bool in_place = feats1 == feats0 + (size_t)N0 * C;
+  float* X = in_place ? feats0 : w.x;
+  float* x0 = X;
+  float* x1 = X + (size_t)N0 * C;
+  if (!in_place) {
+    GR_CHECK_CUDA(cudaMemcpyAsync(x0, feats0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GR_CHECK_CUDA(cudaMemcpyAsync(x1, feats1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   for (int i = 0; i < n_layers; ++i) {
     const gr_layer_weights& L = layers[i];
     if (L.is_self) {
       if (!emb0 || !emb1 || !L.wp || !L.bp) return GR_ERR_BAD_ARG;
-      GR_TRY(self_layer(L, w.x, N0, N1, emb0, emb1, C, num_heads, w, stream));
+      GR_TRY(self_layer(L, X, N0, N1, emb0, emb1, C, num_heads, w, stream));
     } else {
       if (tf_fused() && C == 256 && num_heads == 4 && L.wqkv && L.bqkv && cross_attention_fits(N0 > N1 ? N0 : N1)) {
-        GR_TRY(cross_pair(L, w.x, N0, N1, C, w, stream));
+        GR_TRY(cross_pair(L, X, N0, N1, C, w, stream));
       } else {
         GR_TRY(cross_layer(L, x0, N0, x1, N1, C, num_heads, w, stream));
         GR_TRY(cross_layer(L, x1, N1, x0, N0, C, num_heads, w, stream));
       }
     }
   }
-  GR_CHECK_CUDA(cudaMemcpyAsync(feats0, x0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  GR_CHECK_CUDA(cudaMemcpyAsync(feats1, x1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (!in_place) {
+    GR_CHECK_CUDA(cudaMemcpyAsync(feats0, x0, (size_t)N0 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GR_CHECK_CUDA(cudaMemcpyAsync(feats1, x1, (size_t)N1 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return GR_OK;
 }

@@ -89,8 +89,13 @@ class GeoTransformer(nn.Module):
         ref_feats_c, src_feats_c = self.transformer(ref_points_c, src_points_c, feats_c[:ref_length_c], feats_c[ref_length_c:],
                                                     embeddings=(ref_emb, src_emb))
         del ref_emb, src_emb
-        ref_feats_c_norm = ops.l2_normalize_rows(ref_feats_c)
-        src_feats_c_norm = ops.l2_normalize_rows(src_feats_c)
+        both = ops.stacked_rows(ref_feats_c, src_feats_c)
+        if both is not None:
+            both = ops.l2_normalize_rows(both)
+            ref_feats_c_norm, src_feats_c_norm = both[:ref_feats_c.shape[0]], both[ref_feats_c.shape[0]:]
+        else:
+            ref_feats_c_norm = ops.l2_normalize_rows(ref_feats_c)
+            src_feats_c_norm = ops.l2_normalize_rows(src_feats_c)
         out["ref_feats_c"], out["src_feats_c"] = ref_feats_c_norm, src_feats_c_norm
         ref_feats_f, src_feats_f = feats_f[:ref_length_f], feats_f[ref_length_f:]
         out["ref_feats_f"], out["src_feats_f"] = ref_feats_f, src_feats_f

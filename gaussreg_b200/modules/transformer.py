@@ -312,11 +312,22 @@ class GeometricTransformer(nn.Module):
         else:
             ref_emb = self.embedding(rp)
             src_emb = self.embedding(sp)
-        rf = ops.linear(rf, self.in_proj.weight, self.in_proj.bias)
-        sf = ops.linear(sf, self.in_proj.weight, self.in_proj.bias)
+        n0 = rf.shape[0]
+        both = ops.stacked_rows(rf, sf)  # the model passes row slices of one (N0+N1, C) matrix: project them in one product
+        if both is not None:
+            both = ops.linear(both, self.in_proj.weight, self.in_proj.bias)
+            rf, sf = both[:n0], both[n0:]
+        else:
+            rf = ops.linear(rf, self.in_proj.weight, self.in_proj.bias)
+            sf = ops.linear(sf, self.in_proj.weight, self.in_proj.bias)
         rf, sf = self.transformer(rf, sf, ref_emb, src_emb, masks0=ref_masks, masks1=src_masks)
-        rf = ops.linear(rf, self.out_proj.weight, self.out_proj.bias)
-        sf = ops.linear(sf, self.out_proj.weight, self.out_proj.bias)
+        both = ops.stacked_rows(rf, sf)
+        if both is not None:
+            both = ops.linear(both, self.out_proj.weight, self.out_proj.bias)
+            rf, sf = both[:n0], both[n0:]
+        else:
+            rf = ops.linear(rf, self.out_proj.weight, self.out_proj.bias)
+            sf = ops.linear(sf, self.out_proj.weight, self.out_proj.bias)
         if batched:
             rf, sf = rf.unsqueeze(0), sf.unsqueeze(0)
         return rf, sf

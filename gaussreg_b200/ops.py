@@ -769,6 +769,17 @@ def _transposed(weight):
     return cached[1]
 
 
+def stacked_rows(a, b):
+    """The (Na+Nb, ...) tensor whose row blocks `a` and `b` are, if they are adjacent contiguous views of one storage
+    (e.g. x[:n] and x[n:]); else None.  Row-wise ops then run once on both clouds."""
+    if (a.dim() >= 1 and a.dim() == b.dim() and a.shape[1:] == b.shape[1:] and a.dtype == b.dtype and a.is_contiguous()
+            and b.is_contiguous() and a.numel() > 0 and b.numel() > 0
+            and a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+            and a.data_ptr() + a.numel() * a.element_size() == b.data_ptr()):
+        return torch.as_strided(a, (a.shape[0] + b.shape[0],) + tuple(a.shape[1:]), a.stride())
+    return None
+
+
 def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, num_heads):
     """RPEConditionalTransformer.forward in one C-ABI call; feats are updated in place and returned."""
     import ctypes
@@ -798,7 +809,12 @@ def conditional_transformer(layer_modules, blocks, feats0, feats1, emb0, emb1, n
         w1t, w2t = _transposed(o.expand.weight), _transposed(o.squeeze.weight)
         keep.append((w1t, w2t))
         w.w1t, w.w2t = w1t.data_ptr(), w2t.data_ptr()
-    f0, f1 = _req(feats0).clone(), _req(feats1).clone()
+    both = stacked_rows(feats0, feats1) if feats0.dtype == _F32 and feats0.is_cuda else None
+    if both is not None:  # one copy; the library then works in place on the stacked rows (no staging copies either)
+        both = both.clone()
+        f0, f1 = both[:feats0.shape[0]], both[feats0.shape[0]:]
+    else:
+        f0, f1 = _req(feats0).clone(), _req(feats1).clone()
     N0, C = f0.shape
     N1 = f1.shape[0]
     L = _lib.lib()
@@ -842,6 +858,6 @@ def _device_guarded(fn):
 
 for _name, _obj in list(globals().items()):
     if callable(_obj) and getattr(_obj, "__module__", None) == __name__ and not _name.startswith("_") and \
-            _name not in ("invalidate_weight_caches",):
+            _name not in ("invalidate_weight_caches", "stacked_rows"):
         globals()[_name] = _device_guarded(_obj)
 del _name, _obj

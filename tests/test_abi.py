@@ -32,3 +32,31 @@ def test_workspace_queries_and_version():
     assert L.gr_grid_subsample_workspace_size(60000, 2) > 60000 * 12
     assert L.gr_radius_neighbors_workspace_size(60000, 60000, 2) > 60000 * 16
     assert L.gr_launch_count() == 0
+    # T1 table size query (no device work): angle nodes for sigma_a = 15 are [0, 12] at step 1/8 (+ guard), distance nodes
+    # [0, 1024] at step 1/2, (f, h f') resp. (f, h f', h^2 f'') rows of hidden_dim channels
+    n = L.gr_structure_embedding_table_floats(256, 15.0)
+    assert n == (99 * 2 + 2049 * 3) * 256
+    assert L.gr_structure_embedding_table_floats(250, 15.0) == 0 and L.gr_structure_embedding_table_floats(256, 0.0) == 0
+
+
+def test_module_key_cache_follows_parameter_changes():
+    """Host logic: the native parameter structs are keyed on (version, storage) of a CACHED flat tensor list (walking the
+    module tree costs 0.5 ms per call); the list must be dropped whenever Parameters can have been replaced."""
+    import torch
+    import torch.nn as nn
+
+    from gaussreg_b200 import ops
+    m = nn.Sequential(nn.Linear(4, 4), nn.GroupNorm(2, 4))
+    k0 = ops._module_key(m)
+    assert ops._module_key(m) == k0 and len(k0) == 4
+    with torch.no_grad():
+        m[0].weight.add_(1.0)  # in-place edit: version counter
+    k1 = ops._module_key(m)
+    assert k1 != k0
+    sd = {k: v.clone() + 1 for k, v in m.state_dict().items()}
+    m.load_state_dict(sd, assign=True)  # replaces the Parameter objects: the post-hook drops the cached list
+    k2 = ops._module_key(m)
+    assert k2 != k1 and all(p.data_ptr() in [d for _, d in k2] for p in m.parameters())
+    m[0].weight = nn.Parameter(torch.zeros(4, 4))  # manual surgery needs the documented invalidation
+    ops.invalidate_weight_caches(m)
+    assert m[0].weight.data_ptr() in [d for _, d in ops._module_key(m)]

@@ -256,6 +256,14 @@ def test_structure_embedding_table_edges():
         fa = exact(a_idx.cpu(), Wa, ba).reshape(150, 150, k, -1).max(dim=2)[0]
         ex = (exact(d_idx.cpu(), Wd, bd).reshape(150, 150, -1) + fa).float()
         assert rel_l2(got, ex) < 5e-7, k
+    # other angle bandwidths: sigma_a = 7.5 doubles the angle table (still in shared memory), sigma_a = 3 does not fit one
+    # SM's shared memory -> GR_ERR_CAPACITY -> the module falls back to the tensor-core kernel
+    for sigma_a in (7.5, 3.0):
+        emb.sigma_a, emb.factor_a = sigma_a, 180.0 / (sigma_a * np.pi)
+        want = onet.structure_embedding(sd, pts, 0.2, sigma_a, 3)
+        got = emb(pts.cuda()).cpu()
+        assert rel_l2(got, want) < 1e-5, sigma_a
+    emb.sigma_a, emb.factor_a = 15, 180.0 / (15 * np.pi)
     # NaN coordinates propagate as they do through torch.max
     bad = pts.clone()
     bad[3, 1] = float("nan")
