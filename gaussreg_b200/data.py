@@ -215,10 +215,27 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
                 value = torch.from_numpy(value)
             collated.setdefault(key, []).append(value)
     dev = ext._device()
-    feats = torch.cat(collated.pop("ref_feats") + collated.pop("src_feats"), dim=0).to(dev, non_blocking=True)
+    feat_list = collated.pop("ref_feats") + collated.pop("src_feats")
     points_list = collated.pop("ref_points") + collated.pop("src_points")
     lengths = torch.LongTensor([p.shape[0] for p in points_list])
-    points = torch.cat(points_list, dim=0)
+    main = torch.cuda.current_stream(dev)
+    feats_ready = None
+    if precompute_data and (early is None or batch_size != 1) and not any(t.is_cuda for t in feat_list):
+        # the points go first (the pyramid starts from them); the features are first read by the backbone, so their upload
+        # runs on a copy stream underneath the subsampling chain.  The copy stream starts where the caller's stream is NOW
+        # (a recycled buffer's previous readers are ordered before it).
+        cs = ext.copy_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)
+        with torch.cuda.stream(cs):
+            feats = ext.h2d_rows(feat_list, dev)
+            feats_ready = torch.cuda.Event()
+            feats_ready.record(cs)
+        feats.record_stream(main)
+    else:
+        feats = ext.h2d_rows(feat_list, dev)
+    points = ext.h2d_rows(points_list, dev)
     if batch_size == 1:
         for key, value in collated.items():
             collated[key] = value[0]
@@ -226,8 +243,10 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
     if precompute_data:
         collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits,
                                                    early=early if batch_size == 1 else None, features=feats))
+        if feats_ready is not None:
+            main.wait_event(feats_ready)  # long complete: the host has just waited for the subsampling chain
     else:
-        collated["points"] = points.to(dev)
+        collated["points"] = points
         collated["lengths"] = lengths.to(dev)
     collated["batch_size"] = batch_size
     return collated

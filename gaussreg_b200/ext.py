@@ -118,6 +118,32 @@ def side_stream(dev):
     return s
 
 
+_copy_streams = {}
+
+
+def copy_stream(dev):
+    """A host->device copy stream per (device, current stream): inputs that are first needed late in the step (the
+    network's input features) are uploaded there, next to the kernels of the neighbour pyramid."""
+    key = (dev.index, _stream())
+    s = _copy_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _copy_streams[key] = s
+    return s
+
+
+def h2d_rows(tensors, dev, dtype=torch.float32):
+    """torch.cat(tensors).to(dev) without the pageable intermediate: every piece is copied from where it lies (pinned
+    memory: an asynchronous DMA) into its rows of one device buffer on the current stream."""
+    n = sum(int(t.shape[0]) for t in tensors)
+    out = torch.empty((n,) + tuple(tensors[0].shape[1:]), dtype=dtype, device=dev)
+    o = 0
+    for t in tensors:
+        out[o:o + t.shape[0]].copy_(t, non_blocking=True)
+        o += int(t.shape[0])
+    return out
+
+
 def radius_neighbors_device(q_points, s_points, q_lengths, s_lengths, radius, ld, out=None, grid_ws=None, reuse_grid=False,
                             max_count=None):
     """Sync-free core: fills a (Nq, ld) int64 table (first min(count, ld) sorted neighbours per row,
