@@ -182,16 +182,27 @@ __device__ __forceinline__ float ref_sqdist(float qx, float qy, float qz, float 
 }
 
 // One warp per query row.
+constexpr int kInlineBatch = 64;  // clouds per call up to which the search kernel derives the query offsets itself
+
 __global__ void __launch_bounds__(kSearchWarps * 32) radius_search_kernel(
     const float* __restrict__ q, const float4* __restrict__ sorted, const uint32_t* __restrict__ cell_start,
-    const CellGrid* __restrict__ grids, const int* __restrict__ q_off, const int* __restrict__ s_off, int batch, float r2,
-    long long* __restrict__ out, long long ld, int* __restrict__ max_count) {
+    const CellGrid* __restrict__ grids, const int* __restrict__ q_off_in, const int* __restrict__ s_off, int batch, float r2,
+    long long* __restrict__ out, long long ld, int* __restrict__ max_count, const long long* __restrict__ q_len) {
   pdl_wait();
   pdl_trigger();
   __shared__ unsigned long long sh_hits[kSearchWarps][kHitCap];
   __shared__ int sh_max;
-  if (threadIdx.x == 0) sh_max = 0;
+  __shared__ int sh_qoff[kInlineBatch + 1];
+  if (threadIdx.x == 0) {
+    sh_max = 0;
+    if (q_len != nullptr) {  // query offsets straight from the lengths (batch <= kInlineBatch): no one-CTA prep launch
+      long long acc = 0;
+      sh_qoff[0] = 0;
+      for (int b = 0; b < batch; ++b) { acc += q_len[b]; sh_qoff[b + 1] = (int)acc; }
+    }
+  }
   __syncthreads();
+  const int* q_off = q_len != nullptr ? sh_qoff : q_off_in;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kSearchWarps + warp;
@@ -560,6 +571,60 @@ __device__ void block_suffix_scan(unsigned int* w, unsigned int n, unsigned int*
   }
 }
 
+// The same exclusive SUFFIX sum by ALL CTAs of the cluster (global-memory phases: n reaches tens of thousands, and one
+// CTA walking 20+ dependent L2 round trips per thread was a quarter of the phase).  Every thread takes one contiguous
+// chunk; per-CTA totals cross the cluster through distributed shared memory.  Integer sums: any order gives the same
+// result.  Ends with the CTA totals consumed; the caller's cluster barrier orders the writes to w.
+__device__ void cluster_suffix_scan(unsigned int* w, unsigned int n, unsigned int* sh, unsigned int* sh_tot, unsigned int crank,
+                                    unsigned int ncta) {
+  const unsigned int T = blockDim.x;
+  const unsigned int GT = ncta * T;
+  const unsigned int chunk = (n + GT - 1) / GT;
+  const unsigned int g = crank * T + threadIdx.x;
+  const unsigned int lo = min(n, g * chunk), hi = min(n, lo + chunk);
+  unsigned int s = 0;
+  for (unsigned int i = lo; i < hi; ++i) s += ld_cg(&w[i]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
+  unsigned int x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int y = __shfl_down_sync(0xffffffffu, x, o);
+    if (lane + o < 32) x += y;
+  }
+  if (lane == 0) sh[warp] = x;  // warp total
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int t = lane < nwarp ? sh[lane] : 0u;
+    unsigned int u = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int y = __shfl_down_sync(0xffffffffu, u, o);
+      if (lane + o < 32) u += y;
+    }
+    sh[lane] = u - t;  // sum of warps strictly after this one
+    if (lane == 0) *sh_tot = u;  // CTA total
+  }
+  // cluster barrier: totals visible to the peers (it is a CTA barrier as well)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  unsigned int after = 0;
+  {
+    const unsigned int local = (unsigned int)__cvta_generic_to_shared(sh_tot);
+    for (unsigned int r = crank + 1; r < ncta; ++r) {
+      unsigned int remote, v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+      after += v;
+    }
+  }
+  unsigned int run = after + sh[warp] + (x - s);  // sum of everything after this thread's chunk
+  for (unsigned int i = hi; i > lo; --i) {
+    const unsigned int v = ld_cg(&w[i - 1]);
+    w[i - 1] = run;
+    run += v;
+  }
+}
+
 // One phase of the replay over arrays that live either in the shared memory of the cluster's CTA 0 (CL_ACTIVE = 1:
 // only that CTA works, barriers are __syncthreads) or in global memory (all CL CTAs of the cluster work, barriers are
 // cluster barriers).  `bkc` caches each position's bucket so the 64-bit modulo runs once per phase.
@@ -578,7 +643,7 @@ __device__ __forceinline__ void replay_phase(const unsigned long long* __restric
                                              unsigned int n_prev, const unsigned int* lin, unsigned int* lout, unsigned int* ft,
                                              unsigned int* cn, unsigned int* fill, unsigned int* w, unsigned int* tmp,
                                              unsigned int* bkc, unsigned int* sh_scan, unsigned int gtid, unsigned int GT,
-                                             bool scan_cta) {
+                                             bool scan_cta, unsigned int* sh_tot = nullptr) {
   for (unsigned int k = gtid; k < nb; k += GT) { ft[k] = kNoTouch; cn[k] = 0u; fill[k] = 0u; }
   replay_barrier<CLUSTER>();
   for (unsigned int s = gtid; s < n; s += GT) {
@@ -594,7 +659,8 @@ __device__ __forceinline__ void replay_phase(const unsigned long long* __restric
     w[s] = (ld_cg(&ft[bk]) == s) ? ld_cg(&cn[bk]) : 0u;
   }
   replay_barrier<CLUSTER>();
-  if (scan_cta) block_suffix_scan(w, n, sh_scan);
+  if (CLUSTER && sh_tot != nullptr) cluster_suffix_scan(w, n, sh_scan, sh_tot, gtid / blockDim.x, GT / blockDim.x);
+  else if (scan_cta) block_suffix_scan(w, n, sh_scan);
   replay_barrier<CLUSTER>();
   for (unsigned int s = gtid; s < n; s += GT) {
     const unsigned int bk = ld_cg(&bkc[s]);
@@ -628,11 +694,13 @@ template <int CL>
 __global__ void __launch_bounds__(kReplayThreads, 1) hash_order_replay_kernel(
     const int* __restrict__ off, int batch, const uint32_t* __restrict__ fscan, const unsigned long long* __restrict__ vkey,
     const float* __restrict__ bary, unsigned int* g_list0, unsigned int* g_list1, unsigned int* g_w, unsigned int* g_tmp,
-    unsigned int* g_bkc, unsigned int* g_ft, unsigned int* g_cn, unsigned int* g_fill, float* __restrict__ out_points) {
+    unsigned int* g_bkc, unsigned int* g_ft, unsigned int* g_cn, unsigned int* g_fill, float* __restrict__ out_points,
+    int cluster_scan) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ unsigned int smem[];
   __shared__ unsigned int sh_scan[33];
+  __shared__ unsigned int sh_tot;  // this CTA's total in the cluster-wide scan (read by the peers through DSMEM)
   const int b = blockIdx.x / CL;
   const unsigned int crank = blockIdx.x % CL;  // cluster dims (CL,1,1): rank inside the cluster
   const unsigned int vbase = fscan[off[b]];
@@ -679,7 +747,7 @@ __global__ void __launch_bounds__(kReplayThreads, 1) hash_order_replay_kernel(
       const unsigned int n = min(D, nb);
       unsigned int* lout = (lin == l0) ? l1 : l0;
       replay_phase<(CL > 1)>(key, nb, n, n_prev, lin, lout, g_ft + tbase, g_cn + tbase, g_fill + tbase, g_w + ebase,
-                             g_tmp + ebase, g_bkc + ebase, sh_scan, gtid, GT, crank == 0);
+                             g_tmp + ebase, g_bkc + ebase, sh_scan, gtid, GT, crank == 0, cluster_scan ? &sh_tot : nullptr);
       lin = lout;
       n_prev = n;
       if (n == D) break;
@@ -720,6 +788,7 @@ struct G1Workspace {
   int* scalars;
   size_t tab_slots;
   size_t tbl_elems;
+  size_t zero_bytes;  // span tab_cnt .. end of vfill (cleared by one memset)
   size_t bytes;
 };
 
@@ -733,13 +802,15 @@ static G1Workspace carve_g1(void* ws, size_t ws_bytes, int64_t n, int batch, boo
   w.geom = c.take<VoxelGeom>(batch);
   w.tab_key = c.take<unsigned long long>(w.tab_slots);
   w.tab_first = c.take<int>(w.tab_slots);
+  // tab_cnt | vcnt | vfill are carved back to back: one memset clears all three (zero_bytes)
   w.tab_cnt = c.take<uint32_t>(w.tab_slots);
+  w.vcnt = c.take<uint32_t>(n + 2);
+  w.vfill = c.take<uint32_t>(n + 1);
+  w.zero_bytes = (size_t)(reinterpret_cast<char*>(w.vfill + (n + 1)) - reinterpret_cast<char*>(w.tab_cnt));
   w.tab_vid = c.take<int>(w.tab_slots);
   w.slot_of = c.take<int>(n + 1);
   w.fscan = c.take<uint32_t>(n + 2);
   w.vkey = c.take<unsigned long long>(n + 1);
-  w.vcnt = c.take<uint32_t>(n + 2);
-  w.vfill = c.take<uint32_t>(n + 1);
   w.plist = c.take<int>(n + 1);
   w.bary = c.take<float>(3 * (size_t)n + 3);
   w.list0 = c.take<unsigned int>(n + 1);
@@ -773,10 +844,11 @@ extern "C" size_t gr_radius_neighbors_workspace_size(int64_t nq, int64_t ns, int
 /* Same search; `reuse_grid` != 0 promises that `ws` still holds the cell grid a previous call built for the SAME
  * (s_points, s_lengths, radius): the support cloud is not binned again (of the 13 searches of one pyramid only 5 use
  * a new support cloud / radius combination). */
-extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_points, const int64_t* q_lengths,
-                                          const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
-                                          int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
-                                          int reuse_grid, void* stream) {
+// count_zeroed: *out_max_count is already 0 in stream order (gr_radius_pyramid clears all its counters with one memset)
+static int radius_neighbors_impl(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                                 const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
+                                 int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
+                                 int reuse_grid, bool count_zeroed, void* stream) {
   if (batch <= 0 || nq < 0 || ns < 0 || !q_lengths || !s_lengths || !out_max_count || (out_idx && ld <= 0) ||
       nq >= (1ll << 31) || ns >= (1ll << 31) || (int64_t)batch * kCellsPerCloud >= (1ll << 31))
     return GR_ERR_BAD_ARG;
@@ -787,15 +859,19 @@ extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t ncell = (size_t)batch * kCellsPerCloud + 1;
 
-  GR_CHECK_CUDA(cudaMemsetAsync(out_max_count, 0, sizeof(int32_t), st));
+  if (!count_zeroed) GR_CHECK_CUDA(cudaMemsetAsync(out_max_count, 0, sizeof(int32_t), st));
+  const long long* q_len_inline = batch <= kInlineBatch ? reinterpret_cast<const long long*>(q_lengths) : nullptr;
   if (reuse_grid) {
-    // only the query offsets change (the bounding boxes this kernel resets are not needed once the grid exists)
-    GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, q_lengths, w.q_off, nullptr, nullptr, batch, w.bbox, w.scalars, 8));
-    GR_CHECK_LAUNCH("prep_offsets_kernel");
+    // only the query offsets change: the search kernel derives them from the lengths itself (small batches), else one
+    // prep launch (the bounding boxes that kernel resets are not needed once the grid exists)
+    if (!q_len_inline) {
+      GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, q_lengths, w.q_off, nullptr, nullptr, batch, w.bbox, w.scalars, 8));
+      GR_CHECK_LAUNCH("prep_offsets_kernel");
+    }
     if (nq > 0) {
       const float r2 = radius * radius;
       GR_CHECK_CUDA(launch_pdl(radius_search_kernel, dim3(ceil_div(nq, kSearchWarps)), dim3(kSearchWarps * 32), (size_t)(0), st, q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
-          (long long)ld, out_max_count));
+          (long long)ld, out_max_count, q_len_inline));
       GR_CHECK_LAUNCH("radius_search_kernel");
     }
     return GR_OK;
@@ -824,10 +900,18 @@ extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_
   if (nq > 0) {
     const float r2 = radius * radius;  // radius_neighbors_cpu.cpp:12 (host float multiply, one rounding)
     GR_CHECK_CUDA(launch_pdl(radius_search_kernel, dim3(ceil_div(nq, kSearchWarps)), dim3(kSearchWarps * 32), (size_t)(0), st, q_points, w.sorted, w.cell_cnt, w.grids, w.q_off, w.s_off, batch, r2, reinterpret_cast<long long*>(out_idx),
-        (long long)ld, out_max_count));
+        (long long)ld, out_max_count, (const long long*)nullptr));
     GR_CHECK_LAUNCH("radius_search_kernel");
   }
   return GR_OK;
+}
+
+extern "C" int gr_radius_neighbors_cached(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                                          const int64_t* s_lengths, int batch, int64_t nq, int64_t ns, float radius,
+                                          int64_t* out_idx, int64_t ld, int32_t* out_max_count, void* ws, size_t ws_bytes,
+                                          int reuse_grid, void* stream) {
+  return radius_neighbors_impl(q_points, s_points, q_lengths, s_lengths, batch, nq, ns, radius, out_idx, ld, out_max_count, ws, ws_bytes,
+                               reuse_grid, false, stream);
 }
 
 extern "C" int gr_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
@@ -859,11 +943,10 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
 
   GR_CHECK_CUDA(cudaMemsetAsync(w.tab_key, 0xff, w.tab_slots * sizeof(unsigned long long), st));
   GR_CHECK_CUDA(cudaMemsetAsync(w.tab_first, 0x7f, w.tab_slots * sizeof(int), st));
-  GR_CHECK_CUDA(cudaMemsetAsync(w.tab_cnt, 0, w.tab_slots * sizeof(uint32_t), st));
-  GR_CHECK_CUDA(cudaMemsetAsync(w.vfill, 0, ((size_t)n + 1) * sizeof(uint32_t), st));
-  // the scan below walks all n + 1 capacity slots of vcnt; only the first (number of voxels) + 1 are written by
-  // voxel_init_kernel -- clear the tail so that no kernel reads uninitialised memory (initcheck-clean)
-  GR_CHECK_CUDA(cudaMemsetAsync(w.vcnt, 0, ((size_t)n + 2) * sizeof(uint32_t), st));
+  // tab_cnt, vfill and vcnt in one memset (adjacent in the workspace).  vcnt: the scan below walks all n + 1 capacity slots;
+  // only the first (number of voxels) + 1 are written by voxel_init_kernel -- the tail is cleared so that no kernel reads
+  // uninitialised memory (initcheck-clean)
+  GR_CHECK_CUDA(cudaMemsetAsync(w.tab_cnt, 0, w.zero_bytes, st));
   GR_CHECK_CUDA(launch_pdl(prep_offsets_kernel, dim3(1), dim3(256), (size_t)(0), st, lengths, w.off, nullptr, nullptr, batch, w.bbox, w.scalars, 8));
   GR_CHECK_LAUNCH("prep_offsets_kernel");
   if (n > 0) {
@@ -899,6 +982,8 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
     GR_CHECK_CUDA(ensure_smem_attr(reinterpret_cast<const void*>(hash_order_replay_kernel<kReplayCluster>), (int)smem));
     static int cl_knob = -1;
     if (cl_knob < 0) { const char* e = getenv("GAUSSREG_REPLAY_CLUSTER"); cl_knob = e ? atoi(e) : kReplayCluster; }
+    static int scan_knob = -1;  // 1: the suffix scans of the global-memory phases run on every CTA of the cluster
+    if (scan_knob < 0) { const char* e = getenv("GAUSSREG_REPLAY_SCAN"); scan_knob = e ? atoi(e) : 1; }
     if (n > kReplaySmemElems && cl_knob > 1) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)batch * kReplayCluster);
@@ -911,10 +996,10 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
       cfg.attrs = attr; cfg.numAttrs = 1;
       GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hash_order_replay_kernel<kReplayCluster>, (const int*)w.off, batch,
                                        (const uint32_t*)w.fscan, (const unsigned long long*)w.vkey, (const float*)w.bary, w.list0,
-                                       w.list1, w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points));
+                                       w.list1, w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points, scan_knob));
     } else {
       GR_CHECK_CUDA(launch_pdl(hash_order_replay_kernel<1>, dim3(batch), dim3(kReplayThreads), (size_t)(smem), st, w.off, batch, w.fscan, w.vkey, w.bary, w.list0, w.list1,
-                                                                        w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points));
+                                                                        w.w, w.tmp, w.bkc, w.ft, w.cn, w.fill, out_points, 0));
     }
   }
   GR_CHECK_LAUNCH("hash_order_replay_kernel");
@@ -931,6 +1016,10 @@ extern "C" int gr_radius_pyramid(const float* const* stage_points, const int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool built[16] = {};
   for (int i = 0; i < 16; ++i) built[i] = (built_mask >> i) & 1u;  // grids an earlier call already left in stage_grid_ws
+  // the searches' counters: one memset when they are consecutive int32s (the usual (n_searches,) tensor), else one each
+  bool counters_contiguous = n_searches > 0 && searches[0].out_max_count != nullptr;
+  for (int j = 0; j < n_searches && counters_contiguous; ++j) counters_contiguous = searches[j].out_max_count == searches[0].out_max_count + j;
+  if (counters_contiguous) GR_CHECK_CUDA(cudaMemsetAsync(searches[0].out_max_count, 0, (size_t)n_searches * sizeof(int32_t), st));
   int waited = 0;
   for (int j = 0; j < n_searches; ++j) {
     const gr_pyramid_search& q = searches[j];
@@ -941,10 +1030,10 @@ extern "C" int gr_radius_pyramid(const float* const* stage_points, const int64_t
       if (stage_ready_events && stage_ready_events[waited])
         GR_CHECK_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(stage_ready_events[waited]), 0));
     }
-    const int rc = gr_radius_neighbors_cached(stage_points[q.query_stage], stage_points[q.support_stage], stage_lengths[q.query_stage],
-                                              stage_lengths[q.support_stage], batch, capacity, capacity, q.radius, q.out_idx, q.limit,
-                                              q.out_max_count, stage_grid_ws[q.support_stage], grid_ws_bytes,
-                                              built[q.support_stage] ? 1 : 0, stream);
+    const int rc = radius_neighbors_impl(stage_points[q.query_stage], stage_points[q.support_stage], stage_lengths[q.query_stage],
+                                         stage_lengths[q.support_stage], batch, capacity, capacity, q.radius, q.out_idx, q.limit,
+                                         q.out_max_count, stage_grid_ws[q.support_stage], grid_ws_bytes,
+                                         built[q.support_stage] ? 1 : 0, counters_contiguous, stream);
     if (rc != GR_OK) return rc;
     built[q.support_stage] = true;
   }

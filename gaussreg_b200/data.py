@@ -100,9 +100,22 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             specs.append(("subsampling", i + 1, i, r, neighbor_limits[i]))
             specs.append(("upsampling", i, i + 1, r * 2, neighbor_limits[i + 1]))
         r *= 2
-    tables = [torch.empty((n0, limit), dtype=torch.int64, device=dev) for (_, _, _, _, limit) in specs]
+    # ONE allocation for the 13 tables and one for the 5 cell grids (18 torch.empty calls were 0.1 ms of host time between the
+    # last subsample call and the searches, i.e. in front of the stage-size read the whole step waits for)
+    table_off, o = [], 0
+    for (_, _, _, _, limit) in specs:
+        table_off.append(o)
+        o += (n0 * limit + 31) // 32 * 32  # every table starts on a 256-byte boundary, as separate allocations would
+    table_pool = torch.empty((max(o, 1),), dtype=torch.int64, device=dev)
+    table_base = table_pool.data_ptr()
+
+    def table(j):  # (n0, limit) view of table j; built where it is needed (finalize), not in front of the searches
+        return table_pool[table_off[j]:table_off[j] + n0 * specs[j][4]].view(n0, specs[j][4])
+
     assert len(specs) == counts_dev.shape[0]
-    grids = [ext.radius_grid_workspace(points, lengths) for _ in range(num_stages)]  # sized by the upper bound n0
+    grid_bytes = (max(_lib.lib().gr_radius_neighbors_workspace_size(0, n0, nb), 256) + 255) // 256 * 256  # upper bound n0
+    grid_pool = torch.empty((num_stages * grid_bytes,), dtype=torch.uint8, device=dev)
+    grids = [grid_pool[i * grid_bytes:(i + 1) * grid_bytes] for i in range(num_stages)]
     # --- radius searches (limit-wide tables, widths come back later).  Stage i's support cloud is searched with radius
     # r_i by "neighbors" and "subsampling" of stage i and (r_i = 2 r_{i-1}) by "upsampling" of stage i-1: one cell grid per
     # stage serves all three (5 grids for 13 searches).
@@ -111,12 +124,13 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     def searches_native(stream, first=0, last=None, built_mask=0):
         # one C-ABI call for the searches [first, last) (gr_radius_pyramid): ~50 us of host time instead of ~0.6 ms for 13
         L = _lib.lib()
+        counts_base = counts_dev.data_ptr()
         sel = specs[first:last]
         arr = (_lib.PyramidSearch * len(sel))()
         for j, (key, qs, ss, rad, limit) in enumerate(sel, start=first):
             a = arr[j - first]
             a.query_stage, a.support_stage, a.radius, a.limit = qs, ss, float(rad), int(limit)
-            a.out_idx, a.out_max_count = tables[j].data_ptr(), counts_dev[j:j + 1].data_ptr()
+            a.out_idx, a.out_max_count = table_base + 8 * table_off[j], counts_base + 4 * j
         vp = ctypes.c_void_p * num_stages
         pts_arr = vp(*[p.data_ptr() for p in pts_cap])
         len_arr = vp(*[l.data_ptr() for l in len_dev])
@@ -138,7 +152,7 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             ev0 = torch.cuda.Event()
             ev0.record(side)
         main.wait_event(ev0)
-        early_out = early(features, pts_cap[0], tables[0])
+        early_out = early(features, pts_cap[0], table(0))
 
     def searches():
         if native:
@@ -152,7 +166,7 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
                 while waited < need:
                     waited += 1
                     side.wait_event(ready[waited])
-            ext.radius_neighbors_device(pts_cap[qs], pts_cap[ss], len_dev[qs], len_dev[ss], rad, limit, out=tables[j],
+            ext.radius_neighbors_device(pts_cap[qs], pts_cap[ss], len_dev[qs], len_dev[ss], rad, limit, out=table(j),
                                         grid_ws=grids[ss], reuse_grid=built[ss], max_count=counts_dev[j:j + 1])
             built[ss] = True
 
@@ -184,9 +198,9 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             torch.cuda.current_stream(dev).wait_event(done)  # the searches' tables become visible to the caller's stream
         else:
             widths = counts_dev.cpu().tolist()  # sync 2
-        for t, w, (key, qs, _, _, limit) in zip(tables, widths, specs):
+        for j, (w, (key, qs, _, _, limit)) in enumerate(zip(widths, specs)):
             w = min(int(w), limit)
-            t = t[: sizes[qs]]
+            t = table(j)[: sizes[qs]]
             list.append(out[key], t[:, :w] if w == t.shape[1] else t[:, :w].contiguous())
         for key in ("neighbors", "subsampling", "upsampling"):
             out[key]._finalize = None
