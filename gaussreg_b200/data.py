@@ -49,7 +49,7 @@ class LazyTables(list):
 
 
 def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, lazy=True, early=None,
-                               features=None):
+                               features=None, after_chain=None):
     """utils/data.py:13-77 on the GPU.  Returns the reference's dict plus `lengths_host` (python ints per stage and
     cloud, read in the same device->host transfer as the stage sizes, so that the model needs no sync of its own).
     With `lazy` (default) the three table lists are LazyTables: same contents, trimmed on first access.
@@ -89,6 +89,8 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             ev.record(main)
             ready.append(ev)
     sizes_dev = torch.cat(totals + len_dev) if totals else torch.cat(len_dev)
+    if after_chain is not None:
+        after_chain()  # host work of the caller that only has to happen before the network runs (the feature upload)
 
     # --- buffers (all on the caller's stream / allocator pool, every stage sized by the upper bound n0): allocated AFTER the
     # subsampling chain has been queued, so that the GPU is already working while the host does this (0.1 ms per pair)
@@ -233,35 +235,41 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
     points_list = collated.pop("ref_points") + collated.pop("src_points")
     lengths = torch.LongTensor([p.shape[0] for p in points_list])
     main = torch.cuda.current_stream(dev)
-    feats_ready = None
-    if precompute_data and (early is None or batch_size != 1) and not any(t.is_cuda for t in feat_list):
-        # the points go first (the pyramid starts from them); the features are first read by the backbone, so their upload
-        # runs on a copy stream underneath the subsampling chain.  The copy stream starts where the caller's stream is NOW
-        # (a recycled buffer's previous readers are ordered before it).
+    late = precompute_data and (early is None or batch_size != 1) and not any(t.is_cuda for t in feat_list)
+    up = {}
+
+    def upload_features():
+        # The features are first read by the backbone: their upload runs on a copy stream underneath the subsampling chain,
+        # and is issued only after that chain has been queued (the points go first, the pyramid starts from them).  The copy
+        # stream starts where the caller's stream was at the beginning of this call (a recycled buffer's previous readers
+        # are ordered before it).
         cs = ext.copy_stream(dev)
-        start = torch.cuda.Event()
-        start.record(main)
         cs.wait_event(start)
         with torch.cuda.stream(cs):
-            feats = ext.h2d_rows(feat_list, dev)
-            feats_ready = torch.cuda.Event()
-            feats_ready.record(cs)
-        feats.record_stream(main)
+            up["feats"] = ext.h2d_rows(feat_list, dev)
+            up["ready"] = torch.cuda.Event()
+            up["ready"].record(cs)
+        up["feats"].record_stream(main)
+
+    if late:
+        start = torch.cuda.Event()
+        start.record(main)
     else:
-        feats = ext.h2d_rows(feat_list, dev)
+        up["feats"] = ext.h2d_rows(feat_list, dev)
     points = ext.h2d_rows(points_list, dev)
     if batch_size == 1:
         for key, value in collated.items():
             collated[key] = value[0]
-    collated["features"] = feats
     if precompute_data:
         collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits,
-                                                   early=early if batch_size == 1 else None, features=feats))
-        if feats_ready is not None:
-            main.wait_event(feats_ready)  # long complete: the host has just waited for the subsampling chain
+                                                   early=early if batch_size == 1 else None, features=up.get("feats"),
+                                                   after_chain=upload_features if late else None))
+        if late:
+            main.wait_event(up["ready"])  # long complete: the host has just waited for the subsampling chain
     else:
         collated["points"] = points
         collated["lengths"] = lengths.to(dev)
+    collated["features"] = up["feats"]
     collated["batch_size"] = batch_size
     return collated
 
