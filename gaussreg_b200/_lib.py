@@ -74,6 +74,7 @@ _SIGNATURES = {
     "gr_last_error": (ctypes.c_char_p, []),
     "gr_launch_count": (_i64, []),
     "gr_grid_subsample_workspace_size": (_sz, [_i64, _i32]),
+    "gr_grid_subsample_chain": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gr_grid_subsample": (_i32, [_vp, _vp, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gr_radius_neighbors_workspace_size": (_sz, [_i64, _i64, _i32]),
     "gr_radius_neighbors": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),

@@ -15,6 +15,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -1003,6 +1005,48 @@ extern "C" int gr_grid_subsample(const float* points, const int64_t* lengths, in
     }
   }
   GR_CHECK_LAUNCH("hash_order_replay_kernel");
+  return GR_OK;
+}
+
+/* G1 chain: every subsampling stage of a pyramid in one call (see include/gaussreg_b200.h). */
+extern "C" int gr_grid_subsample_chain(const float* points, const int64_t* lengths, int batch, int64_t n_points,
+                                       const float* voxel_sizes, int n_sub, float* out_points, int64_t* out_lengths,
+                                       int64_t* out_totals, void* ws, size_t ws_bytes, void** stage_events, void* stream) {
+  if (n_sub < 0 || n_sub > 15 || batch <= 0 || n_points < 0 || !lengths || (n_sub > 0 && (!voxel_sizes || !out_lengths || !out_totals)))
+    return GR_ERR_BAD_ARG;
+  // events per (thread, device), created once: a later cudaStreamWaitEvent refers to the record that precedes it, so the
+  // handles can be re-recorded by the next chain while earlier waits are still pending
+  struct Pool { int dev; cudaEvent_t ev[16]; };
+  static thread_local std::vector<Pool> pools;
+  Pool* pool = nullptr;
+  if (stage_events) {
+    int dev = 0;
+    GR_CHECK_CUDA(cudaGetDevice(&dev));
+    for (Pool& p : pools) if (p.dev == dev) pool = &p;
+    if (!pool) {
+      Pool p;
+      p.dev = dev;
+      for (int i = 0; i < 16; ++i) GR_CHECK_CUDA(cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming));
+      pools.push_back(p);
+      pool = &pools.back();
+    }
+    stage_events[0] = nullptr;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* in_pts = points;
+  const int64_t* in_len = lengths;
+  for (int i = 0; i < n_sub; ++i) {
+    float* o_pts = out_points + (size_t)i * (size_t)n_points * 3;
+    int64_t* o_len = out_lengths + (size_t)i * batch;
+    const int rc = gr_grid_subsample(in_pts, in_len, batch, n_points, voxel_sizes[i], o_pts, o_len, out_totals + i, ws, ws_bytes, stream);
+    if (rc != GR_OK) return rc;
+    if (stage_events) {
+      GR_CHECK_CUDA(cudaEventRecord(pool->ev[i + 1], st));
+      stage_events[i + 1] = pool->ev[i + 1];
+    }
+    in_pts = o_pts;
+    in_len = o_len;
+  }
   return GR_OK;
 }
 

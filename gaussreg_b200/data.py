@@ -69,14 +69,22 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
 
     # the searches' row-count maxima accumulate into this (zero-filled BEFORE the helper stream forks off the caller's)
     counts_dev = torch.zeros((3 * num_stages - 2,), dtype=torch.int32, device=dev)
-    # GAUSSREG_CHAIN_PRIORITY=1 (opt-in): the chain runs on a high-priority stream of its own (ext.chain_stream), so that its
-    # small kernels go ahead of the wide search kernels of the helper stream instead of queueing behind their CTAs.  Its
-    # outputs are allocated HERE, on the caller's stream / allocator pool, before the other streams fork off.  Measured on
-    # B200: the chain itself gets faster (0.70 -> 0.57 ms, the two small-stage calls 0.17 / 0.19 -> 0.09 / 0.09 ms), but
-    # every launch into the third stream costs the host ~1 us more and the deprioritised searches finish 0.25 ms later --
-    # this phase is bound by the host's launch rate, and the step got slower (6.82 vs 6.69 ms).  Off by default.
+    # GAUSSREG_CHAIN_PRIORITY=1: the subsampling chain runs on a high-priority stream of its own (ext.chain_stream), so that
+    # its small kernels go ahead of the wide search kernels of the helper stream instead of queueing behind their CTAs (the
+    # two small-stage calls: 0.17 / 0.19 ms next to the searches, 0.09 / 0.09 ms with priority).  Every buffer the chain
+    # writes is allocated HERE, on the caller's stream / allocator pool, before the other streams fork off.
+    native = os.environ.get("GAUSSREG_PYRAMID_NATIVE", "1") != "0"
     chain = ext.chain_stream(dev) if side is not None and os.environ.get("GAUSSREG_CHAIN_PRIORITY", "0") == "1" else None
-    chain_out = [ext.grid_subsample_outputs(n0, nb, dev) for _ in range(1, num_stages)] if chain is not None else None
+    native_chain = native and side is not None and num_stages > 1 and os.environ.get("GAUSSREG_CHAIN_NATIVE", "1") != "0"
+    S = num_stages - 1
+    if native_chain:
+        # two allocations for all outputs of the chain: the stage points, and [totals | lengths of every stage] -- which
+        # is exactly the vector the host reads below (no torch.cat)
+        fpool = torch.empty((S, n0, 3), dtype=torch.float32, device=dev)
+        ipool = torch.empty((S + num_stages * nb,), dtype=torch.int64, device=dev)
+        ipool[S:S + nb].copy_(lengths, non_blocking=True)
+    elif chain is not None:
+        chain_out = [ext.grid_subsample_outputs(n0, nb, dev) for _ in range(1, num_stages)]
     if side is not None:
         # the helper streams start where the caller's stream is NOW: inputs are ready, and every kernel that may still
         # read a recycled buffer (the previous pair's forward) has been ordered before it
@@ -87,22 +95,45 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             chain.wait_event(start)
 
     # --- grid subsampling chain, device-side lengths, capacity-sized outputs
+    sizes_dev = None
     pts_cap, len_dev, totals, ready = [points], [lengths], [], [None]
     with torch.cuda.stream(chain if chain is not None else main):
-        for i in range(1, num_stages):
-            voxel_size_i = voxel_size * (2 ** i)
-            out, out_len, out_total = ext.grid_subsample_device(pts_cap[-1], len_dev[-1], voxel_size_i, n_points=n0,
-                                                                out=chain_out[i - 1] if chain is not None else None)
-            pts_cap.append(out)
-            len_dev.append(out_len)
-            totals.append(out_total)
-            if side is not None:
-                ev = torch.cuda.Event()
-                ev.record(chain if chain is not None else main)
-                ready.append(ev)
-    if chain is not None and ready[-1] is not None:
-        main.wait_event(ready[-1])  # the caller's stream continues behind the chain
-    sizes_dev = torch.cat(totals + len_dev) if totals else torch.cat(len_dev)
+        if native_chain:
+            # ONE C-ABI call for the whole chain (gr_grid_subsample_chain); the per-stage events come back as raw handles
+            # for gr_radius_pyramid
+            L = _lib.lib()
+            vox = (ctypes.c_float * S)(*[voxel_size * (2 ** i) for i in range(1, num_stages)])
+            ev_out = (ctypes.c_void_p * num_stages)()
+            ws = ext._workspace(L.gr_grid_subsample_workspace_size(n0, nb), dev)
+            st = L.gr_grid_subsample_chain(points.data_ptr(), lengths.data_ptr(), nb, n0, vox, S, fpool.data_ptr(),
+                                           ipool.data_ptr() + 8 * (S + nb), ipool.data_ptr(), ws.data_ptr(), ws.numel(), ev_out,
+                                           ext._stream())
+            _lib.check(st, "grid_subsample_chain")
+            for i in range(S):
+                pts_cap.append(fpool[i])
+                len_dev.append(ipool[S + nb * (i + 1):S + nb * (i + 2)])
+                totals.append(None)
+                ready.append(ev_out[i + 1])
+            sizes_dev = ipool
+        else:
+            for i in range(1, num_stages):
+                voxel_size_i = voxel_size * (2 ** i)
+                out, out_len, out_total = ext.grid_subsample_device(pts_cap[-1], len_dev[-1], voxel_size_i, n_points=n0,
+                                                                    out=chain_out[i - 1] if chain is not None else None)
+                pts_cap.append(out)
+                len_dev.append(out_len)
+                totals.append(out_total)
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(chain if chain is not None else main)
+                    ready.append(ev)
+        if chain is not None:
+            chain_done = torch.cuda.Event()
+            chain_done.record(chain)
+    if chain is not None:
+        main.wait_event(chain_done)  # the caller's stream continues behind the chain
+    if sizes_dev is None:
+        sizes_dev = torch.cat(totals + len_dev) if totals else torch.cat(len_dev)
     if after_chain is not None:
         after_chain()  # host work of the caller that only has to happen before the network runs (the feature upload)
 
@@ -151,12 +182,11 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         pts_arr = vp(*[p.data_ptr() for p in pts_cap])
         len_arr = vp(*[l.data_ptr() for l in len_dev])
         ws_arr = vp(*[g.data_ptr() for g in grids])
-        ev_arr = vp(*[(e.cuda_event if e is not None else None) for e in ready]) if side is not None else None
+        ev_arr = vp(*[(e if e is None or isinstance(e, int) else e.cuda_event) for e in ready]) if side is not None else None
         st = L.gr_radius_pyramid(pts_arr, len_arr, num_stages, nb, n0, ws_arr, min(g.numel() for g in grids), ev_arr, arr, len(sel),
                                  built_mask, stream.cuda_stream)
         _lib.check(st, "radius_pyramid")
 
-    native = os.environ.get("GAUSSREG_PYRAMID_NATIVE", "1") != "0"
     early_out = None
     if early is not None and native and side is not None and features is not None and specs[0][:3] == ("neighbors", 0, 0):
         # Stage 0 needs nothing from the subsampling chain: its neighbour table first, then the caller's stage-0 work

@@ -56,6 +56,16 @@ int gr_grid_subsample(const float* points, const int64_t* lengths, int batch, in
                       float* out_points, int64_t* out_lengths, int64_t* out_total, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* The whole subsampling chain of a pyramid (utils/data.py:24-31: stage i = grid_subsampling(stage i-1, voxel_sizes[i-1]))
+ * in ONE call: n_sub dependent gr_grid_subsample calls on `stream`, every stage sized by the capacity n_points.
+ *   out_points  (n_sub, n_points, 3) f32;  out_lengths (n_sub, batch) i64;  out_totals (n_sub) i64  -- all DEVICE
+ *   stage_events (n_sub + 1 entries, may be NULL): [i] receives a cudaEvent_t recorded on `stream` behind stage i
+ *   (i = 1..n_sub; [0] = NULL), owned by the library and valid until this thread's next chain call -- the
+ *   `stage_ready_events` of gr_radius_pyramid. */
+int gr_grid_subsample_chain(const float* points, const int64_t* lengths, int batch, int64_t n_points, const float* voxel_sizes,
+                            int n_sub, float* out_points, int64_t* out_lengths, int64_t* out_totals, void* ws, size_t ws_bytes,
+                            void** stage_events, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * G2  fixed-radius neighbour search.
  * Replaces geotransformer.ext.radius_neighbors
