@@ -218,6 +218,9 @@ class OpProfiler:
                 self.t1_kind = "f16" if name.endswith("_f16") else "tf32"
             elif name == "gr_structure_embedding_tabulated":  # (d_idx, a_idx, rows, angle_k, table, sigma_a, div, hidden, ...)
                 work = 4.0 * a[2] * (a[7] + 1 + a[3])  # HBM bytes: the (rows, hidden) embedding written, the indices read
+            elif name == "gr_structure_embedding_points":  # (points, N, sigma_d, sigma_a, angle_k, table, div, hidden, ...): + indices
+                work = 4.0 * a[1] * a[1] * (a[7] + 1 + a[4])
+                key = "gr_structure_embedding_tabulated"
             # algorithmic HBM bytes of the HBM-class ops (SURVEY.md section 8(d) formulas)
             elif name in ("gr_radius_neighbors", "gr_radius_neighbors_cached"):  # (q, s, ql, sl, batch, nq, ns, radius, out, ld, ...)
                 work = 12.0 * (a[5] + a[6]) + 8.0 * a[5] * a[9]

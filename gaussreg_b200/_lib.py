@@ -117,6 +117,7 @@ _SIGNATURES = {
     "gr_structure_embedding_table_floats": (_i64, [_i32, _f32]),
     "gr_structure_embedding_build_table": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "gr_structure_embedding_tabulated": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gr_structure_embedding_points": (_i32, [_vp, _i32, _f32, _f32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gr_rpe_attention_probs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_rpe_attention_probs_ld": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "gr_softmax_rows": (_i32, [_vp, _i64, _i32, _vp]),

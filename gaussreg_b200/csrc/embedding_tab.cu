@@ -279,3 +279,16 @@ extern "C" int gr_structure_embedding_tabulated(const float* d_idx, const float*
   GR_CHECK_LAUNCH("structure_embedding_table_kernel");
   return GR_OK;
 }
+
+/* T1 from the superpoint coordinates in ONE call: gr_embedding_indices followed by gr_structure_embedding_tabulated (the two
+ * wrappers cost the host ~30 us between them, during which the GPU -- idle since the stage-size read -- has nothing to do).
+ * d_idx (N,N), a_idx (N,N,angle_k), knn (N,angle_k) are the intermediate buffers of gr_embedding_indices. */
+extern "C" int gr_structure_embedding_points(const float* points, int N, float sigma_d, float sigma_a, int angle_k, const float* table,
+                                             const float* div_term, int hidden_dim, const float* W_d, const float* b_d,
+                                             const float* W_a, const float* b_a, float* d_idx, float* a_idx, int32_t* knn,
+                                             float* out, void* stream) {
+  const int rc = gr_embedding_indices(points, N, sigma_d, sigma_a, angle_k, d_idx, a_idx, knn, stream);
+  if (rc != GR_OK) return rc;
+  return gr_structure_embedding_tabulated(d_idx, a_idx, (int64_t)N * N, angle_k, table, sigma_a, div_term, hidden_dim, W_d, b_d, W_a,
+                                          b_a, out, stream);
+}

@@ -246,8 +246,10 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             widths = counts_dev.cpu().tolist()  # sync 2
         for j, (w, (key, qs, _, _, limit)) in enumerate(zip(widths, specs)):
             w = min(int(w), limit)
-            t = table(j)[: sizes[qs]]
-            list.append(out[key], t[:, :w] if w == t.shape[1] else t[:, :w].contiguous())
+            # rows [0, size of the query stage), columns [0, w) of table j: one view op per table (this loop runs between
+            # the embedding's launch and the backbone call, where the host is the bottleneck)
+            t = torch.as_strided(table_pool, (sizes[qs], w), (limit, 1), table_off[j])
+            list.append(out[key], t if w == limit else t.contiguous())
         for key in ("neighbors", "subsampling", "upsampling"):
             out[key]._finalize = None
 

@@ -62,16 +62,18 @@ class GeoTransformer(nn.Module):
             ref_length_c, ref_length_f, ref_length = int(lens[0, 0]), int(lens[1, 0]), int(lens[2, 0])
         points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
         ref_points_c, src_points_c = points_c[:ref_length_c], points_c[ref_length_c:]
+
+        # 3a. geometric structure embedding (geotransformer.py:57-72) depends on the superpoint coordinates only: it is
+        # queued BEFORE the backbone (and before any other host work of this function: the GPU is idle since the stage-size
+        # read), so that the GPU is busy while the host reads the neighbour-table widths (data.LazyTables) and prepares the
+        # backbone call
+        ref_emb = self.transformer.embedding(ref_points_c)
+        src_emb = self.transformer.embedding(src_points_c)
+
         ref_points_f, src_points_f = points_f[:ref_length_f], points_f[ref_length_f:]
         out["ref_points_c"], out["src_points_c"] = ref_points_c, src_points_c
         out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
         out["ref_points"], out["src_points"] = points[:ref_length], points[ref_length:]
-
-        # 3a. geometric structure embedding (geotransformer.py:57-72) depends on the superpoint coordinates only: it is
-        # queued BEFORE the backbone, so that the GPU is busy while the host reads the neighbour-table widths
-        # (data.LazyTables) and prepares the backbone call
-        ref_emb = self.transformer.embedding(ref_points_c)
-        src_emb = self.transformer.embedding(src_points_c)
 
         # 2. KPConv FPN (model.py:129-132)
         feats_list = self.backbone(feats, data_dict)

@@ -60,6 +60,12 @@ class GeometricStructureEmbedding(nn.Module):
         N = pts.shape[0]
         C = self.embedding.d_model
         k = self.angle_k
+        if self.use_fused and C % 64 == 0 and k <= 3 and ops._t1_mode() == "table":
+            # indices + tabulated embedding in one C-ABI call (csrc/embedding_tab.cu)
+            out = ops.structure_embedding_points(pts, self.embedding.div_term, self.proj_d.weight, self.proj_d.bias,
+                                                 self.proj_a.weight, self.proj_a.bias, self.sigma_d, self.sigma_a, k)
+            if out is not None:
+                return out.unsqueeze(0) if batched else out
         d_idx, a_idx = self.get_embedding_indices(pts)
         if self.use_fused and C % 64 == 0 and k <= 3 and ops._t1_mode() == "table":
             # proj(sinusoid(x)) tabulated per channel: no projection in the hot path (csrc/embedding_tab.cu)

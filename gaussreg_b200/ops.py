@@ -366,17 +366,18 @@ def kpconv_fpn(backbone, feats, data_dict, start_block=0):
     P = _lib.Pyramid()
     pts, nb, sub, up = data_dict["points"], data_dict["neighbors"], data_dict["subsampling"], data_dict["upsampling"]
     keep = []
+    fields = [(tabs, len(tabs), getattr(P, key), getattr(P, key + "_w"), getattr(P, key + "_ld"))
+              for key, tabs in (("neighbors", nb), ("subsampling", sub), ("upsampling", up))]
+    P_points, P_n = P.points, P.n_points
     for s in range(_lib.FPN_STAGES):
         pt = _req(pts[s])
         keep.append(pt)
-        P.points[s], P.n_points[s] = pt.data_ptr(), pt.shape[0]
-        for key, tabs in (("neighbors", nb), ("subsampling", sub), ("upsampling", up)):
-            if s < len(tabs):
+        P_points[s], P_n[s] = pt.data_ptr(), pt.shape[0]
+        for tabs, n_tabs, f_ptr, f_w, f_ld in fields:
+            if s < n_tabs:
                 t = tabs[s]
                 assert t.dtype == torch.int64 and t.stride(1) == 1
-                getattr(P, key)[s] = t.data_ptr()
-                getattr(P, key + "_w")[s] = t.shape[1]
-                getattr(P, key + "_ld")[s] = t.stride(0)
+                f_ptr[s], f_w[s], f_ld[s] = t.data_ptr(), t.shape[1], t.stride(0)
     dev = feats.device
     n = [p.shape[0] for p in pts]
     outs = [torch.empty((n[1], W.decoder2.out_channels), dtype=_F32, device=dev),
@@ -591,6 +592,31 @@ def structure_embedding_tabulated(d_idx, a_idx, div_term, proj_d_w, proj_d_b, pr
     if st == -3:  # GR_ERR_CAPACITY: this sigma_a's table does not fit one SM's shared memory
         return None
     _lib.check(st, "structure_embedding_tabulated")
+    return out
+
+
+def structure_embedding_points(points, div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b, sigma_d, sigma_a, angle_k):
+    """geotransformer.py:26-72 from the superpoint coordinates in one C-ABI call (indices + tabulated embedding); None when
+    the table cannot be used."""
+    points = _req(points)
+    N = points.shape[0]
+    C = proj_d_w.shape[0]
+    if not (proj_d_w.is_contiguous() and proj_a_w.is_contiguous()):
+        return None
+    tab = embedding_table(div_term, proj_d_w, proj_d_b, proj_a_w, proj_a_b, sigma_a)
+    if tab is None:
+        return None
+    dev = points.device
+    scratch = torch.empty((N * N * (1 + angle_k) + N * angle_k,), dtype=_F32, device=dev)  # d_idx | a_idx | knn (int32)
+    out = torch.empty((N, N, C), dtype=_F32, device=dev)
+    p0 = scratch.data_ptr()
+    st = _lib.lib().gr_structure_embedding_points(points.data_ptr(), N, float(sigma_d), float(sigma_a), angle_k, tab.data_ptr(),
+                                                  div_term.data_ptr(), C, proj_d_w.data_ptr(), proj_d_b.data_ptr(),
+                                                  proj_a_w.data_ptr(), proj_a_b.data_ptr(), p0, p0 + 4 * N * N,
+                                                  p0 + 4 * N * N * (1 + angle_k), out.data_ptr(), _stream())
+    if st == -3:  # GR_ERR_CAPACITY: this sigma_a's table does not fit one SM's shared memory
+        return None
+    _lib.check(st, "structure_embedding_points")
     return out
 
 

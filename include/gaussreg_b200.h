@@ -338,6 +338,11 @@ int gr_structure_embedding_tabulated(const float* d_idx, const float* a_idx, int
                                      float sigma_a, const float* div_term, int hidden_dim, const float* W_d, const float* b_d,
                                      const float* W_a, const float* b_a, float* out, void* stream);
 
+/* gr_embedding_indices + gr_structure_embedding_tabulated in one call (d_idx, a_idx, knn: the intermediate buffers). */
+int gr_structure_embedding_points(const float* points, int N, float sigma_d, float sigma_a, int angle_k, const float* table,
+                                  const float* div_term, int hidden_dim, const float* W_d, const float* b_d, const float* W_a,
+                                  const float* b_a, float* d_idx, float* a_idx, int32_t* knn, float* out, void* stream);
+
 /* T2  RPE attention probabilities with the p-term reassociated (rpe_transformer.py:50-66), row softmax
  * (vanilla_transformer.py:66), F.normalize (model.py:143-144). */
 int gr_rpe_attention_probs(const float* q, const float* k, const float* U, const float* qb, const float* emb, int N, int C,

@@ -60,3 +60,17 @@ def test_module_key_cache_follows_parameter_changes():
     m[0].weight = nn.Parameter(torch.zeros(4, 4))  # manual surgery needs the documented invalidation
     ops.invalidate_weight_caches(m)
     assert m[0].weight.data_ptr() in [d for _, d in ops._module_key(m)]
+
+
+def test_stacked_rows_detects_adjacent_views():
+    """Host logic: row-wise ops run once on both clouds when they are adjacent views of one matrix."""
+    import torch
+
+    from gaussreg_b200 import ops
+    x = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    both = ops.stacked_rows(x[:3], x[3:])
+    assert both is not None and both.shape == (10, 4) and both.data_ptr() == x.data_ptr() and torch.equal(both, x)
+    assert ops.stacked_rows(x[:3].clone(), x[3:]) is None      # different storage
+    assert ops.stacked_rows(x[:3], x[4:]) is None              # a gap between them
+    assert ops.stacked_rows(x[:3, :2], x[3:, :2]) is None      # not contiguous
+    assert ops.stacked_rows(x[:3], x[3:].double()) is None     # dtype
