@@ -74,3 +74,16 @@ def test_stacked_rows_detects_adjacent_views():
     assert ops.stacked_rows(x[:3], x[4:]) is None              # a gap between them
     assert ops.stacked_rows(x[:3, :2], x[3:, :2]) is None      # not contiguous
     assert ops.stacked_rows(x[:3], x[3:].double()) is None     # dtype
+
+
+def test_argument_checks_need_no_device():
+    """The C ABI rejects malformed calls before touching CUDA (GR_ERR_BAD_ARG = -1): checked here without a GPU."""
+    L = _lib.lib()
+    assert L.gr_grid_subsample_chain(None, None, 2, 100, None, 4, None, None, None, None, 0, None, None) == -1
+    assert L.gr_grid_subsample_chain(None, None, 0, 100, None, 0, None, None, None, None, 0, None, None) == -1
+    # angle_k outside 1..3, hidden_dim not a multiple of 64, sigma_a <= 0
+    for k, C, sa in ((0, 256, 15.0), (4, 256, 15.0), (3, 200, 15.0), (3, 256, 0.0)):
+        assert L.gr_structure_embedding_tabulated(None, None, 10, k, None, sa, None, C, None, None, None, None, None, None) == -1
+    # zero rows: nothing to do
+    assert L.gr_structure_embedding_tabulated(None, None, 0, 3, None, 15.0, None, 256, None, None, None, None, None, None) == 0
+    assert L.gr_structure_embedding_build_table(None, 256, None, None, None, None, 15.0, None, None) == -1
