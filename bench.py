@@ -454,7 +454,9 @@ def table_kernel_entry(ms, hbm_bytes, launches, peaks):
             "ms": ms, "launches": launches, "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
             "bound": "shared-memory bandwidth", "lds_TBps": lds_tbs, "lds_peak_TBps_nominal": 148 * 128 * 1.965e9 / 1e12,
             "frac_of_lds_peak": lds_tbs / (148 * 128 * 1.965e9 / 1e12),
-            "replaces": "2 N^2 (1+k) 256^2 FLOPs of tcgen05 projections (structure_embedding_f16_kernel, GAUSSREG_T1=tc)"}
+            "replaces": "2 N^2 (1+k) 256^2 FLOPs of tcgen05 projections (structure_embedding_f16_kernel, GAUSSREG_T1=tc)",
+            "note": "ms is the C-ABI call gr_structure_embedding_points: it includes the two index kernels (pairwise distances / "
+                    "3-NN / angles, ~0.02 ms per cloud) in front of the table kernel"}
 
 
 def config4_sharded(model, rank, world, dev, pairs_per_rank=128, distinct=8):
